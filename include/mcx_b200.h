@@ -1,0 +1,196 @@
+/*
+ * mcx_b200.h -- C ABI of the B200-native lattice sampling library (libmcx_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of MonteCarloX.jl / SpinSystems: checkerboard
+ * Metropolis / Glauber / heat-bath sweeps over Ising and Blume-Capel lattices, batched over
+ * chains and parallel-tempering replicas, with multicanonical / Wang-Landau table updates.
+ *
+ * The reference (Julia, /root/reference) has no FFI: its extension mechanism is multiple
+ * dispatch.  Each entry point below names the reference method(s) a Julia
+ * shim would forward to it (julia/MonteCarloXB200.jl shows the ccall side; INTEGRATION.md the
+ * wiring).  Plain pointers and sizes only; no torch / CUDA types in signatures (a CUDA stream is
+ * passed as void*).
+ *
+ * Conventions
+ *  - every function returns an int32 status (MCX_OK == 0); mcx_last_error() gives the message
+ *    (thread-local).  The Julia shim maps MCX_ERR_ARGUMENT -> ArgumentError, MCX_ERR_BOUNDS ->
+ *    BoundsError, MCX_ERR_STATE -> AssertionError, the rest -> ErrorException.
+ *  - the library owns device memory behind opaque handles; the caller owns every host pointer and
+ *    keeps it alive for the duration of the call.
+ *  - handles are not thread-safe; distinct handles are.  One host thread/process per GPU.
+ *  - work is enqueued on the context's stream; calls that return host data synchronise it.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    MCX_ERR_CUDA.
+ *
+ * Site order of host spin buffers is the reference's: i = x + Lx*(y + Ly*z), x fastest
+ * (SpinSystems/src/ising.jl:444-456), values -1/+1 (Ising) or -1/0/+1 (Blume-Capel), int8.
+ *
+ * RNG layout v1 (bit-exactness contract): Philox4x32-10,
+ *   key = (seed lo32, seed hi32)
+ *   ctr = (slot >> 3, t lo32, (t >> 32 & 0xffff) | plane << 16 | tag << 24, chain id)
+ *   16-bit lane of a slot = (out[(slot & 7) >> 1] >> 16 * (slot & 1)) & 0xffff
+ *   draw n of a position: high half from plane 2n, low half from plane 2n+1;
+ *   rand(Float64) = (hi << 16 | lo) * 2^-32, rand(Bool) = hi >> 15.
+ *   tag SWEEP(0): t = 2*sweep + colour, slot = row*(Lx/2) + (x >> 1), row = y + Ly*z,
+ *   colour = (x + y + z) & 1.  tag EXCHANGE(1), INIT(2), FLAT(3): see DESIGN.md.
+ */
+#ifndef MCX_B200_H
+#define MCX_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCX_ABI_VERSION 1
+
+enum mcx_status {
+    MCX_OK = 0,
+    MCX_ERR_ARGUMENT = 1,
+    MCX_ERR_BOUNDS = 2,
+    MCX_ERR_CUDA = 3,
+    MCX_ERR_STATE = 4,
+    MCX_ERR_UNSUPPORTED = 5
+};
+enum mcx_model { MCX_ISING = 0, MCX_BLUME_CAPEL = 1 };
+enum mcx_rule { MCX_METROPOLIS = 0, MCX_GLAUBER = 1, MCX_HEATBATH = 2 };
+enum mcx_storage { MCX_STORAGE_INT8 = 0, MCX_STORAGE_BIT = 1 };
+enum mcx_init_mode { MCX_INIT_UP = 0, MCX_INIT_DOWN = 1, MCX_INIT_ZERO = 2, MCX_INIT_RANDOM = 3 };
+enum mcx_flat_kind { MCX_FLAT_MUCA = 0, MCX_FLAT_WANG_LANDAU = 1 };
+enum mcx_flat_observable { MCX_OBS_ENERGY = 0, MCX_OBS_SPIN2_WITH_PAIR_BOLTZMANN = 1 };
+
+typedef struct mcx_ctx mcx_ctx;
+typedef struct mcx_lattice mcx_lattice;
+typedef struct mcx_pt mcx_pt;
+typedef struct mcx_flat mcx_flat;
+
+/* ---- library / context ------------------------------------------------------------------ */
+int32_t     mcx_abi_version(void);
+const char *mcx_last_error(void);
+
+/* Binds a context to a CUDA device.  `stream` is a cudaStream_t to enqueue on (NULL: the library
+ * creates its own non-blocking stream).  Replaces nothing in the reference; plays the role of
+ * parallel_backends.jl:86 `init(:mode)` for a GPU backend. */
+int32_t mcx_ctx_create(int32_t device, void *stream, mcx_ctx **out);
+int32_t mcx_ctx_destroy(mcx_ctx *ctx);                   /* parallel_backends.jl:104 finalize! */
+int32_t mcx_ctx_set_stream(mcx_ctx *ctx, void *stream);
+int32_t mcx_ctx_sync(mcx_ctx *ctx);
+int32_t mcx_ctx_info(mcx_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
+                     uint64_t *total_mem_bytes);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int32_t mcx_ctx_launch_count(mcx_ctx *ctx, uint64_t *count);
+
+/* ---- lattice: SpinSystems Ising / BlumeCapel constructors ---------------------------------
+ * mcx_lattice_create  <- Ising(dims) ising.jl:413, IsingLatticeOptim(Lx,Ly) ising.jl:441,
+ *                        BlumeCapel(dims) blume_capel.jl:500; `nchains` independent lattices
+ *                        (ParallelChains, parallel_chains.jl:14).  Periodic, every dim even, >= 4.
+ *                        All chains start all-up like the reference constructors. */
+int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int32_t *dims,
+                           int32_t nchains, int32_t storage, mcx_lattice **out);
+int32_t mcx_lattice_destroy(mcx_lattice *lat);
+/* couplings used to form energies from the integer sums: E = -J*pair - h*spin + D*spin2
+ * (ising.jl:175-178, blume_capel.jl:222-224).  The update rule itself sees only the tables. */
+int32_t mcx_lattice_set_couplings(mcx_lattice *lat, double J, double h, double D);
+/* RNG chain id of local chain c is first_chain_id + c (global slot id when sharded over GPUs) */
+int32_t mcx_lattice_set_first_chain_id(mcx_lattice *lat, uint32_t first_chain_id);
+/* sys.spins .= host (any caller-side init!), then _recompute_cached! (ising.jl:500-504).
+ * host_spins is [nchains][N]. */
+int32_t mcx_lattice_upload(mcx_lattice *lat, const int8_t *host_spins);
+int32_t mcx_lattice_download(mcx_lattice *lat, int8_t *host_spins);      /* read sys.spins */
+/* init!(sys, :up/:down/:zero/:random; rng) ising.jl:74, blume_capel.jl:106 (INIT stream) */
+int32_t mcx_lattice_init(mcx_lattice *lat, int32_t mode, uint64_t seed);
+
+/* ---- canonical update rule: Metropolis(rng; beta) metropolis.jl:95, Glauber :118,
+ * HeatBath heat_bath.jl:17, and the accept! methods metropolis.jl:14-17,121-127,
+ * importance_sampling.jl:80-85, the heat-bath bodies ising.jl:43-58, blume_capel.jl:61-85.
+ * The host evaluates the reference's float expression for each local configuration and passes
+ * integer thresholds T in [0, 2^32] (u < p <=> m < ceil(p*2^32) for u = m*2^-32), n_labels
+ * tables of table_len entries, label-major.  Index conventions (nn = 2*ndim):
+ *   Ising:  idx = s*(nn+1) + nup, s in {0:down, 1:up}, nup = #up neighbours.
+ *           Metropolis/Glauber: flip iff m < T.  HeatBath: new spin is up iff m < T.
+ *   Blume-Capel Metropolis/Glauber: idx = (so*2 + b)*(2nn+1) + (sum+nn), so in {0,1,2} for
+ *           {-1,0,+1}, b the Bool draw of _propose_state (blume_capel.jl:21-30), sum the
+ *           neighbour spin sum; accept iff m < T.
+ *   Blume-Capel HeatBath: idx = k*(2nn+1) + (sum+nn), k in {0,1}: new = m<T0 ? -1 : m<T1 ? 0 : +1.
+ */
+int32_t mcx_set_rule(mcx_lattice *lat, int32_t rule, const uint64_t *thresholds, int32_t n_labels,
+                     int32_t table_len);
+/* which table (ensemble) each chain currently holds: the ensemble swap of
+ * replica_exchange.jl:133 moves labels, not lattices */
+int32_t mcx_set_labels(mcx_lattice *lat, const int32_t *label_of_chain);
+int32_t mcx_get_labels(mcx_lattice *lat, int32_t *label_of_chain);
+/* PhiloxRNG(seed) and the position of the next sweep (checkpoint/restore is exact) */
+int32_t mcx_set_rng(mcx_lattice *lat, uint64_t seed, uint64_t next_sweep);
+int32_t mcx_get_rng(mcx_lattice *lat, uint64_t *seed, uint64_t *next_sweep);
+
+/* sweep!(sys, alg, nsweeps): nsweeps x (colour 0 half-sweep, colour 1 half-sweep) on every chain.
+ * One attempt per site per sweep = the reference's `for _ in 1:N; spin_flip!(sys, alg); end`
+ * (docs/src/examples/spin_systems/pt_Ising2D.jl:52-57) in checkerboard order.  Asynchronous. */
+int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps);
+
+/* cached sums per chain (any pointer may be NULL), synchronises:
+ *   pair_sum  = sum_<ij> s_i s_j (unweighted; sys.sum_pair_interactions / J)   ising.jl:90
+ *   spin_sum  = sys.sum_spins, spin2_sum = sys.sum_spins2                       blume_capel.jl:124-125
+ *   accepted, steps = alg.accepted, alg.steps                                   importance_sampling.jl:26-27 */
+int32_t mcx_observables(mcx_lattice *lat, int64_t *pair_sum, int64_t *spin_sum, int64_t *spin2_sum,
+                        int64_t *accepted, int64_t *steps);
+int32_t mcx_energies(mcx_lattice *lat, double *energy);                  /* energy(sys) per chain */
+int32_t mcx_reset_counters(mcx_lattice *lat);                            /* reset!(alg) importance_sampling.jl:106 */
+int32_t mcx_recompute(mcx_lattice *lat);                                 /* energy(sys; full=true) */
+/* on (default): sweeps keep pair/spin sums current per flip, like modify! (ising.jl:200-205).
+ * off: sweeps only count accepted moves; the sums are recomputed from the spins on the next
+ * read (same values, fewer instructions per attempt). */
+int32_t mcx_set_tracking(mcx_lattice *lat, int32_t on);
+/* device pointer of the int64 [nchains][4] accumulator block {pair, spin, spin2, accepted}
+ * for zero-copy plumbing (collectives) by the host runtime */
+int32_t mcx_lattice_device_sums(mcx_lattice *lat, void **device_ptr);
+
+/* ---- replica exchange / parallel tempering -------------------------------------------------
+ * ReplicaExchange(backend, algs) replica_exchange.jl:52-66, ParallelTempering(betas; seed)
+ * parallel_tempering.jl:24-53, update!(rx, xs) :158-178 / :227-244, index(rx) :48-50,
+ * acceptance_rates :76-87, reset! :68-74.
+ * n_global replicas over all ranks; this rank's lattice holds slots
+ * [first_slot, first_slot + nchains).  betas[k] is the inverse temperature of ladder index k
+ * (table label k).  Slot r starts at ladder index r. */
+int32_t mcx_pt_create(mcx_lattice *lat, int32_t n_global, int32_t first_slot, const double *betas,
+                      mcx_pt **out);
+int32_t mcx_pt_destroy(mcx_pt *pt);
+/* device buffer double[n_global] of per-slot energies x; mcx_pt_publish fills this rank's slice
+ * from the lattice sums (energy(sys) per replica, pt_Ising2D.jl:96).  With more than one rank the
+ * host runtime all-gathers the buffer in place (NCCL) between publish and exchange. */
+int32_t mcx_pt_energy_buffer(mcx_pt *pt, void **device_ptr);
+int32_t mcx_pt_publish(mcx_pt *pt);
+/* update!(rx, xs): all pairs of the current stage decided on the device with
+ * u = EXCHANGE stream of the lower slot (replica_exchange.jl:168), labels swapped, stage toggled */
+int32_t mcx_pt_exchange(mcx_pt *pt);
+int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices /*[n] 1-based*/, int64_t *steps /*[n-1]*/,
+                     int64_t *accepted /*[n-1]*/, int64_t *stage, int64_t *round);
+int32_t mcx_pt_reset(mcx_pt *pt);
+
+/* ---- flat-histogram ensembles ---------------------------------------------------------------
+ * Multicanonical(rng, bins) algorithms/multicanonical.jl:9, WangLandau(rng, bins; logf)
+ * algorithms/wang_landau.jl:10, accept!(alg, x_new, x_old) importance_sampling.jl:69-78 and
+ * wang_landau.jl:29-37, record_visit! ensembles/multicanonical.jl:25-30, update! :32-44 and
+ * ensembles/wang_landau.jl:23, reset! algorithms/multicanonical.jl:27-33,
+ * merge_histograms!/distribute_logweight! parallel_multicanonical.jl:38-73.
+ * Chains are serial in the global observable, so parallelism is across chains only; the
+ * sweep visits sites 0..N-1 in order (FLAT stream).  Integer bins start:step:start+step*(n-1)
+ * (BinnedObject, binned_object.jl:13-24); an out-of-range lookup makes the next synchronising
+ * call return MCX_ERR_BOUNDS. */
+int32_t mcx_flat_create(mcx_lattice *lat, int32_t kind, int32_t observable, int64_t bin_start,
+                        int64_t bin_step, int64_t nbins, double beta_pair, mcx_flat **out);
+int32_t mcx_flat_destroy(mcx_flat *flat);
+int32_t mcx_flat_set_logweight(mcx_flat *flat, const double *logweight);
+int32_t mcx_flat_get_logweight(mcx_flat *flat, double *logweight);
+int32_t mcx_flat_get_histogram(mcx_flat *flat, double *histogram);
+int32_t mcx_flat_reset_histogram(mcx_flat *flat);
+int32_t mcx_flat_set_logf(mcx_flat *flat, double logf);
+int32_t mcx_flat_sweep(mcx_flat *flat, int64_t nsweeps);
+int32_t mcx_flat_update(mcx_flat *flat);                 /* update!(ens): muca :simple, WL halves logf */
+int32_t mcx_flat_device_histogram(mcx_flat *flat, void **device_ptr, int64_t *nbins);
+int32_t mcx_flat_device_logweight(mcx_flat *flat, void **device_ptr, int64_t *nbins);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,20 @@
+"""mcx_b200: B200-native lattice sampling hot path of MonteCarloX.jl / SpinSystems.
+
+Python mirror of the reference's Julia API for this path, over the C ABI of libmcx_b200.so
+(include/mcx_b200.h).  Names follow the reference; Julia's `f!` is spelled `f_`."""
+from . import _lib
+from ._lib import McxError, build, lib
+from .algorithms import (Glauber, HeatBath, ImportanceSampling, Metropolis, Multicanonical, WangLandau,
+                         acceptance_rate, logistic, reset_)
+from .binned_object import BinnedObject, get_centers, get_values
+from .ensembles import (BoltzmannEnsemble, FunctionEnsemble, MulticanonicalEnsemble, WangLandauEnsemble,
+                        logweight)
+from .parallel import (GPUBackend, ParallelChains, ParallelTempering, ReplicaExchange, ThreadsBackend,
+                       attempt_exchange_pair_, exchange_log_ratio, partition_slots, philox_family, set_betas,
+                       update_)
+from .rng import PhiloxRNG, exchange_u, philox4x32_10
+from .spin_systems import (BlumeCapel, Context, Ising, IsingLatticeOptim, default_context, energy, init_,
+                           magnetization, sweep_)
+from .tables import build_table, table_len
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,74 @@
+// k_pt.cu -- replica exchange on the device.
+//
+// Restates update!(rx::ReplicaExchange{ThreadsBackend}, xs) (src/algorithms/replica_exchange.jl:158-178):
+// the pairs of one stage are disjoint, so they are decided in parallel; ensembles (labels) move
+// between slots, lattices stay (:133).  Every rank holds the full ladder state and runs this
+// kernel on the same all-gathered energies, so all ranks reach identical decisions without the
+// pairwise send/recv + Allgather(new_index) of the MPI backend (:193-244).
+#include "mcx_internal.h"
+
+namespace mcx {
+
+// energy(sys) per local replica from the integer sums (ising.jl:175-178, blume_capel.jl:222-224)
+__global__ void k_pt_publish(const long long *__restrict__ sums, double *__restrict__ x, int nlocal, int first_slot,
+                             double J, double h, double D, int model)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nlocal) return;
+    const long long *s = sums + (int64_t)c * SUM_FIELDS;
+    double e = -(J * (double)s[SUM_PAIR]);
+    if (h != 0.0) e -= h * (double)s[SUM_SPIN];
+    if (model == MCX_BLUME_CAPEL) e += D * (double)s[SUM_SPIN2];
+    x[first_slot + c] = e;
+}
+
+__global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__restrict__ betas,
+                              const double *__restrict__ x, int32_t *__restrict__ index,
+                              int32_t *__restrict__ slot_of, long long *__restrict__ steps,
+                              long long *__restrict__ accepted, int32_t *__restrict__ labels, int nlocal,
+                              int first_slot, uint32_t seed_lo, uint32_t seed_hi)
+{
+    // 0-based pair k joins ladder indices k and k+1; stage 0 takes k = 0,2,4,.. (reference first=1)
+    for (int k = (stage & 1) + 2 * (blockIdx.x * blockDim.x + threadIdx.x); k < n - 1;
+         k += 2 * blockDim.x * gridDim.x) {
+        const int ri = slot_of[k], rj = slot_of[k + 1];
+        steps[k] += 1;
+        // u = rand(algorithm(rx, ri).rng): EXCHANGE stream of slot ri at this round, 53 bits
+        const Philox4 p = stream_block(seed_lo, seed_hi, (uint32_t)ri, TAG_EXCHANGE, round, 0, 0);
+        const uint64_t w = ((uint64_t)p.y << 32) | p.x;
+        const double u = (double)(w >> 11) * (1.0 / 9007199254740992.0);
+        const double bi = betas[k], bj = betas[k + 1], xi = x[ri], xj = x[rj];
+        // exchange_log_ratio (:110-113) with logweight(E) = -beta*E (ensembles/boltzmann.jl:28)
+        const double lr = ((-bi * xj) - (-bi * xi)) + ((-bj * xi) - (-bj * xj));
+        const bool acc = (lr > 0) || (u < exp(lr));
+        if (acc) {
+            accepted[k] += 1;
+            index[ri] = k + 1; index[rj] = k;
+            slot_of[k] = rj; slot_of[k + 1] = ri;
+            if (ri >= first_slot && ri < first_slot + nlocal) labels[ri - first_slot] = k + 1;
+            if (rj >= first_slot && rj < first_slot + nlocal) labels[rj - first_slot] = k;
+        }
+    }
+}
+
+void launch_pt_publish(mcx_pt *pt)
+{
+    mcx_lattice *lat = pt->lat;
+    k_pt_publish<<<(lat->nchains + 127) / 128, 128, 0, lat->ctx->stream>>>(
+        lat->d_sums, pt->d_x, lat->nchains, pt->first_slot, lat->J, lat->h, lat->D, lat->model);
+    lat->ctx->launches++;
+}
+
+void launch_pt_exchange(mcx_pt *pt)
+{
+    mcx_lattice *lat = pt->lat;
+    const int npairs = (pt->n - 1 + 1) / 2;
+    const int blocks = npairs > 0 ? (npairs + 127) / 128 : 1;
+    k_pt_exchange<<<blocks, 128, 0, lat->ctx->stream>>>(
+        pt->n, pt->stage, pt->round, pt->d_betas, pt->d_x, pt->d_index, pt->d_slot_of, pt->d_steps,
+        pt->d_accepted, lat->d_labels, lat->nchains, pt->first_slot, (uint32_t)lat->seed,
+        (uint32_t)(lat->seed >> 32));
+    lat->ctx->launches++;
+}
+
+}  // namespace mcx

@@ -1,0 +1,569 @@
+// mcx_api.cu -- the C ABI of libmcx_b200.so (include/mcx_b200.h).  Host-side handle management only;
+// all compute is in the k_*.cu kernels.  There is no CPU fallback: every path below either
+// launches CUDA work or fails with MCX_ERR_CUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "mcx_internal.h"
+
+using namespace mcx;
+
+static thread_local char g_err[512] = "";
+
+static int32_t fail(int32_t code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                               \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(MCX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define REQUIRE(cond, code, ...)                    \
+    do {                                            \
+        if (!(cond)) return fail(code, __VA_ARGS__); \
+    } while (0)
+
+static int32_t check_launch(mcx_ctx *ctx)
+{
+    (void)ctx;
+    CUDA_TRY(cudaGetLastError());
+    return MCX_OK;
+}
+
+extern "C" {
+
+int32_t mcx_abi_version(void) { return MCX_ABI_VERSION; }
+const char *mcx_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------ context
+int32_t mcx_ctx_create(int32_t device, void *stream, mcx_ctx **out)
+{
+    REQUIRE(out, MCX_ERR_ARGUMENT, "out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MCX_ERR_CUDA, "no CUDA device available (%s); libmcx_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    REQUIRE(device >= 0 && device < count, MCX_ERR_ARGUMENT, "device %d out of range [0,%d)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    REQUIRE(prop.major >= 10, MCX_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only",
+            device, prop.major, prop.minor);
+    mcx_ctx *c = new (std::nothrow) mcx_ctx();
+    REQUIRE(c, MCX_ERR_STATE, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->total_mem = prop.totalGlobalMem;
+    c->launches = 0;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+        c->own_stream = false;
+    } else {
+        cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) {
+            delete c;
+            return fail(MCX_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
+        }
+        c->own_stream = true;
+    }
+    *out = c;
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_destroy(mcx_ctx *ctx)
+{
+    if (!ctx) return MCX_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_set_stream(mcx_ctx *ctx, void *stream)
+{
+    REQUIRE(ctx, MCX_ERR_ARGUMENT, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) {
+        if (!stream) return MCX_OK;
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_sync(mcx_ctx *ctx)
+{
+    REQUIRE(ctx, MCX_ERR_ARGUMENT, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_info(mcx_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor, uint64_t *total_mem_bytes)
+{
+    REQUIRE(ctx, MCX_ERR_ARGUMENT, "ctx is NULL");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (total_mem_bytes) *total_mem_bytes = ctx->total_mem;
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_launch_count(mcx_ctx *ctx, uint64_t *count)
+{
+    REQUIRE(ctx && count, MCX_ERR_ARGUMENT, "NULL argument");
+    *count = ctx->launches;
+    return MCX_OK;
+}
+
+// ------------------------------------------------------------------------------------ lattice
+static void lattice_free(mcx_lattice *lat)
+{
+    if (!lat) return;
+    cudaSetDevice(lat->ctx->device);
+    cudaFree(lat->view.planes);
+    cudaFree(lat->d_sums);
+    cudaFree(lat->d_thi);
+    cudaFree(lat->d_tlo);
+    cudaFree(lat->d_labels);
+    cudaFree(lat->d_staging);
+    free(lat->h_table);
+    delete lat;
+}
+
+int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int32_t *dims, int32_t nchains,
+                           int32_t storage, mcx_lattice **out)
+{
+    REQUIRE(ctx && dims && out, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(model == MCX_ISING || model == MCX_BLUME_CAPEL, MCX_ERR_ARGUMENT, "unknown model %d", model);
+    REQUIRE(ndim >= 1 && ndim <= 3, MCX_ERR_ARGUMENT, "ndim must be 1, 2 or 3 (got %d)", ndim);
+    REQUIRE(nchains >= 1 && nchains <= 65535, MCX_ERR_ARGUMENT, "nchains must be in [1, 65535] (got %d)", nchains);
+    REQUIRE(storage == MCX_STORAGE_INT8, MCX_ERR_UNSUPPORTED, "storage %d not available (int8 planes only)", storage);
+    int64_t N = 1;
+    for (int d = 0; d < ndim; ++d) {
+        REQUIRE(dims[d] >= 4 && dims[d] % 2 == 0, MCX_ERR_ARGUMENT,
+                "periodic checkerboard needs every dimension even and >= 4 (dims[%d] = %d)", d, dims[d]);
+        N *= dims[d];
+    }
+    REQUIRE(N / 16 < ((int64_t)1 << 32), MCX_ERR_ARGUMENT, "lattice too large for the 32-bit block counter");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    mcx_lattice *lat = new (std::nothrow) mcx_lattice();
+    REQUIRE(lat, MCX_ERR_STATE, "out of host memory");
+    memset(lat, 0, sizeof(*lat));
+    lat->ctx = ctx;
+    lat->model = model; lat->ndim = ndim; lat->nn = 2 * ndim; lat->storage = storage; lat->nchains = nchains;
+    lat->dims[0] = dims[0]; lat->dims[1] = ndim > 1 ? dims[1] : 1; lat->dims[2] = ndim > 2 ? dims[2] : 1;
+    lat->N = N;
+    lat->J = 1.0; lat->h = 0.0; lat->D = 0.0;
+    lat->rule = -1;
+    LatView &v = lat->view;
+    v.Lx = lat->dims[0]; v.Ly = lat->dims[1]; v.Lz = lat->dims[2]; v.half = v.Lx / 2;
+    v.ndim = ndim; v.nn = 2 * ndim; v.model = model; v.nchains = nchains;
+    v.halfN = N / 2;
+    v.plane_stride = (v.halfN + 255) / 256 * 256;
+    lat->fast2d = (ndim == 2) && (v.Lx % 32 == 0);
+    lat->track_sums = true;
+    const size_t plane_bytes = (size_t)v.plane_stride * 2 * (size_t)nchains;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&v.planes, plane_bytes)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&lat->d_sums, sizeof(long long) * SUM_FIELDS * (size_t)nchains)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&lat->d_labels, sizeof(int32_t) * (size_t)nchains)) != cudaSuccess) {
+        lattice_free(lat);
+        return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(lat->d_labels, 0, sizeof(int32_t) * (size_t)nchains, ctx->stream);
+    cudaMemsetAsync(lat->d_sums, 0, sizeof(long long) * SUM_FIELDS * (size_t)nchains, ctx->stream);
+    // constructors start all-up (ising.jl:118, blume_capel.jl:156)
+    launch_init(lat, MCX_INIT_UP, 0);
+    launch_recompute(lat);
+    int32_t st = check_launch(ctx);
+    if (st != MCX_OK) { lattice_free(lat); return st; }
+    *out = lat;
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_destroy(mcx_lattice *lat)
+{
+    if (!lat) return MCX_OK;
+    cudaSetDevice(lat->ctx->device);
+    cudaStreamSynchronize(lat->ctx->stream);
+    lattice_free(lat);
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_set_couplings(mcx_lattice *lat, double J, double h, double D)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    lat->J = J; lat->h = h; lat->D = D;
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_set_first_chain_id(mcx_lattice *lat, uint32_t first_chain_id)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    lat->first_chain = first_chain_id;
+    return MCX_OK;
+}
+
+static int32_t ensure_staging(mcx_lattice *lat)
+{
+    if (lat->d_staging) return MCX_OK;
+    CUDA_TRY(cudaMalloc((void **)&lat->d_staging, (size_t)lat->N * (size_t)lat->nchains));
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_upload(mcx_lattice *lat, const int8_t *host_spins)
+{
+    REQUIRE(lat && host_spins, MCX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    int32_t st = ensure_staging(lat);
+    if (st != MCX_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(lat->d_staging, host_spins, (size_t)lat->N * (size_t)lat->nchains,
+                             cudaMemcpyHostToDevice, lat->ctx->stream));
+    launch_pack(lat);
+    launch_recompute(lat);
+    lat->sums_dirty = false;
+    return check_launch(lat->ctx);
+}
+
+int32_t mcx_lattice_download(mcx_lattice *lat, int8_t *host_spins)
+{
+    REQUIRE(lat && host_spins, MCX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    int32_t st = ensure_staging(lat);
+    if (st != MCX_OK) return st;
+    launch_unpack(lat);
+    CUDA_TRY(cudaMemcpyAsync(host_spins, lat->d_staging, (size_t)lat->N * (size_t)lat->nchains,
+                             cudaMemcpyDeviceToHost, lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    return check_launch(lat->ctx);
+}
+
+int32_t mcx_lattice_init(mcx_lattice *lat, int32_t mode, uint64_t seed)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    REQUIRE(mode >= MCX_INIT_UP && mode <= MCX_INIT_RANDOM, MCX_ERR_ARGUMENT, "Unknown initialization type: %d", mode);
+    REQUIRE(!(mode == MCX_INIT_ZERO && lat->model == MCX_ISING), MCX_ERR_ARGUMENT,
+            "Unknown initialization type: zero is only defined for Blume-Capel");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    launch_init(lat, mode, seed);
+    launch_recompute(lat);
+    lat->sums_dirty = false;
+    return check_launch(lat->ctx);
+}
+
+// ------------------------------------------------------------------------------------ rule
+static int expected_table_len(const mcx_lattice *lat, int rule)
+{
+    const int nn = lat->nn;
+    if (lat->model == MCX_ISING) return 2 * (nn + 1);
+    return rule == MCX_HEATBATH ? 2 * (2 * nn + 1) : 6 * (2 * nn + 1);
+}
+
+int32_t mcx_set_rule(mcx_lattice *lat, int32_t rule, const uint64_t *thresholds, int32_t n_labels, int32_t table_len)
+{
+    REQUIRE(lat && thresholds, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(rule >= MCX_METROPOLIS && rule <= MCX_HEATBATH, MCX_ERR_ARGUMENT, "unknown rule %d", rule);
+    REQUIRE(n_labels >= 1, MCX_ERR_ARGUMENT, "n_labels must be >= 1");
+    REQUIRE(table_len == expected_table_len(lat, rule), MCX_ERR_ARGUMENT, "table_len %d != %d expected for this model/rule",
+            table_len, expected_table_len(lat, rule));
+    const size_t n = (size_t)n_labels * (size_t)table_len;
+    std::vector<uint32_t> hi(n), lo(n);
+    for (size_t i = 0; i < n; ++i) {
+        REQUIRE(thresholds[i] <= ((uint64_t)1 << 32), MCX_ERR_ARGUMENT, "threshold %zu out of range [0, 2^32]", i);
+        hi[i] = (uint32_t)(thresholds[i] >> 16);
+        lo[i] = (uint32_t)(thresholds[i] & 0xffffu);
+    }
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    if (n_labels != lat->n_labels || table_len != lat->table_len || !lat->d_thi) {
+        cudaFree(lat->d_thi); cudaFree(lat->d_tlo);
+        lat->d_thi = lat->d_tlo = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&lat->d_thi, n * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc((void **)&lat->d_tlo, n * sizeof(uint32_t)));
+        free(lat->h_table);
+        lat->h_table = (uint64_t *)malloc(n * sizeof(uint64_t));
+    }
+    memcpy(lat->h_table, thresholds, n * sizeof(uint64_t));
+    CUDA_TRY(cudaMemcpy(lat->d_thi, hi.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(lat->d_tlo, lo.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    lat->rule = rule; lat->n_labels = n_labels; lat->table_len = table_len;
+    // labels outside the new range would index past the tables
+    std::vector<int32_t> lab(lat->nchains);
+    CUDA_TRY(cudaMemcpy(lab.data(), lat->d_labels, sizeof(int32_t) * lat->nchains, cudaMemcpyDeviceToHost));
+    bool fix = false;
+    for (auto &l : lab) if (l < 0 || l >= n_labels) { l = 0; fix = true; }
+    if (fix) CUDA_TRY(cudaMemcpy(lat->d_labels, lab.data(), sizeof(int32_t) * lat->nchains, cudaMemcpyHostToDevice));
+    return MCX_OK;
+}
+
+int32_t mcx_set_labels(mcx_lattice *lat, const int32_t *label_of_chain)
+{
+    REQUIRE(lat && label_of_chain, MCX_ERR_ARGUMENT, "NULL argument");
+    for (int c = 0; c < lat->nchains; ++c)
+        REQUIRE(label_of_chain[c] >= 0 && label_of_chain[c] < (lat->n_labels > 0 ? lat->n_labels : 1), MCX_ERR_BOUNDS,
+                "label %d of chain %d outside [0, %d)", label_of_chain[c], c, lat->n_labels);
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(lat->d_labels, label_of_chain, sizeof(int32_t) * lat->nchains, cudaMemcpyHostToDevice,
+                             lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    return MCX_OK;
+}
+
+int32_t mcx_get_labels(mcx_lattice *lat, int32_t *label_of_chain)
+{
+    REQUIRE(lat && label_of_chain, MCX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaMemcpyAsync(label_of_chain, lat->d_labels, sizeof(int32_t) * lat->nchains, cudaMemcpyDeviceToHost,
+                             lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    return MCX_OK;
+}
+
+int32_t mcx_set_rng(mcx_lattice *lat, uint64_t seed, uint64_t next_sweep)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    REQUIRE(next_sweep < ((uint64_t)1 << 47), MCX_ERR_ARGUMENT, "sweep counter exceeds the 48-bit time field");
+    lat->seed = seed; lat->sweep = next_sweep;
+    return MCX_OK;
+}
+
+int32_t mcx_get_rng(mcx_lattice *lat, uint64_t *seed, uint64_t *next_sweep)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    if (seed) *seed = lat->seed;
+    if (next_sweep) *next_sweep = lat->sweep;
+    return MCX_OK;
+}
+
+int32_t mcx_set_tracking(mcx_lattice *lat, int32_t on)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    lat->track_sums = on != 0;
+    return MCX_OK;
+}
+
+// ------------------------------------------------------------------------------------ sweep
+int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    REQUIRE(nsweeps >= 0, MCX_ERR_ARGUMENT, "nsweeps must be >= 0");
+    REQUIRE(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    for (int64_t s = 0; s < nsweeps; ++s) {
+        for (int colour = 0; colour < 2; ++colour) {
+            const uint64_t t = 2 * lat->sweep + (uint64_t)colour;
+            const bool force_generic = getenv("MCX_FORCE_GENERIC") != nullptr;   // test hook
+            if (force_generic || !launch_sweep_ising2d(lat, colour, t)) launch_sweep_generic(lat, colour, t);
+            else if (!lat->track_sums) lat->sums_dirty = true;
+        }
+        lat->sweep += 1;
+    }
+    lat->steps += nsweeps * lat->N;
+    return check_launch(lat->ctx);
+}
+
+static int32_t refresh_sums(mcx_lattice *lat)
+{
+    if (lat->sums_dirty) {
+        launch_recompute(lat);
+        lat->sums_dirty = false;
+    }
+    return MCX_OK;
+}
+
+int32_t mcx_observables(mcx_lattice *lat, int64_t *pair_sum, int64_t *spin_sum, int64_t *spin2_sum, int64_t *accepted,
+                        int64_t *steps)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    refresh_sums(lat);
+    std::vector<long long> h((size_t)lat->nchains * SUM_FIELDS);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), lat->d_sums, h.size() * sizeof(long long), cudaMemcpyDeviceToHost,
+                             lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    CUDA_TRY(cudaGetLastError());
+    for (int c = 0; c < lat->nchains; ++c) {
+        if (pair_sum) pair_sum[c] = h[(size_t)c * SUM_FIELDS + SUM_PAIR];
+        if (spin_sum) spin_sum[c] = h[(size_t)c * SUM_FIELDS + SUM_SPIN];
+        if (spin2_sum) spin2_sum[c] = lat->model == MCX_ISING ? lat->N : h[(size_t)c * SUM_FIELDS + SUM_SPIN2];
+        if (accepted) accepted[c] = h[(size_t)c * SUM_FIELDS + SUM_ACC];
+        if (steps) steps[c] = lat->steps;
+    }
+    return MCX_OK;
+}
+
+int32_t mcx_energies(mcx_lattice *lat, double *energy)
+{
+    REQUIRE(lat && energy, MCX_ERR_ARGUMENT, "NULL argument");
+    std::vector<int64_t> pair(lat->nchains), spin(lat->nchains), spin2(lat->nchains);
+    int32_t st = mcx_observables(lat, pair.data(), spin.data(), spin2.data(), nullptr, nullptr);
+    if (st != MCX_OK) return st;
+    for (int c = 0; c < lat->nchains; ++c) {
+        double e = -(lat->J * (double)pair[c]);
+        if (lat->h != 0.0) e -= lat->h * (double)spin[c];
+        if (lat->model == MCX_BLUME_CAPEL) e += lat->D * (double)spin2[c];
+        energy[c] = e;
+    }
+    return MCX_OK;
+}
+
+int32_t mcx_reset_counters(mcx_lattice *lat)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    std::vector<long long> h((size_t)lat->nchains * SUM_FIELDS);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), lat->d_sums, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    for (int c = 0; c < lat->nchains; ++c) h[(size_t)c * SUM_FIELDS + SUM_ACC] = 0;
+    CUDA_TRY(cudaMemcpyAsync(lat->d_sums, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    lat->steps = 0;
+    return MCX_OK;
+}
+
+int32_t mcx_recompute(mcx_lattice *lat)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    launch_recompute(lat);
+    lat->sums_dirty = false;
+    return check_launch(lat->ctx);
+}
+
+int32_t mcx_lattice_device_sums(mcx_lattice *lat, void **device_ptr)
+{
+    REQUIRE(lat && device_ptr, MCX_ERR_ARGUMENT, "NULL argument");
+    *device_ptr = lat->d_sums;
+    return MCX_OK;
+}
+
+// ------------------------------------------------------------------------------------ parallel tempering
+int32_t mcx_pt_create(mcx_lattice *lat, int32_t n_global, int32_t first_slot, const double *betas, mcx_pt **out)
+{
+    REQUIRE(lat && betas && out, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(n_global >= 2, MCX_ERR_ARGUMENT, "need at least 2 replicas");
+    REQUIRE(first_slot >= 0 && first_slot + lat->nchains <= n_global, MCX_ERR_ARGUMENT,
+            "slots [%d, %d) do not fit in %d replicas", first_slot, first_slot + lat->nchains, n_global);
+    REQUIRE(lat->n_labels == n_global, MCX_ERR_STATE,
+            "the lattice must hold one rule table per ladder index (n_labels = %d, replicas = %d)", lat->n_labels, n_global);
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    mcx_pt *pt = new (std::nothrow) mcx_pt();
+    REQUIRE(pt, MCX_ERR_STATE, "out of host memory");
+    memset(pt, 0, sizeof(*pt));
+    pt->lat = lat; pt->n = n_global; pt->first_slot = first_slot;
+    const size_t n = (size_t)n_global;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&pt->d_betas, n * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_x, n * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_index, n * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_slot_of, n * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_steps, n * sizeof(long long))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_accepted, n * sizeof(long long))) != cudaSuccess) {
+        mcx_pt_destroy(pt);
+        return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
+    }
+    CUDA_TRY(cudaMemcpy(pt->d_betas, betas, n * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(pt->d_x, 0, n * sizeof(double)));
+    lat->first_chain = (uint32_t)first_slot;
+    lat->track_sums = true;
+    *out = pt;
+    return mcx_pt_reset(pt);
+}
+
+int32_t mcx_pt_destroy(mcx_pt *pt)
+{
+    if (!pt) return MCX_OK;
+    cudaSetDevice(pt->lat->ctx->device);
+    cudaStreamSynchronize(pt->lat->ctx->stream);
+    cudaFree(pt->d_betas); cudaFree(pt->d_x); cudaFree(pt->d_index); cudaFree(pt->d_slot_of);
+    cudaFree(pt->d_steps); cudaFree(pt->d_accepted);
+    delete pt;
+    return MCX_OK;
+}
+
+int32_t mcx_pt_reset(mcx_pt *pt)
+{
+    REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    mcx_lattice *lat = pt->lat;
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    std::vector<int32_t> id(pt->n);
+    for (int i = 0; i < pt->n; ++i) id[i] = i;
+    CUDA_TRY(cudaMemcpy(pt->d_index, id.data(), sizeof(int32_t) * pt->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pt->d_slot_of, id.data(), sizeof(int32_t) * pt->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(pt->d_steps, 0, sizeof(long long) * pt->n));
+    CUDA_TRY(cudaMemset(pt->d_accepted, 0, sizeof(long long) * pt->n));
+    CUDA_TRY(cudaMemcpy(lat->d_labels, id.data() + pt->first_slot, sizeof(int32_t) * lat->nchains, cudaMemcpyHostToDevice));
+    pt->stage = 0;
+    pt->round = 0;
+    return MCX_OK;
+}
+
+int32_t mcx_pt_energy_buffer(mcx_pt *pt, void **device_ptr)
+{
+    REQUIRE(pt && device_ptr, MCX_ERR_ARGUMENT, "NULL argument");
+    *device_ptr = pt->d_x;
+    return MCX_OK;
+}
+
+int32_t mcx_pt_publish(mcx_pt *pt)
+{
+    REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
+    refresh_sums(pt->lat);
+    launch_pt_publish(pt);
+    return check_launch(pt->lat->ctx);
+}
+
+int32_t mcx_pt_exchange(mcx_pt *pt)
+{
+    REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
+    launch_pt_exchange(pt);
+    pt->stage = 1 - pt->stage;
+    pt->round += 1;
+    return check_launch(pt->lat->ctx);
+}
+
+int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices, int64_t *steps, int64_t *accepted, int64_t *stage, int64_t *round)
+{
+    REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    mcx_lattice *lat = pt->lat;
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    if (indices) {
+        std::vector<int32_t> id(pt->n);
+        CUDA_TRY(cudaMemcpy(id.data(), pt->d_index, sizeof(int32_t) * pt->n, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < pt->n; ++i) indices[i] = id[i] + 1;   // 1-based like rx.indices
+    }
+    if (steps) CUDA_TRY(cudaMemcpy(steps, pt->d_steps, sizeof(long long) * (pt->n - 1), cudaMemcpyDeviceToHost));
+    if (accepted) CUDA_TRY(cudaMemcpy(accepted, pt->d_accepted, sizeof(long long) * (pt->n - 1), cudaMemcpyDeviceToHost));
+    if (stage) *stage = pt->stage;
+    if (round) *round = (int64_t)pt->round;
+    return MCX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+// mcx_common.cuh -- shared device helpers for libmcx_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcx_b200.h"
+
+namespace mcx {
+
+enum : uint32_t { TAG_SWEEP = 0, TAG_EXCHANGE = 1, TAG_INIT = 2, TAG_FLAT = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10.  One call yields 128 bits = eight 16-bit lanes = the primary (high-half) draw
+// of eight consecutive slots (RNG layout v1, include/mcx_b200.h).
+// ---------------------------------------------------------------------------------------------
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3,
+                                                      uint32_t k0, uint32_t k1)
+{
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// counter word 2 of the stream layout
+__host__ __device__ __forceinline__ uint32_t ctr_word2(uint64_t t, uint32_t plane, uint32_t tag)
+{
+    return (uint32_t)((t >> 32) & 0xffffu) | (plane << 16) | (tag << 24);
+}
+
+__host__ __device__ __forceinline__ Philox4 stream_block(uint32_t seed_lo, uint32_t seed_hi, uint32_t chain,
+                                                         uint32_t tag, uint64_t t, uint32_t blk, uint32_t plane)
+{
+    return philox4x32_10(blk, (uint32_t)t, ctr_word2(t, plane, tag), chain, seed_lo, seed_hi);
+}
+
+__host__ __device__ __forceinline__ uint32_t lane16(const Philox4 &p, int lane)
+{
+    const uint32_t w = (lane >> 1) == 0 ? p.x : (lane >> 1) == 1 ? p.y : (lane >> 1) == 2 ? p.z : p.w;
+    return (w >> (16 * (lane & 1))) & 0xffffu;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lattice view handed to kernels
+// ---------------------------------------------------------------------------------------------
+struct LatView {
+    uint8_t *planes;        // [nchains][2][plane_stride] one byte per spin, colour planes
+    int64_t plane_stride;   // bytes between planes
+    int64_t halfN;          // sites per colour plane
+    int32_t Lx, Ly, Lz, half;   // half = Lx/2
+    int32_t ndim, nn, model, nchains;
+};
+
+__device__ __forceinline__ uint8_t *plane_ptr(const LatView &L, int chain, int colour)
+{
+    return L.planes + ((int64_t)chain * 2 + colour) * L.plane_stride;
+}
+
+// per-chain accumulator block
+enum { SUM_PAIR = 0, SUM_SPIN = 1, SUM_SPIN2 = 2, SUM_ACC = 3, SUM_FIELDS = 4 };
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace mcx

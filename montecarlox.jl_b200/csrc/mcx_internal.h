@@ -1,0 +1,83 @@
+// mcx_internal.h -- host-side handle layouts and kernel launcher prototypes (not part of the ABI).
+#pragma once
+#include "mcx_common.cuh"
+
+struct mcx_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count, cc_major, cc_minor;
+    size_t total_mem;
+    uint64_t launches;
+};
+
+struct mcx_lattice {
+    mcx_ctx *ctx;
+    mcx::LatView view;
+    int model, ndim, nn, storage, nchains;
+    int dims[3];
+    int64_t N;
+    long long *d_sums;          // [nchains][SUM_FIELDS]
+    int rule, n_labels, table_len;
+    uint32_t *d_thi, *d_tlo;    // [n_labels][table_len]: T >> 16 (0..65536) and T & 0xffff
+    uint64_t *h_table;          // host copy of the thresholds
+    int32_t *d_labels;          // [nchains]
+    uint64_t seed, sweep;
+    uint32_t first_chain;
+    int64_t steps;              // attempts per chain since the last reset (same for every chain)
+    double J, h, D;
+    int8_t *d_staging;          // [nchains][N] reference-order spins for upload/download
+    bool fast2d;                // Lx % 32 == 0 && ndim == 2: row-aligned 128-bit kernels apply
+    bool track_sums;            // fast kernels accumulate pair/spin sums per flip (else recompute lazily)
+    bool sums_dirty;            // pair/spin sums are stale (untracked sweeps ran)
+};
+
+struct mcx_pt {
+    mcx_lattice *lat;
+    int n, first_slot;
+    double *d_betas;            // [n] ladder
+    double *d_x;                // [n] per-slot energies
+    int32_t *d_index;           // [n] 0-based ladder index held by slot
+    int32_t *d_slot_of;         // [n] inverse permutation
+    long long *d_steps, *d_accepted;   // [n-1]
+    int stage;
+    uint64_t round;
+};
+
+struct mcx_flat {
+    mcx_lattice *lat;
+    int kind, observable;
+    int64_t start, step, nbins;
+    double beta_pair, logf;
+    double *d_logweight;        // [nbins] shared by every chain of this rank
+    double *d_histogram;        // [nbins]
+    int8_t *d_spins;            // [N][nchains] chain-interleaved copy used by the serial sweeps
+    long long *d_state;         // [nchains][4]: pair, spin, spin2, accepted
+    int *d_error;               // out-of-range flag
+    uint64_t sweep;
+    bool spins_valid;
+};
+
+namespace mcx {
+
+// k_generic.cu
+void launch_pack(mcx_lattice *lat);      // staging (reference order, -1/0/+1) -> colour planes
+void launch_unpack(mcx_lattice *lat);    // colour planes -> staging
+void launch_init(mcx_lattice *lat, int mode, uint64_t seed);
+void launch_recompute(mcx_lattice *lat);
+void launch_sweep_generic(mcx_lattice *lat, int colour, uint64_t t);
+
+// k_ising2d.cu
+bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t);   // false: shape not supported
+
+// k_pt.cu
+void launch_pt_publish(mcx_pt *pt);
+void launch_pt_exchange(mcx_pt *pt);
+
+// k_flat.cu
+void launch_flat_load(mcx_flat *f);      // planes -> interleaved + state
+void launch_flat_store(mcx_flat *f);     // interleaved -> planes, sums
+void launch_flat_sweep(mcx_flat *f, uint64_t sweep);
+void launch_flat_update(mcx_flat *f);
+
+}  // namespace mcx

@@ -1,0 +1,369 @@
+"""Parallel coordination mirror (src/infrastructure/{parallel_backends,parallel_chains}.jl,
+src/algorithms/{replica_exchange,parallel_tempering}.jl).
+
+The reference's two backends are ThreadsBackend (a vector of algorithms on one host) and MPIBackend
+(one chain per rank).  GPUBackend is the third: one process per GPU (torch.distributed, NCCL),
+each rank holding a contiguous block of replica slots inside ONE batched device lattice.  Only the
+per-replica energies cross NVLink (one all-gather per exchange); the swap decision is evaluated
+identically on every rank from a counter-based u, and labels move, not lattices
+(replica_exchange.jl:133)."""
+import ctypes as C
+import math
+from fractions import Fraction
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .algorithms import ImportanceSampling, Metropolis
+from .rng import PhiloxRNG, exchange_u
+from .tables import build_table, rule_of, beta_of
+
+
+# --------------------------------------------------------------------------- backends
+class ThreadsBackend:
+    """parallel_backends.jl:25-33"""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    rank = 0
+    is_root = True
+
+    @property
+    def size(self):
+        return self.n
+
+
+class GPUBackend:
+    """One process per GPU.  `group` is a torch.distributed process group (None: default group if
+    torch.distributed is initialised, else a single rank).  Mirrors rank/size/is_root of
+    parallel_backends.jl:31-33,68-70."""
+
+    def __init__(self, group=None, root=0):
+        self.group, self.root = group, root
+        try:
+            import torch.distributed as dist
+            self._dist = dist if dist.is_available() and dist.is_initialized() else None
+        except Exception:
+            self._dist = None
+
+    @property
+    def rank(self):
+        return self._dist.get_rank(self.group) if self._dist else 0
+
+    @property
+    def size(self):
+        return self._dist.get_world_size(self.group) if self._dist else 1
+
+    @property
+    def is_root(self):
+        return self.rank == self.root
+
+    def slots(self, n_global):
+        """[first, first + count) replica slots owned by this rank (contiguous, equal blocks)."""
+        return partition_slots(n_global, self.size, self.rank)
+
+    def all_gather_inplace(self, tensor, first, count):
+        """all-gather equal slices of a 1-D tensor in place (each rank owns [first, first+count))."""
+        if not self._dist or self.size == 1:
+            return
+        self._dist.all_gather_into_tensor(tensor, tensor[first:first + count].clone(), group=self.group)
+
+    def all_reduce_sum(self, tensor):
+        if not self._dist or self.size == 1:
+            return
+        self._dist.all_reduce(tensor, group=self.group)
+
+    def barrier(self):
+        if self._dist and self.size > 1:
+            self._dist.barrier(group=self.group)
+
+
+def partition_slots(n_global, nranks, rank):
+    if n_global % nranks != 0:
+        raise ValueError("replicas (%d) must divide evenly over ranks (%d)" % (n_global, nranks))
+    per = n_global // nranks
+    return rank * per, per
+
+
+# --------------------------------------------------------------------------- ParallelChains
+class ParallelChains:
+    """parallel_chains.jl:14-128 (host-side container; `algs` is a list for Threads/GPU backends)."""
+
+    def __init__(self, backend, algs):
+        self.backend, self.algs = backend, list(algs) if isinstance(algs, (list, tuple)) else [algs]
+
+    @property
+    def size(self):
+        return len(self.algs) if not isinstance(self.backend, GPUBackend) else self._n_global()
+
+    def _n_global(self):
+        return len(self.algs)
+
+    @property
+    def rank(self):
+        return self.backend.rank
+
+    @property
+    def is_root(self):
+        return self.backend.is_root
+
+    def algorithm(self, i=0):
+        return self.algs[i]
+
+    def root_chain(self):
+        return 0
+
+    def on_root(self, f):
+        if self.is_root:
+            try:
+                return f(self.root_chain())
+            except TypeError:
+                return f()
+        return None
+
+    def with_parallel(self, f):
+        return [f(i, a) for i, a in enumerate(self.algs)]
+
+
+# --------------------------------------------------------------------------- replica exchange
+def exchange_log_ratio(ens_i, ens_j, x_i, x_j):
+    """replica_exchange.jl:110-113"""
+    return (ens_i.logweight(x_j) - ens_i.logweight(x_i)) + (ens_j.logweight(x_i) - ens_j.logweight(x_j))
+
+
+def _accept_exchange(log_ratio, u):
+    """replica_exchange.jl:115"""
+    return (log_ratio > 0) or (u < math.exp(log_ratio))
+
+
+def attempt_exchange_pair_(alg_i, alg_j, x_i, x_j, u):
+    """replica_exchange.jl:124-136"""
+    if not math.isfinite(u):
+        raise ValueError("shared random number `u` must be finite")
+    accepted = _accept_exchange(exchange_log_ratio(alg_i.ensemble, alg_j.ensemble, x_i, x_j), u)
+    if accepted:
+        alg_i.ensemble, alg_j.ensemble = alg_j.ensemble, alg_i.ensemble
+    return accepted
+
+
+def _resolve_pair(my_index, stage, nranks):
+    """replica_exchange.jl:138-149 -> (active, pair_id, partner_index)"""
+    first = 1 if stage % 2 == 0 else 2
+    offset = my_index - first
+    if offset >= 0 and offset % 2 == 0 and my_index < nranks:
+        return True, my_index, my_index + 1
+    if offset > 0 and offset % 2 == 1 and my_index - 1 >= first:
+        return True, my_index - 1, my_index - 1
+    return False, 0, 0
+
+
+class ReplicaExchange:
+    """replica_exchange.jl:13-19.  indices[r] = 1-based ladder position held by slot r."""
+
+    def __init__(self, backend, algs):
+        algs = list(algs)
+        n = len(algs)
+        if n < 2:
+            raise ValueError("need at least 2 algorithms for replica exchange")
+        self.replica = ParallelChains(backend, algs)
+        self.backend = backend
+        self.stage = 0
+        self.indices = np.arange(1, n + 1, dtype=np.int64)
+        self.steps = np.zeros(n - 1, dtype=np.int64)
+        self.accepted = np.zeros(n - 1, dtype=np.int64)
+        self.round = 0
+        self._pt = None          # device handle once attached to a lattice
+        self._sys = None
+
+    # -- reference accessors
+    @property
+    def size(self):
+        return len(self.replica.algs)
+
+    @property
+    def rank(self):
+        return self.backend.rank
+
+    @property
+    def is_root(self):
+        return self.backend.is_root
+
+    def algorithm(self, i=0):
+        return self.replica.algs[i]
+
+    def index(self, i=None):
+        self._pull()
+        return self.indices if i is None else int(self.indices[i])
+
+    def acceptance_rates(self):
+        self._pull()
+        return [a / s if s > 0 else 0.0 for s, a in zip(self.steps, self.accepted)]
+
+    def acceptance_rate(self):
+        self._pull()
+        tot = int(self.steps.sum())
+        return float(self.accepted.sum()) / tot if tot > 0 else 0.0
+
+    def reset_(self):
+        self.stage = 0
+        self.indices[:] = np.arange(1, self.size + 1)
+        self.steps[:] = 0
+        self.accepted[:] = 0
+        self.round = 0
+        if self._pt is not None:
+            check(lib().mcx_pt_reset(self._pt))
+        return self
+
+    # -- host update!(rx, xs) (ThreadsBackend semantics, :158-178); also the oracle-checkable path
+    def update_(self, xs=None):
+        if xs is None:
+            return self._update_device()
+        if len(xs) != self.size:
+            raise ValueError("xs must have length size(rx)")
+        first = 1 if self.stage % 2 == 0 else 2
+        for pair_id in range(first, self.size, 2):
+            ri = int(np.nonzero(self.indices == pair_id)[0][0])
+            rj = int(np.nonzero(self.indices == pair_id + 1)[0][0])
+            self.steps[pair_id - 1] += 1
+            rng = self.algorithm(ri).rng
+            if isinstance(rng, PhiloxRNG):
+                u = exchange_u(rng.seed, rng.chain, self.round)
+            else:
+                u = rng.rand()
+            if attempt_exchange_pair_(self.algorithm(ri), self.algorithm(rj), xs[ri], xs[rj], u):
+                self.accepted[pair_id - 1] += 1
+                self.indices[ri], self.indices[rj] = self.indices[rj], self.indices[ri]
+        self.stage = 1 - self.stage
+        self.round += 1
+        return None
+
+    # -- device path
+    def attach(self, sys):
+        """Bind the ladder to a batched device lattice holding this rank's replica slots."""
+        n = self.size
+        first, count = self.backend.slots(n) if isinstance(self.backend, GPUBackend) else (0, n)
+        if sys.nchains != count:
+            raise ValueError("lattice holds %d chains but this rank owns %d replica slots" % (sys.nchains, count))
+        algs = self.replica.algs
+        rng0 = algs[0].rng
+        if not isinstance(rng0, PhiloxRNG):
+            raise ValueError("device replica exchange needs PhiloxRNG streams")
+        for r, a in enumerate(algs):
+            if a.rng.seed != rng0.seed or a.rng.chain != r:
+                raise ValueError("replica r must carry PhiloxRNG(seed, chain=r); use philox_family(seed)")
+        betas = np.array([beta_of(a) for a in algs], dtype=np.float64)
+        tables = np.stack([build_table(sys.model, rule_of(a), len(sys.dims), beta_of(a), sys.J, sys.h, sys.D)
+                           for a in algs])
+        sys.set_rule(rule_of(algs[0]), tables)
+        sys.set_rng(rng0.seed)
+        h = C.c_void_p()
+        check(lib().mcx_pt_create(sys.h_lat, n, first, betas.ctypes.data, C.byref(h)))
+        self._pt, self._sys, self._first, self._count = h, sys, first, count
+        self._betas = betas
+        self._xbuf = None
+        return self
+
+    def sweep_system_(self, sys, nsweeps):
+        if self._pt is None or sys is not self._sys:
+            self.attach(sys)
+        check(lib().mcx_sweep(sys.h_lat, int(nsweeps)))
+        for a in self.replica.algs[self._first:self._first + self._count]:
+            a.steps += int(nsweeps) * sys.N
+
+    def _x_tensor(self):
+        if self._xbuf is None:
+            import torch
+            p = C.c_void_p()
+            check(lib().mcx_pt_energy_buffer(self._pt, C.byref(p)))
+            self._xbuf = _as_torch(p.value, self.size, torch.float64, self._sys.ctx.device)
+        return self._xbuf
+
+    def _update_device(self):
+        if self._pt is None:
+            raise AssertionError("update_(rx) without energies needs rx.attach(sys) first")
+        check(lib().mcx_pt_publish(self._pt))
+        if isinstance(self.backend, GPUBackend) and self.backend.size > 1:
+            self.backend.all_gather_inplace(self._x_tensor(), self._first, self._count)
+        check(lib().mcx_pt_exchange(self._pt))
+        self._dirty = True
+        return None
+
+    def _pull(self):
+        if self._pt is None or not getattr(self, "_dirty", False):
+            return
+        st, rd = C.c_int64(), C.c_int64()
+        check(lib().mcx_pt_state(self._pt, self.indices.ctypes.data, self.steps.ctypes.data,
+                                 self.accepted.ctypes.data, C.byref(st), C.byref(rd)))
+        self.stage, self.round = st.value, rd.value
+        # ensembles follow the labels (replica_exchange.jl:133)
+        ens = {i + 1: type(self.replica.algs[0].ensemble)(beta=b) for i, b in enumerate(self._betas)}
+        for r, a in enumerate(self.replica.algs):
+            a.ensemble = ens[int(self.indices[r])]
+        self._dirty = False
+
+    def energies(self):
+        """per-slot energies as last published (all ranks)."""
+        self._sys.sync()
+        return self._x_tensor().cpu().numpy().copy()
+
+    def __del__(self):
+        try:
+            if self._pt is not None:
+                lib().mcx_pt_destroy(self._pt)
+        except Exception:
+            pass
+
+
+class _CudaArray:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def _as_torch(ptr, n, dtype, device):
+    """Zero-copy torch view of a device buffer owned by libmcx_b200 (plumbing for collectives)."""
+    import torch
+    typestr = {torch.float64: "<f8", torch.int64: "<i8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_CudaArray(ptr, n, typestr), device="cuda:%d" % device)
+
+
+def philox_family(seed):
+    """`rng=` argument for ParallelTempering: maps the reference's `rng(seed + i)` call
+    (parallel_tempering.jl:38,44,51) to PhiloxRNG(seed, chain=i-1), one stream per replica slot."""
+    return lambda s: PhiloxRNG(seed, chain=int(s) - int(seed) - 1)
+
+
+def ParallelTempering(betas, seed=1000, rng=None, backend=None):
+    """parallel_tempering.jl:24-53"""
+    betas = [float(b) for b in betas]
+    n = len(betas)
+    if n < 2:
+        raise ValueError("need at least 2 replicas")
+    rng = rng or philox_family(seed)
+    if backend is None:
+        backend = ThreadsBackend(n)
+    if isinstance(backend, ThreadsBackend) and backend.size != n:
+        raise ValueError("size(backend) (=%d) must equal length(betas) (=%d)" % (backend.size, n))
+    algs = [Metropolis(rng(seed + i), beta=betas[i - 1]) for i in range(1, n + 1)]
+    return ReplicaExchange(backend, algs)
+
+
+def set_betas(nreplicas, bmin, bmax, mode="uniform"):
+    """parallel_tempering.jl:146-162: range(bmax, bmin, length=n) (optionally in log space).
+    Julia's float ranges are computed in twice precision; the exact rational lerp rounded once
+    reproduces them for the ladders the reference tests pin (test_parallel_ensembles.jl:152-158)."""
+    n = int(nreplicas)
+    if n < 2:
+        raise ValueError("nreplicas must be >= 2")
+    if mode == "uniform":
+        a, b = Fraction(float(bmax)), Fraction(float(bmin))
+        return [float((a * (n - 1 - i) + b * i) / (n - 1)) for i in range(n)]
+    if mode == "geometric":
+        a, b = Fraction(math.log(float(bmax))), Fraction(math.log(float(bmin)))
+        return [math.exp(float((a * (n - 1 - i) + b * i) / (n - 1))) for i in range(n)]
+    raise ValueError("unknown beta mode %s; use :uniform or :geometric" % mode)
+
+
+def update_(obj, *args, **kwargs):
+    return obj.update_(*args, **kwargs)

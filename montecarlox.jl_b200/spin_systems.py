@@ -1,0 +1,272 @@
+"""SpinSystems mirror (SpinSystems/src/{ising,blume_capel,abstractions}.jl) backed by device lattices.
+
+Same names and observable semantics as the reference (`Ising(dims)`, `BlumeCapel(dims)`,
+`IsingLatticeOptim(Lx, Ly)`, `init!`, `energy`, `magnetization`, field `spins`), plus the one new
+verb the checkerboard needs: `sweep_(sys, alg, nsweeps)` = nsweeps * N single-spin attempts.
+All compute goes through libmcx_b200 (C ABI); nothing here falls back to the CPU."""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .rng import PhiloxRNG
+from .tables import beta_of, build_table, rule_of
+
+_contexts = {}
+
+
+class Context:
+    """One CUDA device + stream (mcx_ctx).  `stream` may be a raw cudaStream_t integer, e.g.
+    torch.cuda.current_stream().cuda_stream, so the host runtime and the kernels share a stream."""
+
+    def __init__(self, device=0, stream=None):
+        h = C.c_void_p()
+        check(lib().mcx_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h, self.device = h, int(device)
+
+    def sync(self):
+        check(lib().mcx_ctx_sync(self.h))
+
+    def set_stream(self, stream):
+        check(lib().mcx_ctx_set_stream(self.h, C.c_void_p(stream) if stream else None))
+
+    def info(self):
+        sm, ma, mi, mem = C.c_int32(), C.c_int32(), C.c_int32(), C.c_uint64()
+        check(lib().mcx_ctx_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def launch_count(self):
+        n = C.c_uint64()
+        check(lib().mcx_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def __del__(self):
+        try:
+            lib().mcx_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+
+def default_context(device=0):
+    if device not in _contexts:
+        _contexts[device] = Context(device)
+    return _contexts[device]
+
+
+_INIT = {"up": _lib.INIT_UP, "down": _lib.INIT_DOWN, "zero": _lib.INIT_ZERO, "random": _lib.INIT_RANDOM}
+
+
+class AbstractSpinSystem:
+    """abstractions.jl:12; a batch of `nchains` independent lattices of identical shape."""
+    model = None
+
+    def __init__(self, dims, J=1, h=0, D=0, nchains=1, ctx=None, periodic=True):
+        if not periodic:
+            raise ValueError("the checkerboard backend supports periodic lattices only")
+        self.dims = [int(d) for d in dims]
+        self.J, self.h, self.D = J, h, D
+        self.nchains = int(nchains)
+        self.N = int(np.prod(self.dims))
+        self.ctx = ctx or default_context()
+        hd = C.c_void_p()
+        d = (C.c_int32 * len(self.dims))(*self.dims)
+        check(lib().mcx_lattice_create(self.ctx.h, self.model, len(self.dims), d, self.nchains, _lib.STORAGE_INT8,
+                                       C.byref(hd)))
+        self.h_lat = hd
+        check(lib().mcx_lattice_set_couplings(hd, float(J), float(h), float(D)))
+        self._rule_key = None
+        self._attached = weakref.WeakSet()
+
+    def __del__(self):
+        try:
+            lib().mcx_lattice_destroy(self.h_lat)
+        except Exception:
+            pass
+
+    # ---- sys.spins
+    def _shape(self, a):
+        return a.reshape(self.N) if self.nchains == 1 else a.reshape(self.nchains, self.N)
+
+    @property
+    def spins(self):
+        out = np.empty(self.nchains * self.N, dtype=np.int8)
+        check(lib().mcx_lattice_download(self.h_lat, out.ctypes.data))
+        return self._shape(out)
+
+    @spins.setter
+    def spins(self, v):
+        v = np.ascontiguousarray(v, dtype=np.int8).reshape(-1)
+        if v.size != self.nchains * self.N:
+            raise ValueError("spins must have nchains*N = %d entries" % (self.nchains * self.N))
+        check(lib().mcx_lattice_upload(self.h_lat, v.ctypes.data))
+
+    def upload_from(self, host_ptr):
+        """Upload from a raw host pointer (e.g. pinned memory) without touching numpy."""
+        check(lib().mcx_lattice_upload(self.h_lat, C.c_void_p(host_ptr)))
+
+    # ---- observables (ising.jl:17-18, blume_capel.jl:18-19)
+    def _sums(self):
+        n = self.nchains
+        a = [np.empty(n, dtype=np.int64) for _ in range(5)]
+        check(lib().mcx_observables(self.h_lat, *[x.ctypes.data for x in a]))
+        return a
+
+    def _scalar(self, arr):
+        return arr[0].item() if self.nchains == 1 else arr
+
+    def energy(self, full=False):
+        if full:
+            check(lib().mcx_recompute(self.h_lat))
+        pair, spin, spin2, _, _ = self._sums()
+        return self._scalar(self._energy_from(pair, spin, spin2))
+
+    def _energy_from(self, pair, spin, spin2):
+        raise NotImplementedError
+
+    def magnetization(self, full=False):
+        if full:
+            check(lib().mcx_recompute(self.h_lat))
+        return self._scalar(self._sums()[1])
+
+    def pair_sum(self):
+        return self._scalar(self._sums()[0])
+
+    def spin2_sum(self):
+        return self._scalar(self._sums()[2])
+
+    def accepted(self):
+        return self._scalar(self._sums()[3])
+
+    # ---- init!(sys, type; rng) (ising.jl:74-78, blume_capel.jl:106-110)
+    def init_(self, type, rng=None):
+        if type not in _INIT:
+            raise RuntimeError("Unknown initialization type: %s" % type)
+        seed = 0
+        if type == "random":
+            assert rng is not None, "Random initialization requires rng"
+            if not isinstance(rng, PhiloxRNG):
+                raise ValueError("device init needs a PhiloxRNG (counter-based); got %s" % type(rng).__name__)
+            seed = rng.seed
+            check(lib().mcx_lattice_set_first_chain_id(self.h_lat, rng.chain))
+        check(lib().mcx_lattice_init(self.h_lat, _INIT[type], seed))
+        return self
+
+    # ---- rule + rng plumbing
+    def set_rule(self, rule, tables):
+        """tables: uint64 [n_labels, table_len]"""
+        t = np.ascontiguousarray(tables, dtype=np.uint64)
+        if t.ndim == 1:
+            t = t[None, :]
+        check(lib().mcx_set_rule(self.h_lat, rule, t.ctypes.data, t.shape[0], t.shape[1]))
+        self._rule_key = None
+
+    def set_labels(self, labels):
+        a = np.ascontiguousarray(labels, dtype=np.int32)
+        check(lib().mcx_set_labels(self.h_lat, a.ctypes.data))
+
+    def get_labels(self):
+        a = np.empty(self.nchains, dtype=np.int32)
+        check(lib().mcx_get_labels(self.h_lat, a.ctypes.data))
+        return a
+
+    def set_rng(self, seed, next_sweep=None):
+        if next_sweep is None:
+            next_sweep = self.sweep_index
+        check(lib().mcx_set_rng(self.h_lat, int(seed), int(next_sweep)))
+
+    @property
+    def sweep_index(self):
+        s, n = C.c_uint64(), C.c_uint64()
+        check(lib().mcx_get_rng(self.h_lat, C.byref(s), C.byref(n)))
+        return n.value
+
+    def set_tracking(self, on):
+        check(lib().mcx_set_tracking(self.h_lat, int(bool(on))))
+
+    def sync(self):
+        self.ctx.sync()
+
+    def _bind_alg(self, alg):
+        """Install alg's rule table and RNG stream on the lattice (cached)."""
+        rng = alg.rng
+        if not isinstance(rng, PhiloxRNG):
+            raise ValueError("checkerboard sweeps need alg.rng::PhiloxRNG (counter-based); got %s" % type(rng).__name__)
+        key = (alg.kind, beta_of(alg), self.J, self.h, self.D, rng.seed, rng.chain)
+        if key != self._rule_key:
+            T = build_table(self.model, rule_of(alg), len(self.dims), beta_of(alg), self.J, self.h, self.D)
+            self.set_rule(rule_of(alg), T)
+            check(lib().mcx_lattice_set_first_chain_id(self.h_lat, rng.chain))
+            self.set_rng(rng.seed)
+            self._rule_key = key
+
+
+class AbstractIsing(AbstractSpinSystem):
+    model = _lib.ISING
+
+    def _energy_from(self, pair, spin, spin2):
+        # -sum_pair_interactions - sum_field_interactions (ising.jl:175-177)
+        e = -(self.J * pair)
+        if self.h != 0:
+            e = e - self.h * spin
+        return e
+
+
+class Ising(AbstractIsing):
+    """Ising(dims; J=1, periodic=true, h=0) (ising.jl:413-424) on a periodic grid."""
+
+
+class IsingLatticeOptim(AbstractIsing):
+    """IsingLatticeOptim(Lx, Ly) (ising.jl:430-461): 2-D, J=1, h=0."""
+
+    def __init__(self, Lx, Ly, nchains=1, ctx=None):
+        super().__init__([Lx, Ly], 1, 0, 0, nchains, ctx)
+
+
+class AbstractBlumeCapel(AbstractSpinSystem):
+    model = _lib.BLUME_CAPEL
+
+    def _energy_from(self, pair, spin, spin2):
+        # -sum_pair - sum_field + D*sum_spins2 (blume_capel.jl:222-224); sum_pair is Float64 there
+        e = -(float(self.J) * pair)
+        if self.h != 0:
+            e = e - self.h * spin
+        return e + self.D * spin2
+
+
+class BlumeCapel(AbstractBlumeCapel):
+    """BlumeCapel(dims; J=1, D=0, periodic=true, h=0) (blume_capel.jl:500-511)."""
+
+    def __init__(self, dims, J=1, D=0, h=0, nchains=1, ctx=None, periodic=True):
+        super().__init__(dims, J, h, D, nchains, ctx, periodic)
+
+
+def energy(sys, full=False):
+    return sys.energy(full=full)
+
+
+def magnetization(sys, full=False):
+    return sys.magnetization(full=full)
+
+
+def init_(sys, type, rng=None):
+    return sys.init_(type, rng=rng)
+
+
+def sweep_(sys, alg, nsweeps=1):
+    """nsweeps * N attempts in checkerboard order = `for _ in 1:N*nsweeps; spin_flip!(sys, alg); end`
+    (pt_Ising2D.jl:52-57) with the update order changed from random-site to checkerboard.
+    Asynchronous; `alg.steps` / `alg.accepted` follow the reference's counters
+    (importance_sampling.jl:80-85) and are read back lazily."""
+    if hasattr(alg, "sweep_system_"):          # ReplicaExchange: every replica with its own label
+        return alg.sweep_system_(sys, nsweeps)
+    sys._bind_alg(alg)
+    before = None
+    if getattr(alg, "_track_counters", True):
+        before = sys._sums()[3].copy()
+    check(lib().mcx_sweep(sys.h_lat, int(nsweeps)))
+    alg.steps += int(nsweeps) * sys.N
+    if before is not None and hasattr(alg, "accepted"):
+        alg.accepted += int((sys._sums()[3] - before).sum())
+    return None

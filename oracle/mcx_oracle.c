@@ -498,6 +498,88 @@ double mcxo_baseline_random_site(int L, double beta, int nchains, int64_t sweeps
     return (double)(ts1.tv_sec - ts0.tv_sec) + 1e-9 * (double)(ts1.tv_nsec - ts0.tv_nsec);
 }
 
+/* Lean variant of the same loop for lattices whose 32 B/site neighbour table (ising.jl:436,
+ * nbr4::Vector{NTuple{4,Int}}) would not fit comfortably in host memory (L = 16384: 8.6 GB):
+ * identical algorithm and draws, neighbours computed arithmetically instead of looked up.
+ * One chain per thread; returns seconds for `nattempts` attempts per chain. */
+typedef struct {
+    int8_t *spins; int L; double beta; int64_t nattempts; mcxo_xoshiro rng; int64_t accepted; int use_table;
+    pthread_barrier_t *bar; double t0, t1;
+} lean_job;
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void *lean_worker(void *arg)
+{
+    lean_job *j = (lean_job *)arg;
+    const int L = j->L;
+    const uint64_t N = (uint64_t)L * (uint64_t)L;
+    int8_t *sp = j->spins;
+    for (uint64_t i = 0; i < N; i += 64) {                      /* init!(sys, :random), untimed */
+        uint64_t w = mcxo_xoshiro_next(&j->rng);
+        for (uint64_t b = 0; b < 64 && i + b < N; ++b) sp[i + b] = ((w >> b) & 1) ? 1 : -1;
+    }
+    pthread_barrier_wait(j->bar);
+    j->t0 = now_s();
+    const double p4 = exp(-4 * j->beta), p8 = exp(-8 * j->beta);
+    int64_t acc = 0;
+    for (int64_t n = 0; n < j->nattempts; ++n) {
+        uint64_t i = mcxo_xoshiro_next(&j->rng) % N;           /* pick_site, abstractions.jl:19 */
+        int x = (int)(i % (uint64_t)L), y = (int)(i / (uint64_t)L);
+        int xl = x == 0 ? L - 1 : x - 1, xr = x == L - 1 ? 0 : x + 1;
+        int yu = y == 0 ? L - 1 : y - 1, yd = y == L - 1 ? 0 : y + 1;
+        int s = sp[i];
+        int lpi = s * (sp[(uint64_t)y * L + xl] + sp[(uint64_t)y * L + xr] + sp[(uint64_t)yu * L + x] + sp[(uint64_t)yd * L + x]);
+        int dE = 2 * lpi;                                       /* -dpair, ising.jl:484-491 */
+        int accepted;
+        if (j->use_table) {                                     /* TableMetropolis, importance_Ising2D.jl:74-92 */
+            if (dE <= 0) accepted = 1;
+            else accepted = xoshiro_f64(&j->rng) < (dE == 4 ? p4 : p8);
+        } else {                                                /* _accept!, importance_sampling.jl:80-85 */
+            double log_ratio = -j->beta * (double)dE;
+            accepted = (log_ratio > 0) || (xoshiro_f64(&j->rng) < exp(log_ratio));
+        }
+        if (accepted) { sp[i] = (int8_t)-s; acc++; }
+    }
+    j->accepted = acc;
+    j->t1 = now_s();
+    return 0;
+}
+
+double mcxo_baseline_lean(int L, double beta, int nchains, int64_t nattempts, int use_table, uint64_t seed,
+                          double *accept_rate)
+{
+    const uint64_t N = (uint64_t)L * (uint64_t)L;
+    lean_job *jobs = (lean_job *)calloc((size_t)nchains, sizeof(lean_job));
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nchains);
+    pthread_barrier_t bar;
+    pthread_barrier_init(&bar, 0, (unsigned)nchains);
+    for (int c = 0; c < nchains; ++c) {
+        jobs[c].spins = (int8_t *)malloc(N);
+        mcxo_xoshiro_seed(&jobs[c].rng, seed + (uint64_t)c);
+        jobs[c].L = L; jobs[c].beta = beta; jobs[c].nattempts = nattempts; jobs[c].use_table = use_table;
+        jobs[c].bar = &bar;
+    }
+    for (int c = 0; c < nchains; ++c) pthread_create(&th[c], 0, lean_worker, &jobs[c]);
+    for (int c = 0; c < nchains; ++c) pthread_join(th[c], 0);
+    pthread_barrier_destroy(&bar);
+    int64_t acc = 0;
+    double t0 = jobs[0].t0, t1 = jobs[0].t1;
+    for (int c = 0; c < nchains; ++c) {
+        acc += jobs[c].accepted; free(jobs[c].spins);
+        if (jobs[c].t0 < t0) t0 = jobs[c].t0;
+        if (jobs[c].t1 > t1) t1 = jobs[c].t1;
+    }
+    if (accept_rate) *accept_rate = (double)acc / ((double)nattempts * nchains);
+    free(jobs); free(th);
+    return t1 - t0;
+}
+
 /* ===================================================================== */
 /* Integer threshold tables.  For a draw u = m*2^-32 and a Float64 p:     */
 /*   u < p  <=>  m < ceil(p * 2^32)   (p*2^32 is exact).                  */

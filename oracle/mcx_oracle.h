@@ -107,6 +107,10 @@ void mcxo_sweep_random_site(mcxo_system *s, mcxo_alg *a, mcxo_xoshiro *x, int64_
 double mcxo_baseline_random_site(int L, double beta, int nchains, int64_t sweeps, int nthreads,
                                  int use_table, uint64_t seed, double *mean_abs_m, double *mean_e);
 
+/* lean multi-chain baseline for very large L (neighbours computed, not tabulated) */
+double mcxo_baseline_lean(int L, double beta, int nchains, int64_t nattempts, int use_table, uint64_t seed,
+                          double *accept_rate);
+
 /* ---------------- integer threshold tables (what the host hands the GPU) -- */
 int mcxo_table_len(int model, int rule, int ndim);
 void mcxo_build_table(int model, int rule, int ndim, double beta, double J, double h, double D,

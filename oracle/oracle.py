@@ -97,6 +97,8 @@ def lib():
     L.mcxo_xoshiro_seed.argtypes = [C.POINTER(_Xo), u64]
     L.mcxo_baseline_random_site.argtypes = [ci, dbl, ci, i64, ci, ci, u64, pd, pd]
     L.mcxo_baseline_random_site.restype = dbl
+    L.mcxo_baseline_lean.argtypes = [ci, dbl, ci, i64, ci, u64, pd]
+    L.mcxo_baseline_lean.restype = dbl
     L.mcxo_table_len.argtypes = [ci, ci, ci]
     L.mcxo_table_len.restype = ci
     L.mcxo_build_table.argtypes = [ci, ci, ci, dbl, dbl, dbl, dbl, C.POINTER(u64)]
@@ -294,3 +296,10 @@ def baseline_random_site(L, beta, nchains, sweeps, nthreads, use_table=False, se
     secs = lib().mcxo_baseline_random_site(L, beta, nchains, sweeps, nthreads, int(use_table), seed,
                                            C.byref(m), C.byref(e))
     return secs, m.value, e.value
+
+
+def baseline_lean(L, beta, nchains, nattempts, use_table=False, seed=42):
+    """(seconds, acceptance rate) of the reference's random-site loop, one chain per thread."""
+    r = C.c_double()
+    secs = lib().mcxo_baseline_lean(L, beta, nchains, nattempts, int(use_table), seed, C.byref(r))
+    return secs, r.value

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Runs on the GPU box (via gpurun): parity tests, smoke, a short bench.  Outputs under gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
+echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+echo "smoke exit: $?" >> gpurun_out/smoke.log
+timeout 600 python bench.py --steps 3 --warmup 3 --sweeps-per-step 20 --cpu-seconds 5 > gpurun_out/bench.log 2>&1
+echo "bench exit: $?" >> gpurun_out/bench.log
+tail -5 gpurun_out/pytest_gpu.log; tail -3 gpurun_out/smoke.log; tail -2 gpurun_out/bench.log

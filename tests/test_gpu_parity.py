@@ -1,0 +1,246 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit-exact.
+
+Integer/byte work: spins, sum s_i s_j, sum s, accepted counts must be identical (tolerance 0)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BETA_C = 0.440686793509772
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mcx_b200
+    mcx_b200.lib()
+    return mcx_b200
+
+
+def _oracle_run(oracle, model, dims, rule, beta, J, h, D, seed, chain, nsweeps, spins0=None):
+    s = oracle.System(model, dims, J=float(J), h=float(h), D=float(D))
+    if spins0 is None:
+        s.init_random(seed, chain)
+    else:
+        s.spins = spins0
+    a = oracle.Alg(rule, beta)
+    s.sweep_checkerboard(a, seed, chain, 0, nsweeps)
+    return s, a
+
+
+def _make_alg(m, rule, beta, seed, chain):
+    rng = m.PhiloxRNG(seed, chain)
+    if rule == 0:
+        return m.Metropolis(rng, beta=beta)
+    if rule == 1:
+        return m.Glauber(rng, beta=beta)
+    return m.HeatBath(rng, beta=beta)
+
+
+def _check(sys_gpu, s_or, a_or, alg, nsweeps):
+    assert np.array_equal(sys_gpu.spins, s_or.spins)
+    assert sys_gpu.pair_sum() == s_or.pair_count()
+    assert sys_gpu.magnetization() == s_or.magnetization(full=True)
+    assert sys_gpu.magnetization() == sys_gpu.magnetization(full=True)
+    assert sys_gpu.energy() == sys_gpu.energy(full=True)
+    assert alg.steps == a_or.steps == nsweeps * s_or.N
+    if hasattr(alg, "accepted"):
+        assert alg.accepted == a_or.accepted
+
+
+@pytest.mark.parametrize("L", [8, 16, 64, 256])
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_ising2d_bit_exact(m, oracle, L, rule):
+    for beta, seed in ((BETA_C, 42), (0.2, 7), (1.0, 123456789012345)):
+        nsweeps = 12 if L <= 64 else 6
+        s_or, a_or = _oracle_run(oracle, oracle.ISING, [L, L], rule, beta, 1, 0, 0, seed, 3, nsweeps)
+        sys_ = m.Ising([L, L])
+        alg = _make_alg(m, rule, beta, seed, 3)
+        sys_.init_("random", rng=alg.rng)
+        m.sweep_(sys_, alg, nsweeps)
+        _check(sys_, s_or, a_or, alg, nsweeps)
+
+
+@pytest.mark.parametrize("L", [64, 128])
+def test_fast_kernel_equals_generic_kernel(m, L):
+    """same trajectories from the vectorised and the generic kernels, any strip height"""
+    outs = []
+    for env in ({"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}):
+        for k in ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        sys_ = m.Ising([L, L])
+        alg = _make_alg(m, 0, BETA_C, 99, 0)
+        sys_.init_("random", rng=alg.rng)
+        m.sweep_(sys_, alg, 10)
+        outs.append((sys_.spins.copy(), sys_.pair_sum(), sys_.magnetization(), alg.accepted))
+    for k in ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP"):
+        os.environ.pop(k, None)
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and o[1:] == outs[0][1:]
+
+
+def test_ising2d_untracked_sums_match(m, oracle):
+    L, nsweeps = 128, 5
+    s_or, a_or = _oracle_run(oracle, oracle.ISING, [L, L], 0, BETA_C, 1, 0, 0, 5, 0, nsweeps)
+    sys_ = m.Ising([L, L])
+    sys_.set_tracking(False)
+    alg = _make_alg(m, 0, BETA_C, 5, 0)
+    sys_.init_("random", rng=alg.rng)
+    m.sweep_(sys_, alg, nsweeps)
+    _check(sys_, s_or, a_or, alg, nsweeps)
+
+
+def test_ising2d_rectangular_and_field(m, oracle):
+    for dims, J, h in (([64, 8], 1, 0), ([8, 64], 1, 0), ([32, 12], 2, 0.3), ([12, 10], 1.5, -0.2)):
+        s_or, a_or = _oracle_run(oracle, oracle.ISING, dims, 0, 0.5, J, h, 0, 11, 1, 8)
+        sys_ = m.Ising(dims, J=J, h=h)
+        alg = _make_alg(m, 0, 0.5, 11, 1)
+        sys_.init_("random", rng=alg.rng)
+        m.sweep_(sys_, alg, 8)
+        assert np.array_equal(sys_.spins, s_or.spins)
+        assert sys_.pair_sum() == s_or.pair_count()
+        assert alg.accepted == a_or.accepted
+        assert sys_.energy(full=True) == pytest.approx(s_or.energy(full=True), abs=1e-9)
+
+
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_ising3d_bit_exact(m, oracle, rule):
+    dims = [8, 6, 4]
+    s_or, a_or = _oracle_run(oracle, oracle.ISING, dims, rule, 0.2216, 1, 0, 0, 2024, 0, 10)
+    sys_ = m.Ising(dims)
+    alg = _make_alg(m, rule, 0.2216, 2024, 0)
+    sys_.init_("random", rng=alg.rng)
+    m.sweep_(sys_, alg, 10)
+    _check(sys_, s_or, a_or, alg, 10)
+
+
+@pytest.mark.parametrize("dims", [[8, 8], [32, 16], [6, 4, 8]])
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_blume_capel_bit_exact(m, oracle, dims, rule):
+    for beta, J, D, h in ((0.8, 1, 0, 0), (1.1, 1.0, 0.5, 0.0), (0.6, 1.0, 0.2, 0.1)):
+        s_or, a_or = _oracle_run(oracle, oracle.BLUME_CAPEL, dims, rule, beta, J, h, D, 77, 2, 10)
+        sys_ = m.BlumeCapel(dims, J=J, D=D, h=h)
+        alg = _make_alg(m, rule, beta, 77, 2)
+        sys_.init_("random", rng=alg.rng)
+        m.sweep_(sys_, alg, 10)
+        assert np.array_equal(sys_.spins, s_or.spins)
+        assert sys_.pair_sum() == s_or.pair_count()
+        assert sys_.magnetization() == s_or.magnetization(full=True)
+        assert sys_.spin2_sum() == s_or.spin2_sum()
+        assert sys_.energy() == pytest.approx(s_or.energy(full=True), abs=1e-9)
+        if hasattr(alg, "accepted"):
+            assert alg.accepted == a_or.accepted
+
+
+def test_constructor_defaults_and_known_answers(m):
+    # SpinSystems/test/test_ising.jl:8-35 and test_blume_capel.jl:8-31 through the device path
+    s = m.Ising([4, 4])
+    assert s.energy() == -32 and s.magnetization() == 16
+    sp = s.spins.copy()
+    assert sp.dtype == np.int8 and (sp == 1).all()
+    sp[0] = -1
+    s.spins = sp
+    assert s.energy() == -24 and s.magnetization() == 14 and s.spins[0] == -1
+    b = m.BlumeCapel([4, 4], J=1, D=0.5)
+    assert b.energy() == -24.0 and b.magnetization() == 16
+    sp = b.spins.copy()
+    sp[0] = 0
+    b.spins = sp
+    assert b.magnetization() == 15 and b.energy() == -24.0 + 3.5
+    b.init_("zero")
+    assert b.energy() == 0 and b.spin2_sum() == 0
+    with pytest.raises(ValueError):
+        m.Ising([5, 4])
+    with pytest.raises(ValueError):
+        s.init_("zero")
+
+
+def test_batched_chains_with_labels(m, oracle):
+    """many independent chains in one launch, each with its own table (label) and chain id"""
+    L, n, nsweeps = 32, 6, 8
+    betas = [0.2, 0.3, 0.4, 0.44, 0.5, 0.7]
+    sys_ = m.Ising([L, L], nchains=n)
+    tables = np.stack([m.build_table(0, 0, 2, b) for b in betas])
+    sys_.set_rule(0, tables)
+    labels = [5, 0, 3, 1, 4, 2]
+    sys_.set_labels(labels)
+    sys_.set_rng(31337, 0)
+    sys_.init_("random", rng=m.PhiloxRNG(31337, 0))
+    m.lib().mcx_sweep(sys_.h_lat, nsweeps)
+    got = sys_.spins
+    for c in range(n):
+        s_or, a_or = _oracle_run(oracle, oracle.ISING, [L, L], 0, betas[labels[c]], 1, 0, 0, 31337, c, nsweeps)
+        assert np.array_equal(got[c], s_or.spins)
+        assert sys_.pair_sum()[c] == s_or.pair_count()
+        assert sys_.accepted()[c] == a_or.accepted
+
+
+def test_parallel_tempering_matches_oracle(m, oracle):
+    """sweep + exchange rounds: label permutation, per-edge counters and lattices vs the oracle
+    (replica_exchange.jl:158-178 restated in oracle.rx_update)"""
+    L, n, rounds, seed = 32, 8, 24, 2025
+    betas = m.set_betas(n, 0.3, 0.6, "uniform")
+    pt = m.ParallelTempering(betas, seed=seed, backend=m.GPUBackend())
+    sys_ = m.Ising([L, L], nchains=n)
+    pt.attach(sys_)
+    sys_.init_("random", rng=m.PhiloxRNG(seed, 0))
+    # oracle side
+    o_sys = []
+    for r in range(n):
+        s = oracle.System(oracle.ISING, [L, L])
+        s.init_random(seed, r)
+        o_sys.append(s)
+    idx = np.arange(1, n + 1, dtype=np.int64)
+    steps = np.zeros(n - 1, dtype=np.int64)
+    acc = np.zeros(n - 1, dtype=np.int64)
+    beta_of_slot = np.array(betas, dtype=np.float64)
+    stage = 0
+    for rd in range(rounds):
+        m.sweep_(sys_, pt, 1)
+        m.update_(pt)
+        for r in range(n):
+            a = oracle.Alg(oracle.METROPOLIS, float(beta_of_slot[r]))
+            o_sys[r].sweep_checkerboard(a, seed, r, rd, 1)
+        xs = [o_sys[r].energy() for r in range(n)]
+        us = [oracle.lib().mcxo_exchange_u(seed, r, rd) for r in range(n)]
+        stage = oracle.rx_update(stage, idx, steps, acc, beta_of_slot, xs, us)
+    assert list(pt.index()) == list(idx)
+    assert list(pt.steps) == list(steps) and list(pt.accepted) == list(acc)
+    assert pt.stage == stage
+    assert acc.sum() > 0
+    got = sys_.spins
+    for r in range(n):
+        assert np.array_equal(got[r], o_sys[r].spins)
+        assert pt.algorithm(r).ensemble.beta == beta_of_slot[r]
+    assert np.allclose(pt.energies(), [s.energy() for s in o_sys])
+
+
+def test_large_lattice_properties(m):
+    """L = 4096 (beyond what the oracle sweeps in seconds): size-independent properties"""
+    L = 4096
+    sys_ = m.Ising([L, L])
+    alg = _make_alg(m, 0, BETA_C, 42, 0)
+    sys_.init_("random", rng=alg.rng)
+    m.sweep_(sys_, alg, 5)
+    e_cached, m_cached, acc = sys_.energy(), sys_.magnetization(), alg.accepted
+    assert e_cached == sys_.energy(full=True) and m_cached == sys_.magnetization(full=True)
+    assert 0 < acc < alg.steps
+    sp = sys_.spins
+    assert int(sp.astype(np.int64).sum()) == m_cached and set(np.unique(sp)) == {-1, 1}
+    # host recomputation of the energy from the downloaded spins
+    g = sp.reshape(L, L).astype(np.int32)
+    pair = int((g * np.roll(g, 1, 0)).sum() + (g * np.roll(g, 1, 1)).sum())
+    assert e_cached == -pair
+    # determinism and restart: 5 sweeps == 2 + 3 sweeps with the counter carried over
+    sys2 = m.Ising([L, L])
+    alg2 = _make_alg(m, 0, BETA_C, 42, 0)
+    sys2.init_("random", rng=alg2.rng)
+    m.sweep_(sys2, alg2, 2)
+    assert sys2.sweep_index == 2
+    m.sweep_(sys2, alg2, 3)
+    assert np.array_equal(sys2.spins, sp) and alg2.accepted == acc
+    # upload/download round trip is the identity
+    sys2.spins = sp
+    assert np.array_equal(sys2.spins, sp) and sys2.energy() == e_cached
