@@ -196,7 +196,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream shared by torch and libmcx_b200, so that torch.cuda.Event
+    # brackets exactly the kernels the library launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx = m.Context(local, stream=stream.cuda_stream)
 
     def barrier():
@@ -232,7 +235,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.5)
     launches0 = ctx.launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

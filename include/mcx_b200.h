@@ -176,15 +176,21 @@ int32_t mcx_pt_reset(mcx_pt *pt);
  * Chains are serial in the global observable, so parallelism is across chains only; the
  * sweep visits sites 0..N-1 in order (FLAT stream).  Integer bins start:step:start+step*(n-1)
  * (BinnedObject, binned_object.jl:13-24); an out-of-range lookup makes the next synchronising
- * call return MCX_ERR_BOUNDS. */
+ * call return MCX_ERR_BOUNDS (out_of_range_policy 0, the reference's behaviour,
+ * test/test_multicanonical.jl:39-43) or is rejected as a move (policy 1: energy windows, which the
+ * reference does not have).  Multicanonical chains share one log-weight table and one histogram
+ * (the state after merge_histograms!/distribute_logweight!); Wang-Landau chains own one table
+ * each ([nchains][nbins]), like one WangLandauEnsemble per algorithm object. */
 int32_t mcx_flat_create(mcx_lattice *lat, int32_t kind, int32_t observable, int64_t bin_start,
-                        int64_t bin_step, int64_t nbins, double beta_pair, mcx_flat **out);
+                        int64_t bin_step, int64_t nbins, double beta_pair, int32_t out_of_range_policy,
+                        mcx_flat **out);
 int32_t mcx_flat_destroy(mcx_flat *flat);
 int32_t mcx_flat_set_logweight(mcx_flat *flat, const double *logweight);
 int32_t mcx_flat_get_logweight(mcx_flat *flat, double *logweight);
 int32_t mcx_flat_get_histogram(mcx_flat *flat, double *histogram);
 int32_t mcx_flat_reset_histogram(mcx_flat *flat);
 int32_t mcx_flat_set_logf(mcx_flat *flat, double logf);
+int32_t mcx_flat_get_logf(mcx_flat *flat, double *logf);
 int32_t mcx_flat_sweep(mcx_flat *flat, int64_t nsweeps);
 int32_t mcx_flat_update(mcx_flat *flat);                 /* update!(ens): muca :simple, WL halves logf */
 int32_t mcx_flat_device_histogram(mcx_flat *flat, void **device_ptr, int64_t *nbins);

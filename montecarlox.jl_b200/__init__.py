@@ -9,6 +9,8 @@ from .algorithms import (Glauber, HeatBath, ImportanceSampling, Metropolis, Mult
 from .binned_object import BinnedObject, get_centers, get_values
 from .ensembles import (BoltzmannEnsemble, FunctionEnsemble, MulticanonicalEnsemble, WangLandauEnsemble,
                         logweight)
+from .flat import (DeviceFlat, PairBoltzmannSpin2Ensemble, ParallelMulticanonical, distribute_logweight_,
+                   flat_for, merge_histograms_)
 from .parallel import (GPUBackend, ParallelChains, ParallelTempering, ReplicaExchange, ThreadsBackend,
                        attempt_exchange_pair_, exchange_log_ratio, partition_slots, philox_family, set_betas,
                        update_)

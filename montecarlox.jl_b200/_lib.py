@@ -69,13 +69,14 @@ SIGNATURES = {
     "mcx_pt_exchange": (_i32, [_vp]),
     "mcx_pt_state": (_i32, [_vp, _vp, _vp, _vp, _P(_i64), _P(_i64)]),
     "mcx_pt_reset": (_i32, [_vp]),
-    "mcx_flat_create": (_i32, [_vp, _i32, _i32, _i64, _i64, _i64, _dbl, _P(_vp)]),
+    "mcx_flat_create": (_i32, [_vp, _i32, _i32, _i64, _i64, _i64, _dbl, _i32, _P(_vp)]),
     "mcx_flat_destroy": (_i32, [_vp]),
     "mcx_flat_set_logweight": (_i32, [_vp, _vp]),
     "mcx_flat_get_logweight": (_i32, [_vp, _vp]),
     "mcx_flat_get_histogram": (_i32, [_vp, _vp]),
     "mcx_flat_reset_histogram": (_i32, [_vp]),
     "mcx_flat_set_logf": (_i32, [_vp, _dbl]),
+    "mcx_flat_get_logf": (_i32, [_vp, _P(_dbl)]),
     "mcx_flat_sweep": (_i32, [_vp, _i64]),
     "mcx_flat_update": (_i32, [_vp]),
     "mcx_flat_device_histogram": (_i32, [_vp, _P(_vp), _P(_i64)]),

@@ -23,6 +23,9 @@ static int32_t fail(int32_t code, const char *fmt, ...)
     return code;
 }
 
+// shared with k_flat.cu
+int32_t mcx_set_error(int32_t code, const char *msg) { return fail(code, "%s", msg); }
+
 #define CUDA_TRY(expr)                                                                               \
     do {                                                                                             \
         cudaError_t e__ = (expr);                                                                    \

@@ -46,11 +46,11 @@ struct mcx_pt {
 
 struct mcx_flat {
     mcx_lattice *lat;
-    int kind, observable;
+    int kind, observable, policy, ntables;
     int64_t start, step, nbins;
     double beta_pair, logf;
     double *d_logweight;        // [nbins] shared by every chain of this rank
-    double *d_histogram;        // [nbins]
+    void *d_histogram;          // [nbins] unsigned long long visit counters
     int8_t *d_spins;            // [N][nchains] chain-interleaved copy used by the serial sweeps
     long long *d_state;         // [nchains][4]: pair, spin, spin2, accepted
     int *d_error;               // out-of-range flag
@@ -77,7 +77,7 @@ void launch_pt_exchange(mcx_pt *pt);
 // k_flat.cu
 void launch_flat_load(mcx_flat *f);      // planes -> interleaved + state
 void launch_flat_store(mcx_flat *f);     // interleaved -> planes, sums
-void launch_flat_sweep(mcx_flat *f, uint64_t sweep);
+void launch_flat_sweep(mcx_flat *f, uint64_t sweep0, int nsweeps);
 void launch_flat_update(mcx_flat *f);
 
 }  // namespace mcx

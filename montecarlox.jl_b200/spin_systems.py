@@ -261,6 +261,10 @@ def sweep_(sys, alg, nsweeps=1):
     (importance_sampling.jl:80-85) and are read back lazily."""
     if hasattr(alg, "sweep_system_"):          # ReplicaExchange: every replica with its own label
         return alg.sweep_system_(sys, nsweeps)
+    ens = getattr(alg, "ensemble", None)
+    if ens is not None and not hasattr(ens, "beta"):
+        from .flat import flat_for             # Multicanonical / WangLandau: serial chains, FLAT stream
+        return flat_for(sys, alg).sweep_(nsweeps)
     sys._bind_alg(alg)
     before = None
     if getattr(alg, "_track_counters", True):

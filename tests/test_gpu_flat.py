@@ -1,0 +1,159 @@
+"""GPU parity for the flat-histogram path (multicanonical / Wang-Landau) against the oracle and
+against the exact 8x8 density of states (tests/golden/ising2d_8x8_logdos.csv, which
+gen_exact_dos.py checked against the reference's ising2D_8x8.csv)."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mcx_b200
+    mcx_b200.lib()
+    return mcx_b200
+
+
+def _exact_logdos(L=8):
+    rows = [ln.split(",") for ln in open(os.path.join(GOLD, "ising2d_%dx%d_logdos.csv" % (L, L))) if ln[0] in "-0123456789"]
+    return {int(r[0]): float(r[2]) for r in rows}
+
+
+def test_muca_ising_trajectory_bit_exact(m, oracle):
+    L, seed, nsweeps = 8, 1000, 50
+    bins = range(-2 * L * L, 2 * L * L + 1, 4)
+    sys_ = m.Ising([L, L])
+    rng = m.PhiloxRNG(seed, 0)
+    sys_.init_("random", rng=rng)
+    alg = m.Multicanonical(rng, bins)
+    lw0 = np.linspace(0.0, 1.5, len(bins)) ** 2
+    alg.ensemble.logweight_table.values[:] = lw0
+    m.sweep_(sys_, alg, nsweeps)
+
+    s = oracle.System(oracle.ISING, [L, L])
+    s.init_random(seed, 0)
+    a = oracle.Alg(oracle.METROPOLIS, 0.0)
+    f = oracle.Flat(bins[0], 4, len(bins))
+    f.logweight[:] = lw0
+    assert s.flat_sweep(a, f, 0, 0, 0.0, seed, 0, 0, nsweeps) == 0
+    assert np.array_equal(sys_.spins, s.spins)
+    assert np.array_equal(alg.ensemble.histogram.values, f.histogram)
+    assert alg.ensemble.histogram.values.sum() == nsweeps * L * L == alg.steps
+    assert alg.accepted == a.accepted
+    assert sys_.energy() == s.energy() == s.energy(full=True)
+    # update!(ens; mode=:simple): lw -= log(h) where h > 0
+    alg.ensemble.update_()
+    f.muca_update()
+    assert np.allclose(alg.ensemble.logweight_table.values, f.logweight, rtol=0, atol=1e-12)
+    # a second iteration continues the same streams (sweep counter carried over)
+    alg.reset_()
+    f.histogram[:] = 0
+    m.sweep_(sys_, alg, 20)
+    a2 = oracle.Alg(oracle.METROPOLIS, 0.0)
+    assert s.flat_sweep(a2, f, 0, 0, 0.0, seed, 0, nsweeps, 20) == 0
+    assert np.array_equal(sys_.spins, s.spins) and np.array_equal(alg.ensemble.histogram.values, f.histogram)
+
+
+def test_wang_landau_trajectory_bit_exact(m, oracle):
+    L, seed, nsweeps = 8, 77, 40
+    bins = range(-2 * L * L, 2 * L * L + 1, 4)
+    sys_ = m.Ising([L, L])
+    rng = m.PhiloxRNG(seed, 5)
+    sys_.init_("random", rng=rng)
+    alg = m.WangLandau(rng, bins, logf=1.0)
+    m.sweep_(sys_, alg, nsweeps)
+    alg.ensemble.update_()             # logf <- logf / 2
+    m.sweep_(sys_, alg, nsweeps)
+
+    s = oracle.System(oracle.ISING, [L, L])
+    s.init_random(seed, 5)
+    a = oracle.Alg(oracle.METROPOLIS, 0.0)
+    f = oracle.Flat(bins[0], 4, len(bins), logf=1.0)
+    assert s.flat_sweep(a, f, 1, 0, 0.0, seed, 5, 0, nsweeps) == 0
+    f.f.logf = 0.5
+    assert s.flat_sweep(a, f, 1, 0, 0.0, seed, 5, nsweeps, nsweeps) == 0
+    assert alg.ensemble.logf == 0.5
+    assert np.array_equal(sys_.spins, s.spins)
+    assert np.array_equal(alg.ensemble.logweight_table.values, f.logweight)
+    assert alg.accepted == a.accepted and alg.steps == a.steps
+
+
+def test_muca_blume_capel_pair_spin2(m, oracle):
+    """muca_BlumeCapel.jl: Boltzmann(T=0.9) on the pair term, multicanonical in sum s^2, bins 0:1:N"""
+    L, seed, nsweeps, T = 8, 42, 30, 0.9
+    N = L * L
+    sys_ = m.BlumeCapel([L, L])
+    rng = m.PhiloxRNG(seed, 0)
+    ens = m.PairBoltzmannSpin2Ensemble(m.BoltzmannEnsemble(T=T), m.MulticanonicalEnsemble(range(0, N + 1)))
+    alg = m.Metropolis(rng, ens)
+    m.sweep_(sys_, alg, nsweeps)
+
+    s = oracle.System(oracle.BLUME_CAPEL, [L, L], J=1.0, D=0.0)
+    a = oracle.Alg(oracle.METROPOLIS, 0.0)
+    f = oracle.Flat(0, 1, N + 1)
+    assert s.flat_sweep(a, f, 0, 1, 1.0 / T, seed, 0, 0, nsweeps) == 0
+    assert np.array_equal(sys_.spins, s.spins)
+    assert np.array_equal(ens.spin2.histogram.values, f.histogram)
+    assert sys_.spin2_sum() == s.spin2_sum() and alg.accepted == a.accepted
+
+
+def test_muca_many_chains_share_weights_and_histogram(m, oracle):
+    """ParallelMulticanonical on one GPU: chains share the weights; the device histogram is the sum
+    merge_histograms! would form (parallel_multicanonical.jl:38-48)"""
+    L, seed, nsweeps, nch = 8, 9, 25, 40
+    bins = range(-2 * L * L, 2 * L * L + 1, 4)
+    sys_ = m.Ising([L, L], nchains=nch)
+    rng = m.PhiloxRNG(seed, 0)
+    sys_.init_("random", rng=rng)
+    alg = m.Multicanonical(rng, bins)
+    m.sweep_(sys_, alg, nsweeps)
+    total = np.zeros(len(bins))
+    for c in range(nch):
+        s = oracle.System(oracle.ISING, [L, L])
+        s.init_random(seed, c)
+        f = oracle.Flat(bins[0], 4, len(bins))
+        assert s.flat_sweep(oracle.Alg(0, 0.0), f, 0, 0, 0.0, seed, c, 0, nsweeps) == 0
+        total += f.histogram
+        assert np.array_equal(sys_.spins[c], s.spins)
+    assert np.array_equal(alg.ensemble.histogram.values, total)
+
+
+def test_bounds_error_and_window_policy(m):
+    L = 8
+    sys_ = m.Ising([L, L])            # all up: E = -128
+    rng = m.PhiloxRNG(3, 0)
+    alg = m.Multicanonical(rng, range(-128, -100, 4))   # too narrow: the chain walks out
+    with pytest.raises(IndexError):
+        m.sweep_(sys_, alg, 50)
+    # policy 1 (energy window): proposals leaving the window are rejected instead
+    sys2 = m.Ising([L, L])
+    alg2 = m.Multicanonical(m.PhiloxRNG(3, 0), range(-128, -100, 4))
+    m.flat_for(sys2, alg2, policy=1).sweep_(50)
+    assert -128 <= sys2.energy() <= -104
+    assert alg2.ensemble.histogram.values.sum() == 50 * L * L
+
+
+def test_muca_iterations_converge_to_exact_dos(m):
+    """statistical gate: log g(E) from multicanonical iterations vs the exact 8x8 DOS
+    (RMSE as in muca_Ising2D.jl:36-39).  Tolerance: RMSE < 0.35 after 8 iterations of
+    2000 sweeps x 64 chains (typical value ~0.1)."""
+    L, nch = 8, 64
+    exact = _exact_logdos(L)
+    bins = range(-2 * L * L, 2 * L * L + 1, 4)
+    sys_ = m.Ising([L, L], nchains=nch)
+    rng = m.PhiloxRNG(1000, 0)
+    sys_.init_("random", rng=rng)
+    alg = m.Multicanonical(rng, bins)
+    for _ in range(8):
+        m.sweep_(sys_, alg, 100)       # thermalise
+        alg.reset_()
+        m.sweep_(sys_, alg, 2000)
+        alg.ensemble.update_()
+    lw = alg.ensemble.logweight_table
+    est = {e: -(lw[e] - lw[0]) for e in exact}
+    ref = {e: exact[e] - exact[0] for e in exact}
+    rmse = np.sqrt(np.mean([(est[e] - ref[e]) ** 2 for e in exact]))
+    assert rmse < 0.35, rmse
