@@ -1,0 +1,305 @@
+# MonteCarloXB200.jl -- Julia shim over libmcx_b200.so (include/mcx_b200.h).
+#
+# NOT RUNNABLE IN THIS IMAGE (no julia binary, SURVEY.md section 0 finding 2).  It is the
+# reference-side binding a maintainer would add: it shows, entry point by entry point, what the
+# C ABI replaces and how the reference's own types keep working.  The Python package
+# montecarlox.jl_b200/ mirrors exactly this file and is what the tests drive.
+#
+# Three pieces:
+#   1. PhiloxRNG <: AbstractRNG        -- the counter-based RNG injected into `alg.rng`
+#   2. sweep!(sys, alg, n) on CPU      -- the executable definition of "the Philox-driven
+#                                         reference": the UNMODIFIED reference spin_flip! visiting
+#                                         sites in checkerboard order
+#   3. DeviceIsing / DeviceBlumeCapel  -- the same verbs forwarded to the GPU through ccall
+module MonteCarloXB200
+
+using Random
+using MonteCarloX
+using SpinSystems
+import MonteCarloX: update!, reset!, acceptance_rate
+import SpinSystems: energy, magnetization, init!, spin_flip!
+
+const libmcx = get(ENV, "MCX_B200_LIB", "libmcx_b200.so")
+
+# ----------------------------------------------------------------------------------------------
+# status codes -> the exceptions the reference throws (SURVEY.md 8b)
+# ----------------------------------------------------------------------------------------------
+function check(status::Int32)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:mcx_last_error, libmcx), Cstring, ()))
+    status == 1 && throw(ArgumentError(msg))
+    status == 2 && throw(BoundsError(msg))
+    status == 4 && throw(AssertionError(msg))
+    error("libmcx_b200 status $status: $msg")
+end
+
+# ----------------------------------------------------------------------------------------------
+# 1. PhiloxRNG (RNG layout v1, include/mcx_b200.h).  Precedent for RNG injection in the
+#    reference: MutableRandomNumbers <: AbstractRNG (src/infrastructure/rng.jl:55).
+# ----------------------------------------------------------------------------------------------
+const TAG_SWEEP, TAG_EXCHANGE, TAG_INIT, TAG_FLAT = UInt32(0), UInt32(1), UInt32(2), UInt32(3)
+
+mutable struct PhiloxRNG <: AbstractRNG
+    seed::UInt64
+    chain::UInt32
+    tag::UInt32
+    t::UInt64
+    q::UInt64      # slot: row*(Lx/2) + (x>>1) for SWEEP, linear site for FLAT
+    site::UInt64   # 0-based linear site served by the next rand(rng, UInt)
+    draw::UInt32
+end
+PhiloxRNG(seed::Integer; chain::Integer=0) = PhiloxRNG(UInt64(seed), UInt32(chain), TAG_SWEEP, 0, 0, 0, 0)
+
+function philox4x32_10(c0::UInt32, c1::UInt32, c2::UInt32, c3::UInt32, k0::UInt32, k1::UInt32)
+    for _ in 1:10
+        p0 = UInt64(0xD2511F53) * c0
+        p1 = UInt64(0xCD9E8D57) * c2
+        c0, c1, c2, c3 = (UInt32(p1 >> 32) ⊻ c1 ⊻ k0), UInt32(p1 & 0xffffffff),
+                         (UInt32(p0 >> 32) ⊻ c3 ⊻ k1), UInt32(p0 & 0xffffffff)
+        k0 += 0x9E3779B9
+        k1 += 0xBB67AE85
+    end
+    return (c0, c1, c2, c3)
+end
+
+function lane16(r::PhiloxRNG, plane::UInt32)
+    c2 = UInt32((r.t >> 32) & 0xffff) | (plane << 16) | (r.tag << 24)
+    out = philox4x32_10(UInt32((r.q >> 3) & 0xffffffff), UInt32(r.t & 0xffffffff), c2, r.chain,
+                        UInt32(r.seed & 0xffffffff), UInt32(r.seed >> 32))
+    lane = r.q & 7
+    return (out[(lane >> 1) + 1] >> (16 * (lane & 1))) & 0xffff
+end
+
+"position the stream before one attempt: (tag, time, slot) and the site pick_site will return"
+function position!(r::PhiloxRNG, tag::UInt32, t::Integer, q::Integer, site::Integer)
+    r.tag, r.t, r.q, r.site, r.draw = tag, UInt64(t), UInt64(q), UInt64(site), 0
+    return r
+end
+
+# Every rand flavour the hot path uses is overridden, so nothing depends on Julia-version defaults
+# (SURVEY.md 7.3).  rand(rng)::Float64 = m * 2^-32, exact:
+function Random.rand(r::PhiloxRNG, ::Random.SamplerTrivial{Random.CloseOpen01{Float64}})
+    if r.tag == TAG_EXCHANGE          # replica_exchange.jl:168: 53 bits of block 0
+        c2 = UInt32((r.t >> 32) & 0xffff) | (TAG_EXCHANGE << 24)
+        o = philox4x32_10(UInt32(0), UInt32(r.t & 0xffffffff), c2, r.chain,
+                          UInt32(r.seed & 0xffffffff), UInt32(r.seed >> 32))
+        return Float64(((UInt64(o[2]) << 32) | o[1]) >> 11) * 2.0^-53
+    end
+    hi = lane16(r, 2 * r.draw); lo = lane16(r, 2 * r.draw + UInt32(1)); r.draw += 1
+    return Float64((UInt32(hi) << 16) | UInt32(lo)) * 2.0^-32
+end
+# rand(rng, Bool) (blume_capel.jl:22): top bit of the high half of the next draw slot
+function Random.rand(r::PhiloxRNG, ::Random.SamplerType{Bool})
+    hi = lane16(r, 2 * r.draw); r.draw += 1
+    return (hi >> 15) == 1
+end
+# rand(rng, UInt) is only drawn by pick_site (abstractions.jl:19: rand(rng, UInt) % N + 1): it
+# returns the positioned site, so the UNMODIFIED reference spin_flip! visits exactly that site.
+Random.rand(r::PhiloxRNG, ::Random.SamplerType{UInt64}) = r.site
+
+# ----------------------------------------------------------------------------------------------
+# 2. The Philox-driven reference: checkerboard order, unmodified spin_flip! per site.
+#    Works on every CPU system of SpinSystems built on a periodic grid (ising.jl:413, blume_capel.jl:500);
+#    this is what oracle/mcx_oracle.c (mcxo_sweep_checkerboard) restates in C.
+# ----------------------------------------------------------------------------------------------
+function sweep!(sys::SpinSystems.AbstractSpinSystem, alg, dims::Vector{Int}, sweep0::Integer, nsweeps::Integer)
+    rng = alg.rng::PhiloxRNG
+    Lx = dims[1]; Ly = length(dims) > 1 ? dims[2] : 1
+    half = Lx ÷ 2
+    for s in 0:nsweeps-1, colour in 0:1
+        t = 2 * (sweep0 + s) + colour
+        for i in 0:length(sys.spins)-1
+            x = i % Lx; row = i ÷ Lx; y = row % Ly; z = row ÷ Ly
+            ((x + y + z) & 1) == colour || continue
+            position!(rng, TAG_SWEEP, t, row * half + (x >> 1), i)
+            spin_flip!(sys, alg)           # reference code, untouched (ising.jl:35-58, blume_capel.jl:52-85)
+        end
+    end
+    return nothing
+end
+
+# ----------------------------------------------------------------------------------------------
+# 3. Device-backed systems.  Host-built integer tables: the reference's own float expression is
+#    evaluated IN JULIA (its own exp) for every local configuration; the device only compares
+#    integers (generalises TableMetropolis, docs/src/examples/spin_systems/importance_Ising2D.jl:74-92).
+# ----------------------------------------------------------------------------------------------
+const TWO32 = UInt64(1) << 32
+thr(p::Float64) = p > 0 ? min(UInt64(ceil(p * 4294967296.0)), TWO32) : UInt64(0)
+thr_accept(::MonteCarloX.Glauber, lr) = thr(MonteCarloX.logistic(lr))                 # metropolis.jl:124
+thr_accept(::MonteCarloX.AbstractMetropolis, lr) = lr > 0 ? TWO32 : thr(exp(lr))      # importance_sampling.jl:82
+
+mutable struct DeviceCtx
+    h::Ptr{Cvoid}
+end
+function DeviceCtx(device::Integer=0; stream::Ptr{Cvoid}=C_NULL)
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((:mcx_ctx_create, libmcx), Int32, (Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), device, stream, out))
+    return DeviceCtx(out[])
+end
+
+abstract type AbstractDeviceSystem end
+mutable struct DeviceIsing <: SpinSystems.AbstractIsing     # dispatches like any reference Ising
+    h::Ptr{Cvoid}
+    dims::Vector{Int}
+    nchains::Int
+    J::Float64
+    hfield::Float64
+    rule_key::Any
+end
+
+function DeviceIsing(ctx::DeviceCtx, dims::Vector{Int}; J=1, h=0, nchains::Integer=1)
+    out = Ref{Ptr{Cvoid}}()
+    d = Int32.(dims)
+    check(ccall((:mcx_lattice_create, libmcx), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Ref{Ptr{Cvoid}}),
+                ctx.h, 0, length(d), d, nchains, 0, out))
+    check(ccall((:mcx_lattice_set_couplings, libmcx), Int32, (Ptr{Cvoid}, Float64, Float64, Float64), out[], J, h, 0.0))
+    sys = DeviceIsing(out[], dims, nchains, J, h, nothing)
+    finalizer(s -> ccall((:mcx_lattice_destroy, libmcx), Int32, (Ptr{Cvoid},), s.h), sys)
+    return sys
+end
+
+# sys.spins: examples read length(sys.spins) (muca_Ising2D.jl:81) and copy it
+function Base.getproperty(sys::DeviceIsing, name::Symbol)
+    if name === :spins
+        buf = Vector{Int8}(undef, prod(getfield(sys, :dims)) * getfield(sys, :nchains))
+        GC.@preserve buf check(ccall((:mcx_lattice_download, libmcx), Int32, (Ptr{Cvoid}, Ptr{Int8}), getfield(sys, :h), buf))
+        return buf
+    end
+    return getfield(sys, name)
+end
+
+function sums(sys::DeviceIsing)
+    n = sys.nchains
+    pair, spin, spin2, acc, steps = (Vector{Int64}(undef, n) for _ in 1:5)
+    check(ccall((:mcx_observables, libmcx), Int32,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                sys.h, pair, spin, spin2, acc, steps))
+    return pair, spin, spin2, acc, steps
+end
+
+function energy(sys::DeviceIsing; full=false)            # ising.jl:17
+    full && check(ccall((:mcx_recompute, libmcx), Int32, (Ptr{Cvoid},), sys.h))
+    pair, spin, = sums(sys)
+    e = -(sys.J .* pair) .- sys.hfield .* spin
+    return sys.nchains == 1 ? e[1] : e
+end
+function magnetization(sys::DeviceIsing; full=false)     # ising.jl:18
+    full && check(ccall((:mcx_recompute, libmcx), Int32, (Ptr{Cvoid},), sys.h))
+    m = sums(sys)[2]
+    return sys.nchains == 1 ? m[1] : m
+end
+
+function init!(sys::DeviceIsing, type::Symbol; rng=nothing)     # ising.jl:74-78
+    mode = type == :up ? 0 : type == :down ? 1 : type == :random ? 3 : error("Unknown initialization type: $type")
+    seed = UInt64(0)
+    if type == :random
+        @assert rng !== nothing "Random initialization requires rng"
+        seed = (rng::PhiloxRNG).seed
+        check(ccall((:mcx_lattice_set_first_chain_id, libmcx), Int32, (Ptr{Cvoid}, UInt32), sys.h, rng.chain))
+    end
+    check(ccall((:mcx_lattice_init, libmcx), Int32, (Ptr{Cvoid}, Int32, UInt64), sys.h, mode, seed))
+    return sys
+end
+
+"Ising rule table: idx = s*(nn+1) + nup (include/mcx_b200.h), every entry from the reference's expression"
+function ising_table(alg, ndim::Int, J, h)
+    nn = 2 * ndim
+    β = alg isa MonteCarloX.HeatBath ? alg.β : MonteCarloX.ensemble(alg).beta
+    T = Vector{UInt64}(undef, 2 * (nn + 1))
+    for sb in 0:1, nup in 0:nn
+        s = sb == 1 ? 1 : -1
+        lpi = s * (2nup - nn)                          # local_pair_interactions, abstractions.jl:41-48
+        Δpair = -2 * J * lpi; Δspin = -2 * s           # flip_changes, ising.jl:187-192
+        ΔE = -Δpair - h * Δspin                        # delta_energy, ising.jl:198
+        T[sb * (nn + 1) + nup + 1] = alg isa MonteCarloX.HeatBath ?
+            thr(MonteCarloX.logistic(β * float(s) * ΔE)) :                     # ising.jl:49
+            thr_accept(alg, MonteCarloX.logweight(MonteCarloX.ensemble(alg), ΔE))   # metropolis.jl:14-17
+    end
+    return T
+end
+
+rule_code(::MonteCarloX.Glauber) = Int32(1)
+rule_code(::MonteCarloX.AbstractMetropolis) = Int32(0)
+rule_code(::MonteCarloX.HeatBath) = Int32(2)
+
+"sweep!(sys, alg, n): n*N attempts = `for _ in 1:n*N; spin_flip!(sys, alg); end` in checkerboard order"
+function sweep!(sys::DeviceIsing, alg, nsweeps::Integer=1)
+    rng = alg.rng::PhiloxRNG
+    key = (typeof(alg), alg isa MonteCarloX.HeatBath ? alg.β : MonteCarloX.ensemble(alg).beta, rng.seed, rng.chain)
+    if key != sys.rule_key
+        T = ising_table(alg, length(sys.dims), sys.J, sys.hfield)
+        GC.@preserve T check(ccall((:mcx_set_rule, libmcx), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt64}, Int32, Int32),
+                                   sys.h, rule_code(alg), T, 1, length(T)))
+        check(ccall((:mcx_lattice_set_first_chain_id, libmcx), Int32, (Ptr{Cvoid}, UInt32), sys.h, rng.chain))
+        s = Ref{UInt64}(); n = Ref{UInt64}()
+        check(ccall((:mcx_get_rng, libmcx), Int32, (Ptr{Cvoid}, Ref{UInt64}, Ref{UInt64}), sys.h, s, n))
+        check(ccall((:mcx_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64), sys.h, rng.seed, n[]))
+        sys.rule_key = key
+    end
+    acc0 = sum(sums(sys)[4])
+    check(ccall((:mcx_sweep, libmcx), Int32, (Ptr{Cvoid}, Int64), sys.h, nsweeps))
+    alg.steps += nsweeps * prod(sys.dims)                       # importance_sampling.jl:81
+    hasproperty(alg, :accepted) && (alg.accepted += sum(sums(sys)[4]) - acc0)
+    return nothing
+end
+
+# spin_flip!(sys::DeviceIsing, alg) itself is deliberately NOT defined: a single random-site attempt
+# per ccall would defeat the device; callers replace their `for _ in 1:N; spin_flip!(...)` loop by sweep!.
+
+# ----------------------------------------------------------------------------------------------
+# GPU backend for ParallelChains / ReplicaExchange (parallel_backends.jl:25-70, replica_exchange.jl)
+# ----------------------------------------------------------------------------------------------
+struct GPUBackend
+    rank::Int
+    nranks::Int
+    allgather!::Function     # (device_ptr::Ptr{Float64}, n) -> nothing ; NCCL.jl / MPI.jl (CUDA-aware) plumbing
+end
+MonteCarloX.rank(b::GPUBackend) = b.rank
+Base.size(b::GPUBackend) = b.nranks
+MonteCarloX.is_root(b::GPUBackend) = b.rank == 0
+
+mutable struct DeviceReplicaExchange
+    h::Ptr{Cvoid}
+    sys::DeviceIsing
+    backend::GPUBackend
+    n::Int
+end
+
+"ParallelTempering(betas; seed, rng = s -> PhiloxRNG(seed; chain = s - seed - 1)) bound to a batched lattice"
+function attach(backend::GPUBackend, sys::DeviceIsing, algs::Vector)
+    n = length(algs)
+    per = n ÷ backend.nranks
+    first = backend.rank * per
+    T = reduce(vcat, [ising_table(a, length(sys.dims), sys.J, sys.hfield) for a in algs])
+    GC.@preserve T check(ccall((:mcx_set_rule, libmcx), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt64}, Int32, Int32),
+                               sys.h, rule_code(algs[1]), T, n, length(T) ÷ n))
+    betas = Float64[MonteCarloX.ensemble(a).beta for a in algs]
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((:mcx_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64), sys.h, algs[1].rng.seed, 0))
+    GC.@preserve betas check(ccall((:mcx_pt_create, libmcx), Int32,
+                                   (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ref{Ptr{Cvoid}}), sys.h, n, first, betas, out))
+    return DeviceReplicaExchange(out[], sys, backend, n)
+end
+
+"update!(rx): replica_exchange.jl:158-178 on the device; only the energies cross NVLink"
+function update!(rx::DeviceReplicaExchange)
+    check(ccall((:mcx_pt_publish, libmcx), Int32, (Ptr{Cvoid},), rx.h))
+    if rx.backend.nranks > 1
+        p = Ref{Ptr{Cvoid}}()
+        check(ccall((:mcx_pt_energy_buffer, libmcx), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), rx.h, p))
+        rx.backend.allgather!(Ptr{Float64}(p[]), rx.n)       # in-place all-gather of n doubles
+    end
+    check(ccall((:mcx_pt_exchange, libmcx), Int32, (Ptr{Cvoid},), rx.h))
+    return nothing
+end
+
+function index(rx::DeviceReplicaExchange)                    # replica_exchange.jl:48-50
+    idx = Vector{Int64}(undef, rx.n)
+    check(ccall((:mcx_pt_state, libmcx), Int32,
+                (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                rx.h, idx, C_NULL, C_NULL, C_NULL, C_NULL))
+    return idx
+end
+
+end # module

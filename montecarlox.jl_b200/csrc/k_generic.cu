@@ -254,8 +254,10 @@ void launch_recompute(mcx_lattice *lat)
 {
     const int n = lat->nchains * SUM_FIELDS;
     k_zero_sums<<<(n + 127) / 128, 128, 0, lat->ctx->stream>>>(lat->d_sums, lat->nchains, 1);
+    lat->ctx->launches++;
+    if (launch_recompute_ising2d(lat)) return;
     k_recompute<<<site_grid(lat, lat->view.halfN, 256), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_sums);
-    lat->ctx->launches += 2;
+    lat->ctx->launches++;
 }
 
 template <int MODEL, int RULE>

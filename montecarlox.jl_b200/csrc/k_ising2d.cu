@@ -1,18 +1,23 @@
 // k_ising2d.cu -- vectorised checkerboard half-sweep for 2-D Ising lattices, one byte per spin.
 //
 // Work decomposition.  The target colour plane is a [Ly][Lx/2] byte matrix.  One thread owns a
-// 16-byte column segment (one 128-bit load/store per row) and walks down a strip of R rows,
-// keeping the three neighbour rows of the *other* colour plane (up, centre, down) in a rolling
-// register window, so every byte of the other plane is read once per strip (+2 halo rows) and
-// every byte of the target plane is read once and written once: 3 bytes per attempt, the
-// algorithmic minimum.  The left/right neighbour byte that falls outside the
-// thread's segment comes from the adjacent lane by warp shuffle (edge lanes load one byte).
+// 16-byte column segment (one 128-bit load/store per row) and walks down a strip of R rows, two
+// rows per loop trip, keeping the neighbour rows of the *other* colour plane in a rolling register
+// window, so every byte of the other plane is read once per strip (+2 halo rows) and every byte of
+// the target plane is read once and written once: 3 bytes per attempt, the algorithmic minimum
+// (SURVEY.md 8d).  The left/right neighbour byte that falls outside the thread's segment comes from
+// the adjacent lane by warp shuffle (edge lanes load one byte, prefetched a trip ahead).
 //
-// Randomness.  A thread-row needs 16 draws = two Philox4x32-10 blocks (eight 16-bit lanes each).
-// The 16-bit lane is the HIGH half of the 32-bit draw; the decision m < T is settled by the high
-// halves unless they tie (probability 2^-16 per site), in which case the row is redone exactly
-// with the low halves from plane 1.  Results are bit-identical to k_sweep_generic and to the
-// oracle for every shape both accept.
+// Randomness and the decision.  A thread-row needs 16 draws = two Philox4x32-10 blocks (eight
+// 16-bit lanes each, the HIGH halves of the 32-bit draws).  The decision m < T is first tried on
+// the top 15 bits, two sites per instruction: with hs = (w >> 1) & 0x7fff7fff (two 15-bit values)
+// and tt the pair of 15-bit thresholds of the two sites (ONE shared-memory load from a pair table
+// indexed by both sites' (spin, #up-neighbours) codes),
+//     r  = (hs | 0x80008000) - tt           bit 15 / 31:  h15 >= t15   (not surely accepted)
+//     r2 = r - 0x00010001                   bit 15 / 31:  h15 >  t15   (surely rejected)
+// and a site is undecided (probability 2^-15) iff bit(r) & ~bit(r2).  Any undecided site sends the
+// thread-row to an exact redo with the full 32-bit draws (low halves from Philox plane 1).  The
+// result is bit-identical to k_sweep_generic and to the oracle.
 //
 // Persistent grid: gridDim.x = SMs x resident CTAs, items handed out round-robin.
 #include "mcx_internal.h"
@@ -24,9 +29,9 @@ namespace mcx {
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kTableLen = 10;   // 2 * (nn + 1) for nn = 4
-
-__device__ __forceinline__ uint32_t byte_of(uint32_t w, int b) { return __byte_perm(w, 0, 0x4440 | b); }
+constexpr int kTableLen = 10;                 // 2 * (nn + 1) for nn = 4
+constexpr int kPairRowWords = 256;            // pair table row stride (words): address = v1 * 256 + v0
+constexpr int kPairWords = 9 * kPairRowWords + kTableLen;
 
 struct Acc {
     uint32_t flips = 0;   // number of changed sites
@@ -35,7 +40,7 @@ struct Acc {
     int32_t sn = 0;       // sum over changed sites of s*nup
 };
 
-// Exact redo of one thread-row with full 32-bit draws (taken when a high-half tie was seen).
+// Exact redo of one thread-row with full 32-bit draws (taken when a 15-bit tie was seen).
 template <bool HEATBATH>
 __device__ __noinline__ uint4 row_exact(uint4 tq, uint4 nq, const uint32_t *thi, const uint32_t *tlo,
                                         Philox4 a0, Philox4 b0, Philox4 a1, Philox4 b1)
@@ -57,156 +62,202 @@ __device__ __noinline__ uint4 row_exact(uint4 tq, uint4 nq, const uint32_t *thi,
     return make_uint4(tw[0], tw[1], tw[2], tw[3]);
 }
 
-template <bool HEATBATH, bool TRACK>
-__global__ void __launch_bounds__(kThreads)
-k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
-          const int32_t *__restrict__ labels, int n_labels, long long *__restrict__ sums, uint32_t seed_lo,
-          uint32_t seed_hi, uint64_t t, int colour, uint32_t first_chain, int R, int nstrips,
-          int blocks_per_chain, int nitems)
+__device__ __forceinline__ uint32_t shr1_fma(uint32_t w)
 {
-    extern __shared__ uint32_t smem[];
-    uint32_t *s_thi = smem;                               // [n_labels][10]
-    uint32_t *s_tlo = smem + n_labels * kTableLen;        // [n_labels][10]
-    for (int i = threadIdx.x; i < n_labels * kTableLen; i += kThreads) {
-        s_thi[i] = thi_g[i];
-        s_tlo[i] = tlo_g[i];
+    return __umulhi(w, 0x80000000u);      // w >> 1 on the FMA pipe (the ALU pipe is the busy one)
+}
+
+// One thread-row: 16 target sites (tq), neighbour rows U (above), C (same row, other plane),
+// D (below).  PARITY 0: the in-row neighbour pair of target byte j is other-plane bytes (j-1, j);
+// PARITY 1: (j, j+1).  `side` is the other-plane byte just outside the segment on that side.
+template <int PARITY, bool HEATBATH, bool TRACK>
+__device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const uint4 C, const uint4 D,
+                                            const uint32_t side, const uint32_t blk, const uint32_t t_lo,
+                                            const uint32_t c2, const uint32_t c2lo, const uint32_t chain_id,
+                                            const uint32_t seed_lo, const uint32_t seed_hi,
+                                            const uint32_t *s_pair, const uint32_t *s_thi, const uint32_t *s_tlo,
+                                            Acc &acc, const bool active)
+{
+    const Philox4 ra = philox4x32_10(blk, t_lo, c2, chain_id, seed_lo, seed_hi);
+    const Philox4 rb = philox4x32_10(blk + 1, t_lo, c2, chain_id, seed_lo, seed_hi);
+
+    uint32_t S[4];
+    if (PARITY == 0) {
+        S[0] = (C.x << 8) | side;
+        S[1] = __funnelshift_l(C.x, C.y, 8);
+        S[2] = __funnelshift_l(C.y, C.z, 8);
+        S[3] = __funnelshift_l(C.z, C.w, 8);
+    } else {
+        S[0] = __funnelshift_r(C.x, C.y, 8);
+        S[1] = __funnelshift_r(C.y, C.z, 8);
+        S[2] = __funnelshift_r(C.z, C.w, 8);
+        S[3] = (C.w >> 8) | (side << 24);
     }
-    __syncthreads();
+    const uint32_t nup[4] = {U.x + D.x + C.x + S[0], U.y + D.y + C.y + S[1], U.z + D.z + C.z + S[2],
+                             U.w + D.w + C.w + S[3]};
+    const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
+    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};   // word k: sites 2k, 2k+1
+    uint32_t nw[4];
+    uint32_t tie = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const uint32_t idx4 = tw[w] * 20u + nup[w] * 4u;        // byte b = 4 * (5 s + nup) of site 4w+b
+        const uint32_t ttA = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (idx4 & 0xffffu));
+        const uint32_t ttB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (idx4 >> 16));
+        const uint32_t hA = (shr1_fma(rw[2 * w]) & 0x7fff7fffu) | 0x80008000u;
+        const uint32_t hB = (shr1_fma(rw[2 * w + 1]) & 0x7fff7fffu) | 0x80008000u;
+        const uint32_t rA = hA - ttA, rB = hB - ttB;
+        const uint32_t qA = rA - 0x00010001u, qB = rB - 0x00010001u;
+        tie |= (rA & ~qA) | (rB & ~qB);
+        const uint32_t P = __byte_perm(rA, rB, 0x7531);          // bit 7 of byte b: site 4w+b NOT accepted
+        const uint32_t F = (~P & 0x80808080u) >> 7;              // 0x01 per accepted site
+        nw[w] = HEATBATH ? F : (tw[w] ^ F);
+    }
+    if (tie & 0x80008000u) {
+        // rare (2^-15 per site): settle the whole thread-row with the full 32-bit draws
+        const Philox4 la = philox4x32_10(blk, t_lo, c2lo, chain_id, seed_lo, seed_hi);
+        const Philox4 lb = philox4x32_10(blk + 1, t_lo, c2lo, chain_id, seed_lo, seed_hi);
+        const uint4 ex = row_exact<HEATBATH>(tq, make_uint4(nup[0], nup[1], nup[2], nup[3]), s_thi, s_tlo, ra, rb, la, lb);
+        nw[0] = ex.x; nw[1] = ex.y; nw[2] = ex.z; nw[3] = ex.w;
+    }
+    if (active) {
+        uint32_t fsum = 0, ssum = 0, nsum = 0, snsum = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t Fc = nw[w] ^ tw[w];               // changed sites, 0x01 per byte
+            fsum += Fc;
+            if (TRACK) {
+                const uint32_t SF = tw[w] & Fc;
+                ssum += SF;
+                nsum += nup[w] & (Fc * 255u);
+                snsum += nup[w] & (SF * 255u);
+            }
+        }
+        acc.flips = __dp4a(fsum, 0x01010101u, acc.flips);
+        if (TRACK) {
+            acc.s = __dp4a(ssum, 0x01010101u, (uint32_t)acc.s);
+            acc.n = __dp4a(nsum, 0x01010101u, (uint32_t)acc.n);
+            acc.sn = __dp4a(snsum, 0x01010101u, (uint32_t)acc.sn);
+        }
+    }
+    return make_uint4(nw[0], nw[1], nw[2], nw[3]);
+}
+
+__device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
+
+template <int COLOUR, bool HEATBATH, bool TRACK>
+__global__ void __launch_bounds__(kThreads, 5)
+k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
+          const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
+          uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
+{
+    __shared__ uint32_t s_pair[kPairWords];
+    __shared__ uint32_t s_thi[kTableLen], s_tlo[kTableLen];
+    int cur_label = -1;
 
     const int half = L.half;
     const int nseg = half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
     const int lane = threadIdx.x & 31;
+    const uint32_t t_lo = (uint32_t)t;
     const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
     const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int chain = item / blocks_per_chain;
+        const int label = labels[chain];
+        if (label != cur_label) {
+            // pair table of this chain's ensemble: entry (i1, i0) = t15[i0] | t15[i1] << 16 with
+            // t15 = min(T >> 17, 0x7fff) (T = 2^32, "always", ties on h15 == 0x7fff and is settled exactly)
+            __syncthreads();
+            if (threadIdx.x < kTableLen) {
+                s_thi[threadIdx.x] = thi_g[label * kTableLen + threadIdx.x];
+                s_tlo[threadIdx.x] = tlo_g[label * kTableLen + threadIdx.x];
+            }
+            if (threadIdx.x < kTableLen * kTableLen) {
+                const int i1 = threadIdx.x / kTableLen, i0 = threadIdx.x - i1 * kTableLen;
+                const uint32_t a = min(thi_g[label * kTableLen + i0] >> 1, 0x7fffu);
+                const uint32_t b = min(thi_g[label * kTableLen + i1] >> 1, 0x7fffu);
+                s_pair[i1 * kPairRowWords + i0] = a | (b << 16);
+            }
+            __syncthreads();
+            cur_label = label;
+        }
         const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
         const bool active = g0 < G;
         const int64_t g = active ? g0 : G - 1;
         const int strip = (int)(g / nseg);
         const int seg = (int)(g - (int64_t)strip * nseg);
-        const int row0 = strip * R;
+        const int row0 = strip * R;                               // even
         const uint32_t chain_id = first_chain + (uint32_t)chain;
-        const uint32_t *thi = s_thi + labels[chain] * kTableLen;
-        const uint32_t *tlo = s_tlo + labels[chain] * kTableLen;
 
-        uint8_t *tgt = plane_ptr(L, chain, colour);
-        const uint8_t *__restrict__ oth = plane_ptr(L, chain, colour ^ 1);
+        uint8_t *tgt = plane_ptr(L, chain, COLOUR);
+        const uint8_t *__restrict__ oth = plane_ptr(L, chain, COLOUR ^ 1);
         const int col = seg << 4;
         const int colL = (seg == 0 ? half : col) - 1;             // byte left of the segment (periodic)
         const int colR = (seg == nseg - 1) ? 0 : col + 16;        // byte right of the segment
         const bool loadL = (lane == 0) || (seg == 0);
         const bool loadR = (lane == 31) || (seg == nseg - 1);
+        // even rows of this strip have parity COLOUR, odd rows COLOUR ^ 1 (row0 is even)
+        const bool edgeA = COLOUR == 0 ? loadL : loadR;
+        const bool edgeB = COLOUR == 0 ? loadR : loadL;
+        const int colA = COLOUR == 0 ? colL : colR;
+        const int colB = COLOUR == 0 ? colR : colL;
 
-        auto row_ptr = [&](const uint8_t *base, int row) { return base + (int64_t)row * half; };
-        auto down_of = [&](int row) { return row == L.Ly - 1 ? 0 : row + 1; };
-        // side byte of `row` for the edge lanes (parity p: 0 -> left byte, 1 -> right byte)
-        auto edge_side = [&](int row) -> uint32_t {
-            const int p = (colour + row) & 1;
-            if (p == 0 ? loadL : loadR) return row_ptr(oth, row)[p == 0 ? colL : colR];
-            return 0u;
-        };
         const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
-        uint4 U = *reinterpret_cast<const uint4 *>(row_ptr(oth, rowU) + col);
-        uint4 C = *reinterpret_cast<const uint4 *>(row_ptr(oth, row0) + col);
-        uint4 D = *reinterpret_cast<const uint4 *>(row_ptr(oth, down_of(row0)) + col);
-        uint4 Tq = *reinterpret_cast<const uint4 *>(row_ptr(tgt, row0) + col);
-        uint32_t side_edge = edge_side(row0);
+        const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, current even row
+        uint8_t *pt = tgt + (int64_t)row0 * half + col;           // target plane, current even row
+        uint4 U = ldg128(oth + (int64_t)rowU * half + col);
+        uint4 C = ldg128(po + col);
+        uint4 D = ldg128(po + half + col);
+        uint4 Ta = ldg128(pt), Tb = ldg128(pt + half);
+        uint32_t sideA = edgeA ? po[colA] : 0u;
+        uint32_t sideB = edgeB ? po[half + colB] : 0u;
+        uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
+        const uint32_t blk_step = (uint32_t)(half >> 3);
         Acc acc;
 
 #pragma unroll 1
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < R; r += 2) {
             const int row = row0 + r;
-            // prefetch the next row's inputs before working on this one
-            uint4 Dn = D, Tn = Tq;
-            uint32_t side_edge_n = 0;
-            if (r + 1 < R) {
-                Dn = *reinterpret_cast<const uint4 *>(row_ptr(oth, down_of(row + 1)) + col);
-                Tn = *reinterpret_cast<const uint4 *>(row_ptr(tgt, row + 1) + col);
-                side_edge_n = edge_side(row + 1);
+            // E = other row below the odd row; wraps only at the very last row of the lattice
+            const uint8_t *pe = (row + 2 == L.Ly) ? oth : po + 2 * (int64_t)half;
+            const uint4 E = ldg128(pe + col);
+            // prefetch the next trip's rows (the window slides by two rows)
+            uint4 Dn = D, Tan = Ta, Tbn = Tb;
+            uint32_t sideAn = 0, sideBn = 0;
+            if (r + 2 < R) {
+                Dn = ldg128(po + 3 * (int64_t)half + col);
+                Tan = ldg128(pt + 2 * (int64_t)half);
+                Tbn = ldg128(pt + 3 * (int64_t)half);
+                if (edgeA) sideAn = po[2 * (int64_t)half + colA];
+                if (edgeB) sideBn = po[3 * (int64_t)half + colB];
             }
-            const int p = (colour + row) & 1;   // x offset of the target sites in this row
-
-            // the two Philox blocks of this thread-row
-            const uint32_t blk = (uint32_t)(((int64_t)row * half + col) >> 3);
-            const Philox4 ra = philox4x32_10(blk, (uint32_t)t, c2, chain_id, seed_lo, seed_hi);
-            const Philox4 rb = philox4x32_10(blk + 1, (uint32_t)t, c2, chain_id, seed_lo, seed_hi);
-
-            // neighbour in the same row: other-plane byte j-1 (p == 0) or j+1 (p == 1)
-            uint32_t S[4];
-            if (p == 0) {
-                uint32_t side = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
-                if (loadL) side = side_edge;
-                S[0] = (C.x << 8) | side;
-                S[1] = __funnelshift_l(C.x, C.y, 8);
-                S[2] = __funnelshift_l(C.y, C.z, 8);
-                S[3] = __funnelshift_l(C.z, C.w, 8);
+            // even row: parity COLOUR
+            uint32_t sA, sB;
+            if (COLOUR == 0) {
+                sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
+                sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
             } else {
-                uint32_t side = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
-                if (loadR) side = side_edge;
-                S[0] = __funnelshift_r(C.x, C.y, 8);
-                S[1] = __funnelshift_r(C.y, C.z, 8);
-                S[2] = __funnelshift_r(C.z, C.w, 8);
-                S[3] = (C.w >> 8) | (side << 24);
+                sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
+                sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
             }
-            const uint32_t nup[4] = {U.x + D.x + C.x + S[0], U.y + D.y + C.y + S[1], U.z + D.z + C.z + S[2],
-                                     U.w + D.w + C.w + S[3]};
-            const uint32_t tw[4] = {Tq.x, Tq.y, Tq.z, Tq.w};
-            uint32_t nw[4];
-            bool tie = false;
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const uint32_t rlo = (w & 1) ? ((w < 2) ? ra.z : rb.z) : ((w < 2) ? ra.x : rb.x);
-                const uint32_t rhi = (w & 1) ? ((w < 2) ? ra.w : rb.w) : ((w < 2) ? ra.y : rb.y);
-                const uint32_t idx4 = tw[w] * 20u + nup[w] * 4u;     // byte b = 4 * (5 s + nup)
-                uint32_t F = 0;
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t thr = *reinterpret_cast<const uint32_t *>(
-                        reinterpret_cast<const char *>(thi) + byte_of(idx4, b));
-                    const uint32_t rr = (b < 2) ? rlo : rhi;
-                    const uint32_t h = (b & 1) ? (rr >> 16) : (rr & 0xffffu);
-                    if (h < thr) F |= 1u << (8 * b);
-                    tie |= (h == thr);
-                }
-                nw[w] = HEATBATH ? F : (tw[w] ^ F);
-            }
-            if (tie) {
-                // rare: settle with the low halves (plane 1) for the whole thread-row
-                const Philox4 la = philox4x32_10(blk, (uint32_t)t, c2lo, chain_id, seed_lo, seed_hi);
-                const Philox4 lb = philox4x32_10(blk + 1, (uint32_t)t, c2lo, chain_id, seed_lo, seed_hi);
-                const uint4 ex = row_exact<HEATBATH>(Tq, make_uint4(nup[0], nup[1], nup[2], nup[3]), thi, tlo, ra, rb,
-                                                     la, lb);
-                nw[0] = ex.x; nw[1] = ex.y; nw[2] = ex.z; nw[3] = ex.w;
-            }
+            if (edgeA) sA = sideA;
+            if (edgeB) sB = sideB;
+            const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
+                                                                 seed_hi, s_pair, s_thi, s_tlo, acc, active);
+            const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
+                                                                     seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
             if (active) {
-                uint32_t fsum = 0, ssum = 0, nsum = 0, snsum = 0;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const uint32_t Fc = nw[w] ^ tw[w];               // changed sites, 0x01 per byte
-                    fsum += Fc;
-                    if (TRACK) {
-                        const uint32_t SF = tw[w] & Fc;
-                        ssum += SF;
-                        nsum += nup[w] & (Fc * 255u);
-                        snsum += nup[w] & (SF * 255u);
-                    }
-                }
-                acc.flips = __dp4a(fsum, 0x01010101u, acc.flips);
-                if (TRACK) {
-                    acc.s = __dp4a(ssum, 0x01010101u, (uint32_t)acc.s);
-                    acc.n = __dp4a(nsum, 0x01010101u, (uint32_t)acc.n);
-                    acc.sn = __dp4a(snsum, 0x01010101u, (uint32_t)acc.sn);
-                }
-                *reinterpret_cast<uint4 *>(tgt + (int64_t)row * half + col) = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+                *reinterpret_cast<uint4 *>(pt) = Na;
+                *reinterpret_cast<uint4 *>(pt + half) = Nb;
             }
-            U = C; C = D; D = Dn; Tq = Tn; side_edge = side_edge_n;
+            U = D; C = E; D = Dn; Ta = Tan; Tb = Tbn; sideA = sideAn; sideB = sideBn;
+            po += 2 * (int64_t)half; pt += 2 * (int64_t)half; blk += 2 * blk_step;
         }
 
         // per-chain sums: dspin = 2 - 4 s, dpair = -8 s nup + 16 s + 4 nup - 8 per changed site
-        int nflip = warp_sum((int)acc.flips);
+        const int nflip = warp_sum((int)acc.flips);
         int dspin = 0, dpair = 0;
         if (TRACK) {
             const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
@@ -224,6 +275,58 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
     }
 }
 
+// _recompute_cached! for row-aligned 2-D Ising planes: one thread per 16-byte segment of the colour-0
+// plane.  With e in {0,1}: sum_<ij> s_i s_j = sum over colour-0 sites of (2 e0 - 1)(2 nup - 4)
+//   = 4 sum(e0 nup) - 2 sum(nup) - 8 sum(e0) + 4 (N/2),   sum s = 2 (sum e0 + sum e1) - N.
+__global__ void __launch_bounds__(256)
+k_recompute2d(LatView L, long long *__restrict__ sums, int64_t segs_per_chain)
+{
+    const int chain = blockIdx.y;
+    const int half = L.half, nseg = half >> 4;
+    const uint8_t *__restrict__ p0 = plane_ptr(L, chain, 0);
+    const uint8_t *__restrict__ p1 = plane_ptr(L, chain, 1);
+    long long e0n = 0, nsum = 0, e0 = 0, e1 = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < segs_per_chain;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(g / nseg), seg = (int)(g - (int64_t)row * nseg), col = seg << 4;
+        const int ru = row == 0 ? L.Ly - 1 : row - 1, rd = row == L.Ly - 1 ? 0 : row + 1;
+        const uint4 T = ldg128(p0 + (int64_t)row * half + col);
+        const uint4 C = ldg128(p1 + (int64_t)row * half + col);
+        const uint4 U = ldg128(p1 + (int64_t)ru * half + col);
+        const uint4 D = ldg128(p1 + (int64_t)rd * half + col);
+        uint32_t S[4];
+        if ((row & 1) == 0) {       // colour-0 sites of an even row sit at x = 2j: neighbours j-1, j
+            const uint32_t side = p1[(int64_t)row * half + ((seg == 0 ? half : col) - 1)];
+            S[0] = (C.x << 8) | side;
+            S[1] = __funnelshift_l(C.x, C.y, 8); S[2] = __funnelshift_l(C.y, C.z, 8); S[3] = __funnelshift_l(C.z, C.w, 8);
+        } else {
+            const uint32_t side = p1[(int64_t)row * half + (seg == nseg - 1 ? 0 : col + 16)];
+            S[0] = __funnelshift_r(C.x, C.y, 8); S[1] = __funnelshift_r(C.y, C.z, 8); S[2] = __funnelshift_r(C.z, C.w, 8);
+            S[3] = (C.w >> 8) | (side << 24);
+        }
+        const uint32_t tw[4] = {T.x, T.y, T.z, T.w}, cw[4] = {C.x, C.y, C.z, C.w};
+        const uint32_t nup[4] = {U.x + D.x + C.x + S[0], U.y + D.y + C.y + S[1], U.z + D.z + C.z + S[2], U.w + D.w + C.w + S[3]};
+        uint32_t a = 0, b = 0, c = 0, d = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            a = __dp4a(nup[w] & (tw[w] * 255u), 0x01010101u, a);
+            b = __dp4a(nup[w], 0x01010101u, b);
+            c = __dp4a(tw[w], 0x01010101u, c);
+            d = __dp4a(cw[w], 0x01010101u, d);
+        }
+        e0n += a; nsum += b; e0 += c; e1 += d;
+    }
+    e0n = warp_sum_ll(e0n); nsum = warp_sum_ll(nsum); e0 = warp_sum_ll(e0); e1 = warp_sum_ll(e1);
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
+        // the constant terms (+4 N/2 and -N) are added once by block 0 / warp 0
+        long long pair = 4 * e0n - 2 * nsum - 8 * e0, spin = 2 * (e0 + e1);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { pair += 4 * L.halfN; spin -= 2 * L.halfN; }
+        atomicAdd(o + SUM_PAIR, (unsigned long long)pair);
+        atomicAdd(o + SUM_SPIN, (unsigned long long)spin);
+    }
+}
+
 int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -238,8 +341,8 @@ int pick_rows_per_strip(int Ly, int want)
     return 2;
 }
 
-template <bool HEATBATH, bool TRACK>
-void launch_t(mcx_lattice *lat, int colour, uint64_t t)
+template <int COLOUR, bool HEATBATH, bool TRACK>
+void launch_t(mcx_lattice *lat, uint64_t t)
 {
     const LatView &L = lat->view;
     const int R = pick_rows_per_strip(L.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
@@ -247,36 +350,51 @@ void launch_t(mcx_lattice *lat, int colour, uint64_t t)
     const int nseg = L.half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
     const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
-    const int64_t nitems64 = (int64_t)blocks_per_chain * lat->nchains;
-    const int nitems = (int)nitems64;
-    const size_t smem = (size_t)lat->n_labels * kTableLen * 2 * sizeof(uint32_t);
-    auto kern = k_ising2d<HEATBATH, TRACK>;
+    const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
+    auto kern = k_ising2d<COLOUR, HEATBATH, TRACK>;
     static thread_local int resident = 0;
     if (!resident) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 0);
         if (resident < 1) resident = 1;
     }
     const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
     int grid = lat->ctx->sm_count * ctas_per_sm;
     if (grid > nitems) grid = nitems;
-    kern<<<grid, kThreads, smem, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->n_labels,
-                                                    lat->d_sums, (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t,
-                                                    colour, lat->first_chain, R, nstrips, blocks_per_chain, nitems);
+    kern<<<grid, kThreads, 0, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums,
+                                                 (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain, R,
+                                                 nstrips, blocks_per_chain, nitems);
     lat->ctx->launches++;
+}
+
+template <int COLOUR>
+void launch_c(mcx_lattice *lat, uint64_t t)
+{
+    const bool track = lat->track_sums;
+    if (lat->rule == MCX_HEATBATH) {
+        if (track) launch_t<COLOUR, true, true>(lat, t); else launch_t<COLOUR, true, false>(lat, t);
+    } else {
+        if (track) launch_t<COLOUR, false, true>(lat, t); else launch_t<COLOUR, false, false>(lat, t);
+    }
 }
 
 }  // namespace
 
+bool launch_recompute_ising2d(mcx_lattice *lat)
+{
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8) return false;
+    const int64_t segs = (int64_t)lat->view.Ly * (lat->view.half >> 4);
+    int64_t blocks = (segs + 255) / 256;
+    const int64_t cap = (int64_t)lat->ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_recompute2d<<<dim3((unsigned)blocks, (unsigned)lat->nchains), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_sums, segs);
+    lat->ctx->launches++;
+    return true;
+}
+
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8) return false;
-    if ((size_t)lat->n_labels * kTableLen * 8 > 40 * 1024) return false;
-    const bool track = lat->track_sums;
-    if (lat->rule == MCX_HEATBATH) {
-        if (track) launch_t<true, true>(lat, colour, t); else launch_t<true, false>(lat, colour, t);
-    } else {
-        if (track) launch_t<false, true>(lat, colour, t); else launch_t<false, false>(lat, colour, t);
-    }
+    if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
     return true;
 }
 

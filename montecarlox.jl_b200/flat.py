@@ -75,11 +75,18 @@ class DeviceFlat:
         check(lib().mcx_lattice_set_first_chain_id(sys.h_lat, alg.rng.chain))
         sys.set_rng(alg.rng.seed)
 
+    def close(self):
+        """Free the device mirror (idempotent).  Must happen before the lattice is destroyed; the
+        owning system calls this from its own finaliser."""
+        h, self.h = self.h, None
+        if h is not None:
+            try:
+                lib().mcx_flat_destroy(h)
+            except Exception:
+                pass
+
     def __del__(self):
-        try:
-            lib().mcx_flat_destroy(self.h)
-        except Exception:
-            pass
+        self.close()
 
     def push(self):
         lw = np.ascontiguousarray(self.tab.logweight_table.values, dtype=np.float64)

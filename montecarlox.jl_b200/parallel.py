@@ -308,12 +308,16 @@ class ReplicaExchange:
         self._sys.sync()
         return self._x_tensor().cpu().numpy().copy()
 
+    def close(self):
+        h, self._pt = self._pt, None
+        if h is not None:
+            try:
+                lib().mcx_pt_destroy(h)
+            except Exception:
+                pass
+
     def __del__(self):
-        try:
-            if self._pt is not None:
-                lib().mcx_pt_destroy(self._pt)
-        except Exception:
-            pass
+        self.close()        # self._sys (strong ref) keeps the lattice alive until here
 
 
 class _CudaArray:

@@ -42,11 +42,12 @@ class Context:
         check(lib().mcx_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
-    def __del__(self):
-        try:
-            lib().mcx_ctx_destroy(self.h)
-        except Exception:
-            pass
+    def close(self):
+        """Explicit teardown (parallel_backends.jl:104 finalize!).  Not done implicitly: lattices keep
+        raw pointers to their context, and interpreter shutdown destroys objects in no fixed order."""
+        h, self.h = self.h, None
+        if h is not None:
+            check(lib().mcx_ctx_destroy(h))
 
 
 def default_context(device=0):
@@ -81,6 +82,8 @@ class AbstractSpinSystem:
 
     def __del__(self):
         try:
+            for f in self.__dict__.get("_flat_cache", {}).values():
+                f.close()                      # device mirrors first: they point into the lattice
             lib().mcx_lattice_destroy(self.h_lat)
         except Exception:
             pass
