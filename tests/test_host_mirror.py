@@ -1,0 +1,122 @@
+"""CPU tests of the host-side mirror of the reference API (no GPU): PhiloxRNG, BinnedObject,
+ensembles, scalar accept!, replica-exchange helpers -- the known answers of SURVEY.md 8c again, this
+time through the product's Python layer, and agreement of the host rule tables / RNG with the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+import mcx_b200 as m
+
+
+def test_philox_matches_oracle_and_kat(oracle):
+    assert m.philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    r = m.PhiloxRNG(0x1234567890abcdef, chain=7)
+    o = oracle.Rng(0x1234567890abcdef, 7)
+    for tag, t, q in ((0, 5, 13), (3, 2 ** 40 + 9, 123456789), (0, 0, 0)):
+        r.position(tag, t, q)
+        o.position(tag, t, q)
+        assert r.rand() == o.rand() and r.rand_bool() == o.rand_bool() and r.rand() == o.rand()
+    assert m.exchange_u(99, 3, 17) == oracle.lib().mcxo_exchange_u(99, 3, 17)
+
+
+def test_rule_tables_match_oracle(oracle):
+    for model in (0, 1):
+        for rule in (0, 1, 2):
+            for nd in (1, 2, 3):
+                for beta, J, h, D in ((0.44, 1, 0, 0), (0.7, 1.0, 0.1, 0.2), (1.3, 2, 0, 0.5), (30.0, 1, 0, 0)):
+                    assert np.array_equal(m.build_table(model, rule, nd, beta, J, h, D),
+                                          oracle.build_table(model, rule, nd, beta, J, h, D))
+
+
+def test_binned_object():
+    # test/test_binned_objects.jl
+    bo = m.BinnedObject(range(0, 11, 2), 0.0)
+    assert bo.size == (6,)
+    bo[4] = 2.5
+    assert bo.values[2] == 2.5 and bo(4) == 2.5
+    with pytest.raises(IndexError):
+        bo[12]
+    c = m.BinnedObject([0.0, 1.0, 2.0, 3.0], 0.0)
+    c[1.2] = 7.0
+    assert c.values[1] == 7.0
+    assert m.get_centers(bo) == [0, 2, 4, 6, 8, 10]
+    assert m.BinnedObject(range(-128, 129, 4), 0.0)[-128] == 0.0
+    with pytest.raises(ValueError):
+        m.BinnedObject([0, 1, 3], 0.0)
+
+
+def test_scalar_accept_and_counters():
+    class Fixed:
+        def __init__(self, u):
+            self.u = u
+
+        def rand(self):
+            return self.u
+    a = m.Metropolis(Fixed(0.5), beta=1.0)
+    assert a.accept_(-1.0) is True and a.steps == 1 and a.accepted == 1      # log_ratio > 0: no draw needed
+    assert a.accept_(1.0) is False and a.steps == 2                          # exp(-1) = 0.37 < 0.5
+    assert a.accept_(0.5) is True                                            # exp(-0.5) = 0.61 > 0.5
+    assert m.acceptance_rate(a) == pytest.approx(2 / 3)
+    a.reset_()
+    assert a.steps == 0 and a.accepted == 0
+    g = m.Glauber(Fixed(0.49), beta=1.0)
+    assert g.accept_(0.0) is True and g.steps == 1                           # logistic(0) = 0.5
+    assert m.logistic(0.0) == 0.5 and abs(m.logistic(20.0) - 1) < 1e-8
+    with pytest.raises(ValueError):
+        m.BoltzmannEnsemble()
+    assert m.BoltzmannEnsemble(T=2.0).beta == 0.5
+
+
+def test_multicanonical_and_wang_landau_host():
+    # test/test_multicanonical.jl:16-48, test/test_wang_landau.jl:44-63
+    ens = m.MulticanonicalEnsemble(range(0, 4))
+    ens.histogram.values[:] = [0.2, 0.8, 1.1, 2.5]
+    lw0 = ens.logweight_table.values.copy()
+    ens.update_()
+    assert np.allclose(ens.logweight_table.values, lw0 - np.log([0.2, 0.8, 1.1, 2.5]))
+    alg = m.Multicanonical(m.PhiloxRNG(1), range(0, 4))
+    alg.rng.position(3, 0, 0)
+    n0 = alg.steps
+    with pytest.raises(IndexError):
+        alg.accept_(7, 1)
+    assert alg.steps == n0
+    assert alg.accept_(2, 2) in (True, False) and alg.ensemble.histogram.values.sum() == 1
+    wl = m.WangLandau(m.PhiloxRNG(2), range(0, 5), init=1.5, logf=0.25)
+    wl.rng.position(3, 0, 0)
+    assert wl.accept_(2, 2) is True and wl.ensemble.logweight_table[2] == 1.5 - 0.25
+    wl.ensemble.update_()
+    assert wl.ensemble.logf == 0.125
+
+
+def test_exchange_helpers():
+    # test/test_parallel_ensembles.jl:152-206
+    assert m.set_betas(4, 0.4, 1.0, "uniform") == [1.0, 0.8, 0.6, 0.4]
+    g = m.set_betas(5, 0.25, 2.0, "geometric")
+    assert g[0] == pytest.approx(2.0) and g[-1] == pytest.approx(0.25)
+    from mcx_b200.parallel import _resolve_pair
+    assert _resolve_pair(1, 0, 4) == (True, 1, 2) and _resolve_pair(2, 0, 4) == (True, 1, 1)
+    assert _resolve_pair(1, 1, 4) == (False, 0, 0) and _resolve_pair(3, 1, 4) == (True, 2, 2)
+    ai, aj = m.Metropolis(m.PhiloxRNG(21), beta=1.0), m.Metropolis(m.PhiloxRNG(22), beta=0.5)
+    assert abs(m.exchange_log_ratio(ai.ensemble, aj.ensemble, 0.0, -5.0) - 2.5) < 1e-12
+    assert m.attempt_exchange_pair_(ai, aj, 0.0, -5.0, 0.0) and ai.ensemble.beta == 0.5 and aj.ensemble.beta == 1.0
+    bi, bj = m.Metropolis(m.PhiloxRNG(23), beta=1.0), m.Metropolis(m.PhiloxRNG(24), beta=0.5)
+    assert not m.attempt_exchange_pair_(bi, bj, -5.0, 0.0, 1.0) and bi.ensemble.beta == 1.0
+    with pytest.raises(ValueError):
+        m.attempt_exchange_pair_(bi, bj, 0.0, 0.0, float("nan"))
+    with pytest.raises(ValueError):
+        m.ParallelTempering([1.0])
+    pt = m.ParallelTempering([1.0, 0.5], seed=77)
+    assert pt.size == 2 and list(pt.index()) == [1, 2] and pt.acceptance_rate() == 0.0
+    with pytest.raises(ValueError):
+        pt.update_([1.0])
+    # merge / distribute on two chains (test_parallel_ensembles.jl:96-113)
+    algs = [m.Multicanonical(m.PhiloxRNG(1, c), range(0, 4)) for c in range(2)]
+    algs[0].ensemble.histogram.values[:] = [1, 2, 3, 4]
+    algs[1].ensemble.histogram.values[:] = [4, 3, 2, 1]
+    pc = m.ParallelMulticanonical(m.ThreadsBackend(2), algs)
+    m.merge_histograms_(pc)
+    assert list(algs[0].ensemble.histogram.values) == [5, 5, 5, 5] and list(algs[1].ensemble.histogram.values) == [4, 3, 2, 1]
+    algs[0].ensemble.logweight_table.values[:] = [0.1, 0.2, 0.3, 0.4]
+    m.distribute_logweight_(pc)
+    assert list(algs[1].ensemble.logweight_table.values) == [0.1, 0.2, 0.3, 0.4]
