@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmcx_b200.so")
+LIB_PATH = os.environ.get("MCX_B200_LIB") or os.path.join(_HERE, "lib", "libmcx_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_ARGUMENT, ERR_BOUNDS, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = range(6)

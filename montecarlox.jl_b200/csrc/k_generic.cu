@@ -233,18 +233,21 @@ static dim3 site_grid(const mcx_lattice *lat, int64_t n, int threads)
 
 void launch_pack(mcx_lattice *lat)
 {
+    if (launch_pack_ising2d(lat)) return;
     k_pack<<<site_grid(lat, lat->N, 256), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_staging, lat->N);
     lat->ctx->launches++;
 }
 
 void launch_unpack(mcx_lattice *lat)
 {
+    if (launch_unpack_ising2d(lat)) return;
     k_unpack<<<site_grid(lat, lat->N, 256), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_staging, lat->N);
     lat->ctx->launches++;
 }
 
 void launch_init(mcx_lattice *lat, int mode, uint64_t seed)
 {
+    if (launch_init_ising2d(lat, mode, seed)) return;
     k_init<<<site_grid(lat, lat->N, 256), 256, 0, lat->ctx->stream>>>(
         lat->view, lat->N, mode, (uint32_t)seed, (uint32_t)(seed >> 32), lat->first_chain);
     lat->ctx->launches++;

@@ -64,7 +64,11 @@ __device__ __noinline__ uint4 row_exact(uint4 tq, uint4 nq, const uint32_t *thi,
 
 __device__ __forceinline__ uint32_t shr1_fma(uint32_t w)
 {
+#ifdef MCX_OPT_SHF
+    return w >> 1;
+#else
     return __umulhi(w, 0x80000000u);      // w >> 1 on the FMA pipe (the ALU pipe is the busy one)
+#endif
 }
 
 // One thread-row: 16 target sites (tq), neighbour rows U (above), C (same row, other plane),
@@ -106,8 +110,16 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
         const uint32_t ttB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (idx4 >> 16));
         const uint32_t hA = (shr1_fma(rw[2 * w]) & 0x7fff7fffu) | 0x80008000u;
         const uint32_t hB = (shr1_fma(rw[2 * w + 1]) & 0x7fff7fffu) | 0x80008000u;
+#ifndef MCX_OPT_ALUSUB
+        uint32_t rA, rB, qA, qB;   // subtractions issued as IMAD: measured +3% (the ALU pipe is the contended one)
+        asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rA) : "r"(ttA), "r"(hA));
+        asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rB) : "r"(ttB), "r"(hB));
+        asm("mad.lo.u32 %0, %1, 1, 0xfffeffff;" : "=r"(qA) : "r"(rA));
+        asm("mad.lo.u32 %0, %1, 1, 0xfffeffff;" : "=r"(qB) : "r"(rB));
+#else
         const uint32_t rA = hA - ttA, rB = hB - ttB;
         const uint32_t qA = rA - 0x00010001u, qB = rB - 0x00010001u;
+#endif
         tie |= (rA & ~qA) | (rB & ~qB);
         const uint32_t P = __byte_perm(rA, rB, 0x7531);          // bit 7 of byte b: site 4w+b NOT accepted
         const uint32_t F = (~P & 0x80808080u) >> 7;              // 0x01 per accepted site
@@ -145,8 +157,8 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
 
 __device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
-template <int COLOUR, bool HEATBATH, bool TRACK>
-__global__ void __launch_bounds__(kThreads, 5)
+template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(kThreads, MINB)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
           const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
           uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
@@ -209,10 +221,14 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         uint8_t *pt = tgt + (int64_t)row0 * half + col;           // target plane, current even row
         uint4 U = ldg128(oth + (int64_t)rowU * half + col);
         uint4 C = ldg128(po + col);
-        uint4 D = ldg128(po + half + col);
-        uint4 Ta = ldg128(pt), Tb = ldg128(pt + half);
-        uint32_t sideA = edgeA ? po[colA] : 0u;
-        uint32_t sideB = edgeB ? po[half + colB] : 0u;
+        uint4 D, Ta, Tb;
+        uint32_t sideA = 0, sideB = 0;
+        if (PREFETCH) {
+            D = ldg128(po + half + col);
+            Ta = ldg128(pt); Tb = ldg128(pt + half);
+            if (edgeA) sideA = po[colA];
+            if (edgeB) sideB = po[half + colB];
+        }
         uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
         const uint32_t blk_step = (uint32_t)(half >> 3);
         Acc acc;
@@ -223,17 +239,25 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             // E = other row below the odd row; wraps only at the very last row of the lattice
             const uint8_t *pe = (row + 2 == L.Ly) ? oth : po + 2 * (int64_t)half;
             const uint4 E = ldg128(pe + col);
-            // prefetch the next trip's rows (the window slides by two rows)
-            uint4 Dn = D, Tan = Ta, Tbn = Tb;
+            uint4 Dn, Tan, Tbn;
             uint32_t sideAn = 0, sideBn = 0;
-            if (r + 2 < R) {
-                Dn = ldg128(po + 3 * (int64_t)half + col);
-                Tan = ldg128(pt + 2 * (int64_t)half);
-                Tbn = ldg128(pt + 3 * (int64_t)half);
-                if (edgeA) sideAn = po[2 * (int64_t)half + colA];
-                if (edgeB) sideBn = po[3 * (int64_t)half + colB];
+            if (PREFETCH) {
+                // prefetch the next trip's rows (the window slides by two rows)
+                Dn = D; Tan = Ta; Tbn = Tb;
+                if (r + 2 < R) {
+                    Dn = ldg128(po + 3 * (int64_t)half + col);
+                    Tan = ldg128(pt + 2 * (int64_t)half);
+                    Tbn = ldg128(pt + 3 * (int64_t)half);
+                    if (edgeA) sideAn = po[2 * (int64_t)half + colA];
+                    if (edgeB) sideBn = po[3 * (int64_t)half + colB];
+                }
+            } else {
+                // this trip's rows; their latency is covered by the Philox rounds below
+                D = ldg128(po + half + col);
+                Ta = ldg128(pt); Tb = ldg128(pt + half);
+                if (edgeA) sideA = po[colA];
+                if (edgeB) sideB = po[half + colB];
             }
-            // even row: parity COLOUR
             uint32_t sA, sB;
             if (COLOUR == 0) {
                 sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
@@ -252,11 +276,168 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
                 *reinterpret_cast<uint4 *>(pt) = Na;
                 *reinterpret_cast<uint4 *>(pt + half) = Nb;
             }
-            U = D; C = E; D = Dn; Ta = Tan; Tb = Tbn; sideA = sideAn; sideB = sideBn;
+            U = D; C = E;
+            if (PREFETCH) { D = Dn; Ta = Tan; Tb = Tbn; sideA = sideAn; sideB = sideBn; }
             po += 2 * (int64_t)half; pt += 2 * (int64_t)half; blk += 2 * blk_step;
         }
 
         // per-chain sums: dspin = 2 - 4 s, dpair = -8 s nup + 16 s + 4 nup - 8 per changed site
+        const int nflip = warp_sum((int)acc.flips);
+        int dspin = 0, dpair = 0;
+        if (TRACK) {
+            const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
+            dspin = 2 * nflip - 4 * ss;
+            dpair = -8 * sn + 16 * ss + 4 * nn_ - 8 * nflip;
+        }
+        if (lane == 0) {
+            unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
+            if (nflip) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nflip);
+            if (TRACK) {
+                if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
+                if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Same half-sweep with the row loads staged through shared memory by cp.async (LDGSTS): every
+// thread keeps a private ring of STAGES trips (4 x 16 B per trip: the two new other-plane rows and
+// the two target rows, plus one 4-byte word holding the out-of-segment neighbour byte for edge
+// lanes), issued STAGES trips ahead.  The copies never occupy registers while in flight, so the
+// DRAM latency is covered without the register cost of a software prefetch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, int STAGES>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_ising2d_ring(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
+               const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
+               uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
+{
+    __shared__ uint32_t s_pair[kPairWords];
+    __shared__ uint32_t s_thi[kTableLen], s_tlo[kTableLen];
+    __shared__ uint4 s_ring[STAGES][4][kThreads];        // [stage][D, E, Ta, Tb][thread]
+    __shared__ uint32_t s_side[STAGES][2][kThreads];     // [stage][A, B][thread]
+    int cur_label = -1;
+
+    const int half = L.half;
+    const int nseg = half >> 4;
+    const int64_t G = (int64_t)nstrips * nseg;
+    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const uint32_t t_lo = (uint32_t)t;
+    const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
+    const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
+    const int ntrips = R >> 1;
+
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int chain = item / blocks_per_chain;
+        const int label = labels[chain];
+        if (label != cur_label) {
+            __syncthreads();
+            if (threadIdx.x < kTableLen) {
+                s_thi[threadIdx.x] = thi_g[label * kTableLen + threadIdx.x];
+                s_tlo[threadIdx.x] = tlo_g[label * kTableLen + threadIdx.x];
+            }
+            if (threadIdx.x < kTableLen * kTableLen) {
+                const int i1 = threadIdx.x / kTableLen, i0 = threadIdx.x - i1 * kTableLen;
+                const uint32_t a = min(thi_g[label * kTableLen + i0] >> 1, 0x7fffu);
+                const uint32_t b = min(thi_g[label * kTableLen + i1] >> 1, 0x7fffu);
+                s_pair[i1 * kPairRowWords + i0] = a | (b << 16);
+            }
+            __syncthreads();
+            cur_label = label;
+        }
+        const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
+        const bool active = g0 < G;
+        const int64_t g = active ? g0 : G - 1;
+        const int strip = (int)(g / nseg);
+        const int seg = (int)(g - (int64_t)strip * nseg);
+        const int row0 = strip * R;                               // even
+        const uint32_t chain_id = first_chain + (uint32_t)chain;
+
+        uint8_t *tgt = plane_ptr(L, chain, COLOUR);
+        const uint8_t *__restrict__ oth = plane_ptr(L, chain, COLOUR ^ 1);
+        const int col = seg << 4;
+        const int colL = (seg == 0 ? half : col) - 1;
+        const int colR = (seg == nseg - 1) ? 0 : col + 16;
+        const bool loadL = (lane == 0) || (seg == 0);
+        const bool loadR = (lane == 31) || (seg == nseg - 1);
+        const bool edgeA = COLOUR == 0 ? loadL : loadR;
+        const bool edgeB = COLOUR == 0 ? loadR : loadL;
+        const int colA = COLOUR == 0 ? colL : colR;
+        const int colB = COLOUR == 0 ? colR : colL;
+
+        const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
+        const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, row of the current trip
+        uint8_t *pt = tgt + (int64_t)row0 * half + col;
+        // stage trip k (rows row0 + 2k, row0 + 2k + 1) into ring slot k % STAGES
+        auto issue = [&](int k) {
+            if (k < ntrips) {
+                const int slot = k % STAGES;
+                const int row = row0 + 2 * k;
+                const uint8_t *pk = oth + (int64_t)row * half;
+                const uint8_t *pe = (row + 2 == L.Ly) ? oth : pk + 2 * (int64_t)half;
+                cp_async16(&s_ring[slot][0][tid], pk + half + col);
+                cp_async16(&s_ring[slot][1][tid], pe + col);
+                cp_async16(&s_ring[slot][2][tid], tgt + (int64_t)row * half + col);
+                cp_async16(&s_ring[slot][3][tid], tgt + (int64_t)(row + 1) * half + col);
+                if (edgeA) cp_async4(&s_side[slot][0][tid], pk + (colA & ~3));
+                if (edgeB) cp_async4(&s_side[slot][1][tid], pk + half + (colB & ~3));
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < STAGES; ++k) issue(k);
+        uint4 U = ldg128(oth + (int64_t)rowU * half + col);
+        uint4 C = ldg128(po + col);
+        uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
+        const uint32_t blk_step = (uint32_t)(half >> 3);
+        Acc acc;
+
+#pragma unroll 1
+        for (int k = 0; k < ntrips; ++k) {
+            const int slot = k % STAGES;
+            cp_async_wait<STAGES - 1>();
+            const uint4 D = s_ring[slot][0][tid];
+            const uint4 E = s_ring[slot][1][tid];
+            const uint4 Ta = s_ring[slot][2][tid];
+            const uint4 Tb = s_ring[slot][3][tid];
+            uint32_t sA, sB;
+            if (COLOUR == 0) {
+                sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
+                sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
+            } else {
+                sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
+                sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
+            }
+            if (edgeA) sA = (s_side[slot][0][tid] >> (8 * (colA & 3))) & 0xffu;
+            if (edgeB) sB = (s_side[slot][1][tid] >> (8 * (colB & 3))) & 0xffu;
+            issue(k + STAGES);                                   // refill the slot just consumed
+            const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
+                                                                 seed_hi, s_pair, s_thi, s_tlo, acc, active);
+            const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
+                                                                     seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
+            if (active) {
+                *reinterpret_cast<uint4 *>(pt) = Na;
+                *reinterpret_cast<uint4 *>(pt + half) = Nb;
+            }
+            U = D; C = E;
+            pt += 2 * (int64_t)half; blk += 2 * blk_step;
+        }
+        cp_async_wait<0>();
+
         const int nflip = warp_sum((int)acc.flips);
         int dspin = 0, dpair = 0;
         if (TRACK) {
@@ -327,6 +508,83 @@ k_recompute2d(LatView L, long long *__restrict__ sums, int64_t segs_per_chain)
     }
 }
 
+// Layout conversion for row-aligned 2-D Ising lattices: one thread moves 32 consecutive x-sites of a
+// row (two 128-bit words of host-order spins) to/from 16 bytes of each colour plane.
+// Even x of row y belongs to colour y & 1, odd x to the other colour, both at plane byte x >> 1.
+__global__ void __launch_bounds__(256)
+k_pack2d(LatView L, const int8_t *__restrict__ staging, int64_t N, int64_t segs_per_chain)
+{
+    const int chain = blockIdx.y;
+    const int nseg = L.half >> 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < segs_per_chain; g += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(g / nseg), seg = (int)(g - (int64_t)row * nseg);
+        const uint4 *src = reinterpret_cast<const uint4 *>(staging + (int64_t)chain * N + (int64_t)row * L.Lx + seg * 32);
+        const uint4 a = src[0], b = src[1];
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t ev[4], od[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e0 = (~w[2 * k] >> 7) & 0x01010101u, e1 = (~w[2 * k + 1] >> 7) & 0x01010101u;   // +1 -> 1, -1 -> 0
+            ev[k] = __byte_perm(e0, e1, 0x6420);
+            od[k] = __byte_perm(e0, e1, 0x7531);
+        }
+        const int ce = row & 1;
+        *reinterpret_cast<uint4 *>(plane_ptr(L, chain, ce) + (int64_t)row * L.half + seg * 16) = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+        *reinterpret_cast<uint4 *>(plane_ptr(L, chain, ce ^ 1) + (int64_t)row * L.half + seg * 16) = make_uint4(od[0], od[1], od[2], od[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack2d(LatView L, int8_t *__restrict__ staging, int64_t N, int64_t segs_per_chain)
+{
+    const int chain = blockIdx.y;
+    const int nseg = L.half >> 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < segs_per_chain; g += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(g / nseg), seg = (int)(g - (int64_t)row * nseg);
+        const int ce = row & 1;
+        const uint4 e = ldg128(plane_ptr(L, chain, ce) + (int64_t)row * L.half + seg * 16);
+        const uint4 o = ldg128(plane_ptr(L, chain, ce ^ 1) + (int64_t)row * L.half + seg * 16);
+        const uint32_t ev[4] = {e.x, e.y, e.z, e.w}, od[4] = {o.x, o.y, o.z, o.w};
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t lo = __byte_perm(ev[k], od[k], 0x5140), hi = __byte_perm(ev[k], od[k], 0x7362);
+            w[2 * k] = (lo ^ 0x01010101u) * 0xFEu + 0x01010101u;        // 1 -> 0x01 (+1), 0 -> 0xFF (-1)
+            w[2 * k + 1] = (hi ^ 0x01010101u) * 0xFEu + 0x01010101u;
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(staging + (int64_t)chain * N + (int64_t)row * L.Lx + seg * 32);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// init!(sys, mode; rng): the 32 sites of a thread are exactly one word of the INIT stream
+__global__ void __launch_bounds__(256)
+k_init2d(LatView L, int mode, uint32_t seed_lo, uint32_t seed_hi, uint32_t first_chain, int64_t segs_per_chain)
+{
+    const int chain = blockIdx.y;
+    const int nseg = L.half >> 4;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < segs_per_chain; g += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(g / nseg), seg = (int)(g - (int64_t)row * nseg);
+        uint32_t bits = mode == MCX_INIT_UP ? 0xffffffffu : 0u;
+        if (mode == MCX_INIT_RANDOM) {
+            const int64_t i = (int64_t)row * L.Lx + seg * 32;
+            const Philox4 p = stream_block(seed_lo, seed_hi, first_chain + chain, TAG_INIT, 0, (uint32_t)(i >> 7), 0);
+            const int w = (int)((i >> 5) & 3);
+            bits = w == 0 ? p.x : w == 1 ? p.y : w == 2 ? p.z : p.w;
+        }
+        uint32_t ev[4] = {0, 0, 0, 0}, od[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            ev[k >> 2] |= ((bits >> (2 * k)) & 1u) << (8 * (k & 3));
+            od[k >> 2] |= ((bits >> (2 * k + 1)) & 1u) << (8 * (k & 3));
+        }
+        const int ce = row & 1;
+        *reinterpret_cast<uint4 *>(plane_ptr(L, chain, ce) + (int64_t)row * L.half + seg * 16) = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+        *reinterpret_cast<uint4 *>(plane_ptr(L, chain, ce ^ 1) + (int64_t)row * L.half + seg * 16) = make_uint4(od[0], od[1], od[2], od[3]);
+    }
+}
+
 int env_int(const char *name, int dflt)
 {
     const char *v = getenv(name);
@@ -341,8 +599,8 @@ int pick_rows_per_strip(int Ly, int want)
     return 2;
 }
 
-template <int COLOUR, bool HEATBATH, bool TRACK>
-void launch_t(mcx_lattice *lat, uint64_t t)
+template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
+void launch_v(mcx_lattice *lat, uint64_t t)
 {
     const LatView &L = lat->view;
     const int R = pick_rows_per_strip(L.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
@@ -351,7 +609,7 @@ void launch_t(mcx_lattice *lat, uint64_t t)
     const int64_t G = (int64_t)nstrips * nseg;
     const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
     const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
-    auto kern = k_ising2d<COLOUR, HEATBATH, TRACK>;
+    auto kern = k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH>;
     static thread_local int resident = 0;
     if (!resident) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 0);
@@ -366,6 +624,52 @@ void launch_t(mcx_lattice *lat, uint64_t t)
     lat->ctx->launches++;
 }
 
+template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, int STAGES>
+void launch_ring(mcx_lattice *lat, uint64_t t)
+{
+    const LatView &L = lat->view;
+    const int R = pick_rows_per_strip(L.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
+    const int nstrips = L.Ly / R;
+    const int nseg = L.half >> 4;
+    const int64_t G = (int64_t)nstrips * nseg;
+    const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
+    const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
+    auto kern = k_ising2d_ring<COLOUR, HEATBATH, TRACK, MINB, STAGES>;
+    static thread_local int resident = 0;
+    if (!resident) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 0);
+        if (resident < 1) resident = 1;
+    }
+    const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
+    int grid = lat->ctx->sm_count * ctas_per_sm;
+    if (grid > nitems) grid = nitems;
+    kern<<<grid, kThreads, 0, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums,
+                                                 (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain, R,
+                                                 nstrips, blocks_per_chain, nitems);
+    lat->ctx->launches++;
+}
+
+// MCX_VARIANT (tuning hook): 0 = 5 CTAs/SM + register prefetch, 1 = 6 + prefetch, 2 = 8 + prefetch,
+// 3 = 6, loads at the top of the trip (default), 4 = 8 likewise, 5..8 = cp.async ring
+// (6 CTAs x 2 stages, 6 x 3, 8 x 2, 5 x 3)
+template <int COLOUR, bool HEATBATH, bool TRACK>
+void launch_t(mcx_lattice *lat, uint64_t t)
+{
+    const int variant = env_int("MCX_VARIANT", 3);
+    switch (variant) {
+    case 0: launch_v<COLOUR, HEATBATH, TRACK, 5, true>(lat, t); break;
+    case 1: launch_v<COLOUR, HEATBATH, TRACK, 6, true>(lat, t); break;
+    case 2: launch_v<COLOUR, HEATBATH, TRACK, 8, true>(lat, t); break;
+    case 4: launch_v<COLOUR, HEATBATH, TRACK, 8, false>(lat, t); break;
+    case 5: launch_ring<COLOUR, HEATBATH, TRACK, 6, 2>(lat, t); break;
+    case 6: launch_ring<COLOUR, HEATBATH, TRACK, 6, 3>(lat, t); break;
+    case 7: launch_ring<COLOUR, HEATBATH, TRACK, 8, 2>(lat, t); break;
+    case 8: launch_ring<COLOUR, HEATBATH, TRACK, 5, 3>(lat, t); break;
+    default: launch_v<COLOUR, HEATBATH, TRACK, 6, false>(lat, t); break;
+    }
+}
+
 template <int COLOUR>
 void launch_c(mcx_lattice *lat, uint64_t t)
 {
@@ -378,6 +682,47 @@ void launch_c(mcx_lattice *lat, uint64_t t)
 }
 
 }  // namespace
+
+static dim3 seg_grid(const mcx_lattice *lat, int64_t segs)
+{
+    int64_t blocks = (segs + 255) / 256;
+    const int64_t cap = (int64_t)lat->ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    return dim3((unsigned)blocks, (unsigned)lat->nchains);
+}
+
+static bool is_fast2d(const mcx_lattice *lat)
+{
+    return lat->fast2d && lat->model == MCX_ISING && lat->storage == MCX_STORAGE_INT8;
+}
+
+bool launch_pack_ising2d(mcx_lattice *lat)
+{
+    if (!is_fast2d(lat)) return false;
+    const int64_t segs = (int64_t)lat->view.Ly * (lat->view.half >> 4);
+    k_pack2d<<<seg_grid(lat, segs), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_staging, lat->N, segs);
+    lat->ctx->launches++;
+    return true;
+}
+
+bool launch_unpack_ising2d(mcx_lattice *lat)
+{
+    if (!is_fast2d(lat)) return false;
+    const int64_t segs = (int64_t)lat->view.Ly * (lat->view.half >> 4);
+    k_unpack2d<<<seg_grid(lat, segs), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_staging, lat->N, segs);
+    lat->ctx->launches++;
+    return true;
+}
+
+bool launch_init_ising2d(mcx_lattice *lat, int mode, uint64_t seed)
+{
+    if (!is_fast2d(lat)) return false;
+    const int64_t segs = (int64_t)lat->view.Ly * (lat->view.half >> 4);
+    k_init2d<<<seg_grid(lat, segs), 256, 0, lat->ctx->stream>>>(lat->view, mode, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                lat->first_chain, segs);
+    lat->ctx->launches++;
+    return true;
+}
 
 bool launch_recompute_ising2d(mcx_lattice *lat)
 {

@@ -69,7 +69,10 @@ void launch_sweep_generic(mcx_lattice *lat, int colour, uint64_t t);
 
 // k_ising2d.cu
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t);   // false: shape not supported
-bool launch_recompute_ising2d(mcx_lattice *lat);                        // false: shape not supported
+bool launch_recompute_ising2d(mcx_lattice *lat);
+bool launch_pack_ising2d(mcx_lattice *lat);
+bool launch_unpack_ising2d(mcx_lattice *lat);
+bool launch_init_ising2d(mcx_lattice *lat, int mode, uint64_t seed);                        // false: shape not supported
 
 // k_pt.cu
 void launch_pt_publish(mcx_pt *pt);

@@ -498,6 +498,53 @@ double mcxo_baseline_random_site(int L, double beta, int nchains, int64_t sweeps
     return (double)(ts1.tv_sec - ts0.tv_sec) + 1e-9 * (double)(ts1.tv_nsec - ts0.tv_nsec);
 }
 
+/* Per-chain time averages of e = E/N, |m|, m^2, m^4 from the reference's own loop (random site,
+ * xoshiro256++, exp per uphill attempt), measured every `interval` sweeps after `therm` sweeps.
+ * This stands in for "the reference's Xoshiro runs" in the statistical parity tests.
+ * out is [nchains][4]. */
+typedef struct { int L; double beta; int64_t therm, sweeps, interval; uint64_t seed; int c0, c1; double *out; } stats_job;
+
+static void *stats_worker(void *arg)
+{
+    stats_job *j = (stats_job *)arg;
+    int64_t dims[2] = { j->L, j->L };
+    for (int c = j->c0; c < j->c1; ++c) {
+        mcxo_system *s = mcxo_system_create(MCXO_ISING, 2, dims, 1.0, 0.0, 0.0);
+        mcxo_xoshiro x;
+        mcxo_system_init_random(s, j->seed, (uint32_t)c);
+        mcxo_xoshiro_seed(&x, j->seed * 7919u + (uint64_t)c);
+        mcxo_alg a = { MCXO_METROPOLIS, j->beta, 0, 0 };
+        const int64_t N = s->N;
+        mcxo_sweep_random_site(s, &a, &x, N * j->therm, 0);
+        double se = 0, sm = 0, sm2 = 0, sm4 = 0; int64_t n = 0;
+        for (int64_t sw = 0; sw < j->sweeps; sw += j->interval) {
+            mcxo_sweep_random_site(s, &a, &x, N * j->interval, 0);
+            double m = (double)s->sum_spins / (double)N, e = -s->sum_pair / (double)N;
+            se += e; sm += fabs(m); sm2 += m * m; sm4 += m * m * m * m; n++;
+        }
+        j->out[4 * c + 0] = se / n; j->out[4 * c + 1] = sm / n; j->out[4 * c + 2] = sm2 / n; j->out[4 * c + 3] = sm4 / n;
+        mcxo_system_destroy(s);
+    }
+    return 0;
+}
+
+void mcxo_stats_random_site(int L, double beta, int nchains, int64_t therm, int64_t sweeps, int64_t interval,
+                            int nthreads, uint64_t seed, double *out)
+{
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > nchains) nthreads = nchains;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    stats_job *jobs = (stats_job *)malloc(sizeof(stats_job) * (size_t)nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        stats_job jb = { L, beta, therm, sweeps, interval, seed, (int)((int64_t)nchains * t / nthreads),
+                         (int)((int64_t)nchains * (t + 1) / nthreads), out };
+        jobs[t] = jb;
+        pthread_create(&th[t], 0, stats_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+    free(th); free(jobs);
+}
+
 /* Lean variant of the same loop for lattices whose 32 B/site neighbour table (ising.jl:436,
  * nbr4::Vector{NTuple{4,Int}}) would not fit comfortably in host memory (L = 16384: 8.6 GB):
  * identical algorithm and draws, neighbours computed arithmetically instead of looked up.

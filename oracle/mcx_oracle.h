@@ -107,6 +107,10 @@ void mcxo_sweep_random_site(mcxo_system *s, mcxo_alg *a, mcxo_xoshiro *x, int64_
 double mcxo_baseline_random_site(int L, double beta, int nchains, int64_t sweeps, int nthreads,
                                  int use_table, uint64_t seed, double *mean_abs_m, double *mean_e);
 
+/* per-chain averages of e, |m|, m^2, m^4 from the reference's random-site loop (out: [nchains][4]) */
+void mcxo_stats_random_site(int L, double beta, int nchains, int64_t therm, int64_t sweeps, int64_t interval,
+                            int nthreads, uint64_t seed, double *out);
+
 /* lean multi-chain baseline for very large L (neighbours computed, not tabulated) */
 double mcxo_baseline_lean(int L, double beta, int nchains, int64_t nattempts, int use_table, uint64_t seed,
                           double *accept_rate);

@@ -97,6 +97,7 @@ def lib():
     L.mcxo_xoshiro_seed.argtypes = [C.POINTER(_Xo), u64]
     L.mcxo_baseline_random_site.argtypes = [ci, dbl, ci, i64, ci, ci, u64, pd, pd]
     L.mcxo_baseline_random_site.restype = dbl
+    L.mcxo_stats_random_site.argtypes = [ci, dbl, ci, i64, i64, i64, ci, u64, pd]
     L.mcxo_baseline_lean.argtypes = [ci, dbl, ci, i64, ci, u64, pd]
     L.mcxo_baseline_lean.restype = dbl
     L.mcxo_table_len.argtypes = [ci, ci, ci]
@@ -303,3 +304,11 @@ def baseline_lean(L, beta, nchains, nattempts, use_table=False, seed=42):
     r = C.c_double()
     secs = lib().mcxo_baseline_lean(L, beta, nchains, nattempts, int(use_table), seed, C.byref(r))
     return secs, r.value
+
+
+def stats_random_site(L, beta, nchains, therm, sweeps, interval, nthreads=8, seed=42):
+    """[nchains, 4] per-chain averages of (e, |m|, m^2, m^4) from the reference's random-site loop."""
+    out = np.zeros((nchains, 4), dtype=np.float64)
+    lib().mcxo_stats_random_site(L, beta, nchains, therm, sweeps, interval, nthreads, seed,
+                                 out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out

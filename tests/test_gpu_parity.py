@@ -66,8 +66,11 @@ def test_ising2d_bit_exact(m, oracle, L, rule):
 def test_fast_kernel_equals_generic_kernel(m, L):
     """same trajectories from the vectorised and the generic kernels, any strip height"""
     outs = []
-    for env in ({"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}):
-        for k in ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP"):
+    keys = ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP", "MCX_VARIANT")
+    envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
+    envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in range(9) for r in ("4", "16")]
+    for env in envs:
+        for k in keys:
             os.environ.pop(k, None)
         os.environ.update(env)
         sys_ = m.Ising([L, L])
@@ -75,7 +78,7 @@ def test_fast_kernel_equals_generic_kernel(m, L):
         sys_.init_("random", rng=alg.rng)
         m.sweep_(sys_, alg, 10)
         outs.append((sys_.spins.copy(), sys_.pair_sum(), sys_.magnetization(), alg.accepted))
-    for k in ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP"):
+    for k in keys:
         os.environ.pop(k, None)
     for o in outs[1:]:
         assert np.array_equal(o[0], outs[0][0]) and o[1:] == outs[0][1:]
