@@ -128,6 +128,11 @@ int32_t mcx_get_rng(mcx_lattice *lat, uint64_t *seed, uint64_t *next_sweep);
  * (docs/src/examples/spin_systems/pt_Ising2D.jl:52-57) in checkerboard order.  Asynchronous. */
 int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps);
 
+/* measure!(measurements, sys, i) with an interval schedule (src/measurements/measurements.jl:192-200)
+ * without a host round trip per measurement: nmeasure x (interval sweeps, snapshot of the sums).
+ * out is int64 [nmeasure][nchains][4] = {pair_sum, spin_sum, spin2_sum, accepted}; synchronises. */
+int32_t mcx_sweep_series(mcx_lattice *lat, int64_t nmeasure, int64_t interval, int64_t *out);
+
 /* cached sums per chain (any pointer may be NULL), synchronises:
  *   pair_sum  = sum_<ij> s_i s_j (unweighted; sys.sum_pair_interactions / J)   ising.jl:90
  *   spin_sum  = sys.sum_spins, spin2_sum = sys.sum_spins2                       blume_capel.jl:124-125
@@ -166,6 +171,10 @@ int32_t mcx_pt_exchange(mcx_pt *pt);
 int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices /*[n] 1-based*/, int64_t *steps /*[n-1]*/,
                      int64_t *accepted /*[n-1]*/, int64_t *stage, int64_t *round);
 int32_t mcx_pt_reset(mcx_pt *pt);
+/* restore a checkpointed ladder: rx.indices (1-based), rx.steps, rx.accepted, rx.stage and the
+ * exchange round of the EXCHANGE stream (checkpointing.jl:95-101 restoring replica_exchange.jl:13-19) */
+int32_t mcx_pt_set_state(mcx_pt *pt, const int64_t *indices, const int64_t *steps, const int64_t *accepted,
+                         int64_t stage, int64_t round);
 
 /* ---- flat-histogram ensembles ---------------------------------------------------------------
  * Multicanonical(rng, bins) algorithms/multicanonical.jl:9, WangLandau(rng, bins; logf)

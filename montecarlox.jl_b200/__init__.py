@@ -11,6 +11,10 @@ from .ensembles import (BoltzmannEnsemble, FunctionEnsemble, MulticanonicalEnsem
                         logweight)
 from .flat import (DeviceFlat, PairBoltzmannSpin2Ensemble, ParallelMulticanonical, distribute_logweight_,
                    flat_for, merge_histograms_)
+from .ising2d_exact import distribution_exact_ising2D, distribution_from_logdos, logdos_exact_ising2D
+from .checkpointing import CheckpointSession, checkpoint_, finalize_, init_checkpoint, restore_checkpoint
+from .measurements import (integrated_autocorrelation_time, integrated_autocorrelation_times,
+                           optimize_exchange_interval_, sweep_series_, tau_int)
 from .parallel import (GPUBackend, ParallelChains, ParallelTempering, ReplicaExchange, ThreadsBackend,
                        attempt_exchange_pair_, exchange_log_ratio, partition_slots, philox_family, set_betas,
                        update_)

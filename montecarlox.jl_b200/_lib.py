@@ -56,6 +56,7 @@ SIGNATURES = {
     "mcx_set_rng": (_i32, [_vp, _u64, _u64]),
     "mcx_get_rng": (_i32, [_vp, _P(_u64), _P(_u64)]),
     "mcx_sweep": (_i32, [_vp, _i64]),
+    "mcx_sweep_series": (_i32, [_vp, _i64, _i64, _vp]),
     "mcx_observables": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mcx_energies": (_i32, [_vp, _vp]),
     "mcx_reset_counters": (_i32, [_vp]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "mcx_pt_exchange": (_i32, [_vp]),
     "mcx_pt_state": (_i32, [_vp, _vp, _vp, _vp, _P(_i64), _P(_i64)]),
     "mcx_pt_reset": (_i32, [_vp]),
+    "mcx_pt_set_state": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64]),
     "mcx_flat_create": (_i32, [_vp, _i32, _i32, _i64, _i64, _i64, _dbl, _i32, _P(_vp)]),
     "mcx_flat_destroy": (_i32, [_vp]),
     "mcx_flat_set_logweight": (_i32, [_vp, _vp]),

@@ -388,6 +388,41 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     return check_launch(lat->ctx);
 }
 
+// measure!(measurements, sys, i) with an interval schedule (src/measurements/measurements.jl:192-200),
+// kept on the device: nmeasure x (interval sweeps, then a snapshot of the per-chain sums), one
+// device-to-host copy at the end.  out is [nmeasure][nchains][4] = {pair, spin, spin2, accepted}.
+int32_t mcx_sweep_series(mcx_lattice *lat, int64_t nmeasure, int64_t interval, int64_t *out)
+{
+    REQUIRE(lat && out, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(nmeasure >= 0 && interval >= 1, MCX_ERR_ARGUMENT, "need nmeasure >= 0 and interval >= 1");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    const size_t stride = (size_t)lat->nchains * SUM_FIELDS;
+    long long *d_series = nullptr;
+    if (nmeasure == 0) return MCX_OK;
+    CUDA_TRY(cudaMalloc((void **)&d_series, sizeof(long long) * stride * (size_t)nmeasure));
+    const bool was_tracking = lat->track_sums;
+    lat->track_sums = true;                       // the snapshots need current sums after every interval
+    int32_t st = MCX_OK;
+    if (lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
+    for (int64_t k = 0; k < nmeasure && st == MCX_OK; ++k) {
+        st = mcx_sweep(lat, interval);
+        if (st == MCX_OK && cudaMemcpyAsync(d_series + k * stride, lat->d_sums, sizeof(long long) * stride,
+                                            cudaMemcpyDeviceToDevice, lat->ctx->stream) != cudaSuccess)
+            st = fail(MCX_ERR_CUDA, "snapshot copy failed");
+    }
+    lat->track_sums = was_tracking;
+    if (st == MCX_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_series, sizeof(long long) * stride * (size_t)nmeasure, cudaMemcpyDeviceToHost,
+                                        lat->ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(lat->ctx->stream);
+        if (e != cudaSuccess) st = fail(MCX_ERR_CUDA, "series copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_series);
+    if (lat->model == MCX_ISING && st == MCX_OK)
+        for (int64_t i = 0; i < nmeasure * lat->nchains; ++i) out[i * SUM_FIELDS + SUM_SPIN2] = lat->N;
+    return st;
+}
+
 static int32_t refresh_sums(mcx_lattice *lat)
 {
     if (lat->sums_dirty) {
@@ -522,6 +557,33 @@ int32_t mcx_pt_reset(mcx_pt *pt)
     CUDA_TRY(cudaMemcpy(lat->d_labels, id.data() + pt->first_slot, sizeof(int32_t) * lat->nchains, cudaMemcpyHostToDevice));
     pt->stage = 0;
     pt->round = 0;
+    return MCX_OK;
+}
+
+// restore a checkpointed ladder (checkpointing.jl:95-101 + replica_exchange.jl:13-19 fields)
+int32_t mcx_pt_set_state(mcx_pt *pt, const int64_t *indices, const int64_t *steps, const int64_t *accepted, int64_t stage,
+                         int64_t round)
+{
+    REQUIRE(pt && indices, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(stage == 0 || stage == 1, MCX_ERR_ARGUMENT, "stage must be 0 or 1");
+    mcx_lattice *lat = pt->lat;
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    std::vector<int32_t> idx(pt->n), slot(pt->n, -1);
+    for (int r = 0; r < pt->n; ++r) {
+        REQUIRE(indices[r] >= 1 && indices[r] <= pt->n, MCX_ERR_BOUNDS, "ladder index %lld of slot %d outside 1..%d",
+                (long long)indices[r], r, pt->n);
+        idx[r] = (int32_t)indices[r] - 1;
+        REQUIRE(slot[idx[r]] < 0, MCX_ERR_ARGUMENT, "Replica-exchange local index permutation is inconsistent");
+        slot[idx[r]] = r;
+    }
+    CUDA_TRY(cudaMemcpy(pt->d_index, idx.data(), sizeof(int32_t) * pt->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pt->d_slot_of, slot.data(), sizeof(int32_t) * pt->n, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(lat->d_labels, idx.data() + pt->first_slot, sizeof(int32_t) * lat->nchains, cudaMemcpyHostToDevice));
+    if (steps) CUDA_TRY(cudaMemcpy(pt->d_steps, steps, sizeof(long long) * (pt->n - 1), cudaMemcpyHostToDevice));
+    if (accepted) CUDA_TRY(cudaMemcpy(pt->d_accepted, accepted, sizeof(long long) * (pt->n - 1), cudaMemcpyHostToDevice));
+    pt->stage = (int)stage;
+    pt->round = (uint64_t)round;
     return MCX_OK;
 }
 

@@ -126,6 +126,15 @@ class ParallelChains:
     def with_parallel(self, f):
         return [f(i, a) for i, a in enumerate(self.algs)]
 
+    def merge_(self, buf):
+        """merge!(pc, buf): element-wise sum of a user array over ranks (parallel_chains.jl:121-128;
+        identity for one rank, MPI.Allreduce! otherwise).  `buf` is a torch tensor or numpy array."""
+        if isinstance(self.backend, GPUBackend) and self.backend.size > 1:
+            import torch
+            t = buf if isinstance(buf, torch.Tensor) else torch.from_numpy(buf)
+            self.backend.all_reduce_sum(t)
+        return buf
+
 
 # --------------------------------------------------------------------------- replica exchange
 def exchange_log_ratio(ens_i, ens_j, x_i, x_j):

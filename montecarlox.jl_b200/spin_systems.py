@@ -88,6 +88,27 @@ class AbstractSpinSystem:
         except Exception:
             pass
 
+    # ---- serialisation (checkpoint!/restore_checkpoint, checkpointing.jl:48-101)
+    def __getstate__(self):
+        seed, nxt = C.c_uint64(), C.c_uint64()
+        check(lib().mcx_get_rng(self.h_lat, C.byref(seed), C.byref(nxt)))
+        pair, spin, spin2, acc, steps = self._sums()
+        return {"cls_dims": self.dims, "J": self.J, "h": self.h, "D": self.D, "nchains": self.nchains,
+                "device": self.ctx.device, "spins": self.spins.copy(), "seed": seed.value, "next_sweep": nxt.value,
+                "labels": self.get_labels(), "rule": getattr(self, "_rule_tables", None),
+                "first_chain": getattr(self, "_first_chain", 0)}
+
+    def __setstate__(self, st):
+        AbstractSpinSystem.__init__(self, st["cls_dims"], st["J"], st["h"], st["D"], st["nchains"],
+                                    default_context(st["device"]))
+        self.spins = st["spins"]
+        if st["rule"] is not None:
+            self.set_rule(*st["rule"])
+            self.set_labels(st["labels"])
+        check(lib().mcx_lattice_set_first_chain_id(self.h_lat, st["first_chain"]))
+        self._first_chain = st["first_chain"]
+        check(lib().mcx_set_rng(self.h_lat, st["seed"], st["next_sweep"]))
+
     # ---- sys.spins
     def _shape(self, a):
         return a.reshape(self.N) if self.nchains == 1 else a.reshape(self.nchains, self.N)
@@ -153,6 +174,7 @@ class AbstractSpinSystem:
                 raise ValueError("device init needs a PhiloxRNG (counter-based); got %s" % type(rng).__name__)
             seed = rng.seed
             check(lib().mcx_lattice_set_first_chain_id(self.h_lat, rng.chain))
+            self._first_chain = rng.chain
         check(lib().mcx_lattice_init(self.h_lat, _INIT[type], seed))
         return self
 
@@ -164,6 +186,7 @@ class AbstractSpinSystem:
             t = t[None, :]
         check(lib().mcx_set_rule(self.h_lat, rule, t.ctypes.data, t.shape[0], t.shape[1]))
         self._rule_key = None
+        self._rule_tables = (rule, t.copy())
 
     def set_labels(self, labels):
         a = np.ascontiguousarray(labels, dtype=np.int32)
@@ -201,6 +224,7 @@ class AbstractSpinSystem:
             T = build_table(self.model, rule_of(alg), len(self.dims), beta_of(alg), self.J, self.h, self.D)
             self.set_rule(rule_of(alg), T)
             check(lib().mcx_lattice_set_first_chain_id(self.h_lat, rng.chain))
+            self._first_chain = rng.chain
             self.set_rng(rng.seed)
             self._rule_key = key
 

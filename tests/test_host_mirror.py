@@ -120,3 +120,50 @@ def test_exchange_helpers():
     algs[0].ensemble.logweight_table.values[:] = [0.1, 0.2, 0.3, 0.4]
     m.distribute_logweight_(pc)
     assert list(algs[1].ensemble.logweight_table.values) == [0.1, 0.2, 0.3, 0.4]
+
+
+def test_exact_dos_api():
+    # SpinSystems/test/test_ising.jl:174-191
+    b = m.logdos_exact_ising2D(8)
+    assert b[-128] == math.log(2) and abs(b[0] - 42.41274640460084) < 1e-12 and math.isnan(b[-124])
+    v = m.logdos_exact_ising2D(8, format="vector")
+    assert v[0] == (-128, math.log(2)) and v[-1] == (128, math.log(2))
+    with pytest.raises(RuntimeError):
+        m.logdos_exact_ising2D(10)
+    d = m.distribution_exact_ising2D(8, 0.4)
+    assert abs(np.nansum(d.values) - 1.0) < 1e-12
+
+
+def test_tau_int_and_retuning():
+    # src/measurements/autocorrelations.jl:28-65 on an AR(1) series: tau = 1/2 + phi/(1-phi)
+    rng = np.random.default_rng(0)
+    x = np.zeros(40000)
+    for i in range(1, x.size):
+        x[i] = 0.8 * x[i - 1] + rng.normal()
+    assert abs(m.tau_int(x) - 4.5) < 0.6
+    assert m.tau_int(np.ones(10)) == 0.5
+    with pytest.raises(ValueError):
+        m.tau_int([1.0])
+    with pytest.raises(ValueError):
+        m.tau_int(x, max_lag=x.size)
+    taus = m.integrated_autocorrelation_times([x, x[:3], [1.0]], min_points=4)
+    assert taus[0] > 3 and math.isnan(taus[1]) and math.isnan(taus[2])
+    from mcx_b200.measurements import _retune_exchange_sweeps_
+    assert _retune_exchange_sweeps_([0, 0, 0], [1.0, 2.0, float("nan")], 100, 10, 150) == [67, 133, 100]
+    pt = m.ParallelTempering([1.0, 0.5], seed=3)
+    sweeps = [10, 10]
+    samples = [(1, float(v)) for v in x[:2000]] + [(2, float(v)) for v in rng.normal(size=2000)]
+    m.optimize_exchange_interval_(pt, samples, sweeps, base_sweeps=100, min_points=400)
+    assert sweeps[0] > sweeps[1]
+
+
+def test_checkpoint_session_roundtrip(tmp_path):
+    # src/infrastructure/checkpointing.jl:48-111
+    f = str(tmp_path / "run" / "ckpt.mcx")
+    ck = m.init_checkpoint(f, {"rng": m.PhiloxRNG(42, 3), "x": 1.5}, sweep=0)
+    m.checkpoint_(ck, sweep=100)
+    r = m.restore_checkpoint(f)
+    assert r.sweep == 100 and r.x == 1.5 and r.rng.seed == 42 and r.rng.chain == 3
+    m.finalize_(ck)
+    import os
+    assert not os.path.exists(f)
