@@ -9,6 +9,7 @@
 //   Ising   spin_flip! ising.jl:35-58, flip_changes :187-192/:484-489, modify! :200-205/:493-498
 //   BC      spin_flip! blume_capel.jl:52-85, _propose_state :21-30, propose_changes :235-241
 //   accept! metropolis.jl:14-17,121-127; _accept! importance_sampling.jl:80-85
+#include "k_site.cuh"
 #include "mcx_internal.h"
 
 namespace mcx {
@@ -154,7 +155,7 @@ k_sweep_generic(LatView L, const uint32_t *__restrict__ thi, const uint32_t *__r
     const uint32_t chain_id = first_chain + (uint32_t)chain;
     const int64_t blk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nblk = (L.halfN + 7) >> 3;
-    int dpair = 0, dspin = 0, dspin2 = 0, nacc = 0;
+    SiteAcc acc;
     if (blk < nblk) {
         uint8_t *tgt = plane_ptr(L, chain, colour);
         const uint8_t *oth = plane_ptr(L, chain, colour ^ 1);
@@ -172,57 +173,14 @@ k_sweep_generic(LatView L, const uint32_t *__restrict__ thi, const uint32_t *__r
             const int raw = neighbour_raw_sum(L, oth, s);
             const int so = tgt[q];
             // m < T with the low half fetched only on a tie of the high halves
-            auto less_than = [&](uint32_t hi, int idx, uint32_t lo_plane) -> bool {
-                const uint32_t th = thi[tb + idx], tl = tlo[tb + idx];
-                if (hi < th) return true;
-                if (hi > th || tl == 0) return false;
-                const Philox4 rl = stream_block(seed_lo, seed_hi, chain_id, TAG_SWEEP, t, (uint32_t)blk, lo_plane);
-                return lane16(rl, k) < tl;
-            };
-            int sn = so;
-            if (MODEL == MCX_ISING) {
-                const bool lt = less_than(lane16(r0, k), so * (nn + 1) + raw, 1);
-                if (RULE == MCX_HEATBATH) sn = lt ? 1 : 0;
-                else sn = lt ? (so ^ 1) : so;
-                if (sn != so) {
-                    const int sgn = 2 * so - 1, nsum = 2 * raw - nn;
-                    dpair += -2 * sgn * nsum;
-                    dspin += -2 * sgn;
-                    nacc += 1;
-                }
-            } else {
-                const int nsum = raw - nn;
-                if (RULE == MCX_HEATBATH) {
-                    const uint32_t hi = lane16(r0, k);
-                    const bool lt0 = less_than(hi, raw, 1);
-                    const bool lt1 = lt0 ? true : less_than(hi, (2 * nn + 1) + raw, 1);
-                    sn = lt0 ? 0 : (lt1 ? 1 : 2);
-                } else {
-                    const int b = (int)(lane16(r0, k) >> 15);
-                    const int prop = so == 0 ? (b ? 1 : 2) : so == 1 ? (b ? 0 : 2) : (b ? 0 : 1);
-                    const bool lt = less_than(lane16(r2, k), (so * 2 + b) * (2 * nn + 1) + raw, 3);
-                    sn = lt ? prop : so;
-                }
-                if (sn != so) {
-                    const int d = sn - so;
-                    dpair += d * nsum;
-                    dspin += d;
-                    dspin2 += (sn - 1) * (sn - 1) - (so - 1) * (so - 1);
-                    nacc += 1;
-                }
-            }
+            const int sn = site_update<MODEL, RULE>(so, raw, nn, r0, r2, k, thi + tb, tlo + tb, [&](uint32_t plane) {
+                const Philox4 rl = stream_block(seed_lo, seed_hi, chain_id, TAG_SWEEP, t, (uint32_t)blk, plane);
+                return lane16(rl, k);
+            }, acc);
             if (sn != so) tgt[q] = (uint8_t)sn;
         }
     }
-    dpair = warp_sum(dpair); dspin = warp_sum(dspin); nacc = warp_sum(nacc);
-    if (MODEL == MCX_BLUME_CAPEL) dspin2 = warp_sum(dspin2);
-    if ((threadIdx.x & 31) == 0) {
-        unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
-        if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
-        if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
-        if (MODEL == MCX_BLUME_CAPEL && dspin2) atomicAdd(o + SUM_SPIN2, (unsigned long long)(long long)dspin2);
-        if (nacc) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nacc);
-    }
+    flush_site_acc<MODEL>(acc, sums + (int64_t)chain * SUM_FIELDS);
 }
 
 // ------------------------------------------------------------------ launchers
@@ -276,13 +234,11 @@ static void launch_generic_t(mcx_lattice *lat, int colour, uint64_t t)
 void launch_sweep_generic(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (lat->model == MCX_ISING) {
-        if (lat->rule == MCX_METROPOLIS) launch_generic_t<MCX_ISING, MCX_METROPOLIS>(lat, colour, t);
-        else if (lat->rule == MCX_GLAUBER) launch_generic_t<MCX_ISING, MCX_GLAUBER>(lat, colour, t);
-        else launch_generic_t<MCX_ISING, MCX_HEATBATH>(lat, colour, t);
+        if (lat->rule == MCX_HEATBATH) launch_generic_t<MCX_ISING, MCX_HEATBATH>(lat, colour, t);
+        else launch_generic_t<MCX_ISING, MCX_METROPOLIS>(lat, colour, t);   // Glauber differs only in its table
     } else {
-        if (lat->rule == MCX_METROPOLIS) launch_generic_t<MCX_BLUME_CAPEL, MCX_METROPOLIS>(lat, colour, t);
-        else if (lat->rule == MCX_GLAUBER) launch_generic_t<MCX_BLUME_CAPEL, MCX_GLAUBER>(lat, colour, t);
-        else launch_generic_t<MCX_BLUME_CAPEL, MCX_HEATBATH>(lat, colour, t);
+        if (lat->rule == MCX_HEATBATH) launch_generic_t<MCX_BLUME_CAPEL, MCX_HEATBATH>(lat, colour, t);
+        else launch_generic_t<MCX_BLUME_CAPEL, MCX_METROPOLIS>(lat, colour, t);
     }
 }
 

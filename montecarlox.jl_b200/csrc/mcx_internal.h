@@ -74,6 +74,9 @@ bool launch_pack_ising2d(mcx_lattice *lat);
 bool launch_unpack_ising2d(mcx_lattice *lat);
 bool launch_init_ising2d(mcx_lattice *lat, int mode, uint64_t seed);                        // false: shape not supported
 
+// k_rows8.cu
+bool launch_sweep_rows8(mcx_lattice *lat, int colour, uint64_t t);     // false: shape not supported
+
 // k_pt.cu
 void launch_pt_publish(mcx_pt *pt);
 void launch_pt_exchange(mcx_pt *pt);

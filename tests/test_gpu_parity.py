@@ -67,7 +67,7 @@ def test_fast_kernel_equals_generic_kernel(m, L):
     """same trajectories from the vectorised and the generic kernels, any strip height"""
     outs = []
     keys = ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP", "MCX_VARIANT")
-    envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
+    envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_FORCE_GENERIC": "2"}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
     envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in range(9) for r in ("4", "16")]
     for env in envs:
         for k in keys:
@@ -96,7 +96,7 @@ def test_ising2d_untracked_sums_match(m, oracle):
 
 
 def test_ising2d_rectangular_and_field(m, oracle):
-    for dims, J, h in (([64, 8], 1, 0), ([8, 64], 1, 0), ([32, 12], 2, 0.3), ([12, 10], 1.5, -0.2)):
+    for dims, J, h in (([64, 8], 1, 0), ([8, 64], 1, 0), ([32, 12], 2, 0.3), ([12, 10], 1.5, -0.2), ([48, 10], 1, 0.1)):
         s_or, a_or = _oracle_run(oracle, oracle.ISING, dims, 0, 0.5, J, h, 0, 11, 1, 8)
         sys_ = m.Ising(dims, J=J, h=h)
         alg = _make_alg(m, 0, 0.5, 11, 1)
@@ -108,9 +108,9 @@ def test_ising2d_rectangular_and_field(m, oracle):
         assert sys_.energy(full=True) == pytest.approx(s_or.energy(full=True), abs=1e-9)
 
 
+@pytest.mark.parametrize("dims", [[8, 6, 4], [16, 8, 6], [32, 4, 4]])
 @pytest.mark.parametrize("rule", [0, 1, 2])
-def test_ising3d_bit_exact(m, oracle, rule):
-    dims = [8, 6, 4]
+def test_ising3d_bit_exact(m, oracle, rule, dims):
     s_or, a_or = _oracle_run(oracle, oracle.ISING, dims, rule, 0.2216, 1, 0, 0, 2024, 0, 10)
     sys_ = m.Ising(dims)
     alg = _make_alg(m, rule, 0.2216, 2024, 0)
@@ -119,7 +119,7 @@ def test_ising3d_bit_exact(m, oracle, rule):
     _check(sys_, s_or, a_or, alg, 10)
 
 
-@pytest.mark.parametrize("dims", [[8, 8], [32, 16], [6, 4, 8]])
+@pytest.mark.parametrize("dims", [[8, 8], [32, 16], [6, 4, 8], [64, 12], [16, 6, 4]])
 @pytest.mark.parametrize("rule", [0, 1, 2])
 def test_blume_capel_bit_exact(m, oracle, dims, rule):
     for beta, J, D, h in ((0.8, 1, 0, 0), (1.1, 1.0, 0.5, 0.0), (0.6, 1.0, 0.2, 0.1)):
