@@ -12,6 +12,7 @@
 //     muca: histogram[bin(x_vis)] += 1        WL: lw[bin(x_vis)] -= logf
 // Histograms are privatised per block in shared memory (integer counters) when they fit and
 // merged into the global histogram with one atomic per non-empty bin at the end of the launch.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -36,18 +37,36 @@ struct FlatParams {
     double beta_pair, logf, J;
     uint32_t seed_lo, seed_hi, first_chain;
     uint64_t sweep0;
-    int nsweeps, policy;
+    int nsweeps, policy, step_shift, prefetch;
 };
 
-// rand < p for rand = m * 2^-32, m = hi << 16 | lo, with lo fetched only when hi cannot decide
+// rand < exp(log_ratio) for rand = m * 2^-32, m = hi << 16 | lo, decided exactly but cheaply:
+//  1. a float estimate of p with a rigorous error margin settles all but ~2^-16 of the attempts from
+//     the high half alone (no double-precision exp, no second Philox block);
+//  2. otherwise the double-precision exp decides on the high half, and only if (hi, hi + 1) brackets
+//     p * 2^16 is the low half fetched and the full 32-bit comparison made.
+// The result equals (double)m * 2^-32 < exp(log_ratio) in every case.
 template <class LoFn>
-__device__ __forceinline__ bool draw_less(uint32_t hi, double p, LoFn lo_fn)
+__device__ __forceinline__ bool draw_less_exp(uint32_t hi, double log_ratio, LoFn lo_fn)
 {
-    const double p16 = p * 65536.0;
-    if ((double)(hi + 1) <= p16) return true;
-    if ((double)hi >= p16) return false;
+    const float lf = (float)log_ratio;
+    const float p16 = __expf(lf) * 65536.0f;
+    const float eps = 3.0e-6f + fabsf(lf) * 1.0e-6f;       // > 4x the worst-case relative error of p16
+    if ((float)(hi + 1) <= p16 * (1.0f - eps)) return true;
+    if (hi > 0 && (float)hi >= p16 * (1.0f + eps)) return false;   // hi == 0: a denormal p could still win
+    const double p = exp(log_ratio), pd16 = p * 65536.0;
+    if ((double)(hi + 1) <= pd16) return true;
+    if ((double)hi >= pd16) return false;
     const uint32_t lo = lo_fn();
     return (double)((hi << 16) | lo) * (1.0 / 4294967296.0) < p;
+}
+
+// div(x - start, step) truncating toward zero like Julia's div (binned_object.jl:22-24)
+__device__ __forceinline__ int64_t bin_of(int64_t x, int64_t start, int64_t step, int shift)
+{
+    const int64_t d = x - start;
+    if (shift >= 0) return (d + ((d >> 63) & (step - 1))) >> shift;
+    return d / step;
 }
 
 template <int OBS, int KIND, bool SMEM_HIST>
@@ -68,7 +87,17 @@ __global__ void __launch_bounds__(kFlatThreads) k_flat_sweep(FlatParams P)
         const uint32_t chain_id = P.first_chain + (uint32_t)c;
         const int Lx = P.Lx, Ly = P.Ly, Lz = P.Lz;
         const int64_t sx = nch, sy = (int64_t)Lx * nch, sz = (int64_t)Lx * Ly * nch;
-        bool dead = false;
+        const int shift = P.step_shift;
+        // bin and log-weight of the current state are carried from attempt to attempt
+        int64_t io = bin_of(OBS == MCX_OBS_ENERGY ? -pair : spin2, P.start, P.step, shift);
+        bool dead = io < 0 || io >= P.nbins;
+        if (dead) atomicExch(P.error, 1);
+        double lw_old = dead ? 0.0 : lw[io];
+        // run-length cache for the global histogram (a chain revisits its current bin many times)
+        int64_t run_bin = io;
+        unsigned long long run_cnt = 0;
+        const int64_t pf = (int64_t)P.prefetch * nch;     // prefetch distance in bytes of the interleaved array
+        const int64_t total = P.N * (int64_t)nch;
         for (int sw = 0; sw < P.nsweeps && !dead; ++sw) {
             const uint64_t t = P.sweep0 + (uint64_t)sw;
             Philox4 r0{}, r2{};
@@ -83,19 +112,33 @@ __global__ void __launch_bounds__(kFlatThreads) k_flat_sweep(FlatParams P)
                                 r2 = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, (uint32_t)(i >> 3), 2);
                         }
                         int8_t *p = sp + i * nch;
+                        if (pf) {
+                            // lines first touched `prefetch` sites ahead: the site's own row of the next
+                            // y (and, in 3-D, the z+1 and z-1 planes); addresses wrap like the lattice
+                            int64_t a = i * nch + pf;
+                            if (a >= total) a -= total;
+                            int64_t ay = a + sy; if (ay >= total) ay -= total;
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + ay));
+                            if (P.ndim > 2) {
+                                int64_t az = a + sz; if (az >= total) az -= total;
+                                int64_t aw = a - sz; if (aw < 0) aw += total;
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + az));
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + aw));
+                            }
+                        }
                         const int s = *p;
                         int nb = p[x == 0 ? (Lx - 1) * sx : -sx] + p[x == Lx - 1 ? -(Lx - 1) * sx : sx];
                         if (P.ndim > 1) nb += p[y == 0 ? (Ly - 1) * sy : -sy] + p[y == Ly - 1 ? -(Ly - 1) * sy : sy];
                         if (P.ndim > 2) nb += p[z == 0 ? (Lz - 1) * sz : -sz] + p[z == Lz - 1 ? -(Lz - 1) * sz : sz];
 
                         int s_new, dpair, dspin, dspin2;
-                        int64_t x_old, x_new;
+                        int64_t x_new;
                         uint32_t hi;
                         uint32_t lo_plane;
                         if (OBS == MCX_OBS_ENERGY) {
                             // flip_changes / delta_energy (ising.jl:187-198), integer path J = 1, h = 0
                             s_new = -s; dpair = -2 * s * nb; dspin = -2 * s; dspin2 = 0;
-                            x_old = -pair; x_new = x_old - dpair;
+                            x_new = -pair - dpair;
                             hi = lane16(r0, lane); lo_plane = 1;
                         } else {
                             // _propose_state + propose_changes (blume_capel.jl:21-30,235-241),
@@ -103,50 +146,57 @@ __global__ void __launch_bounds__(kFlatThreads) k_flat_sweep(FlatParams P)
                             const int b = (int)(lane16(r0, lane) >> 15);
                             s_new = s == -1 ? (b ? 0 : 1) : s == 0 ? (b ? -1 : 1) : (b ? -1 : 0);
                             dspin = s_new - s; dspin2 = s_new * s_new - s * s; dpair = dspin * nb;
-                            x_old = spin2; x_new = spin2 + dspin2;
+                            x_new = spin2 + dspin2;
                             hi = lane16(r2, lane); lo_plane = 3;
                         }
-                        // _binindex for integer bins: div(x - start, step) + 1 (binned_object.jl:22-24)
-                        const int64_t in = (x_new - P.start) / P.step, io = (x_old - P.start) / P.step;   // 0-based
-                        bool inside = in >= 0 && in < P.nbins && io >= 0 && io < P.nbins;
-                        if (!inside) {
-                            if (P.policy == 0 || io < 0 || io >= P.nbins) {     // BoundsError
-                                atomicExch(P.error, 1);
-                                dead = true;
-                                break;
-                            }
+                        // _binindex for integer bins: div(x - start, step) + 1 (binned_object.jl:22-24); 0-based here
+                        const int64_t in = bin_of(x_new, P.start, P.step, shift);
+                        const bool inside = in >= 0 && in < P.nbins;
+                        if (!inside && P.policy == 0) {                          // BoundsError
+                            atomicExch(P.error, 1);
+                            dead = true;
+                            break;
                         }
                         bool accepted = false;
+                        double lw_new = lw_old;
                         if (inside) {
+                            lw_new = in == io ? lw_old : lw[in];
                             double log_ratio;
                             if (OBS == MCX_OBS_ENERGY) {
-                                log_ratio = lw[in] - lw[io];
+                                log_ratio = lw_new - lw_old;
                             } else {
                                 const double Ho1 = P.J * (P.J * (double)pair);
                                 const double Hn1 = Ho1 + P.J * (P.J * (double)dpair);
-                                log_ratio = (-P.beta_pair * Hn1 + lw[in]) - (-P.beta_pair * Ho1 + lw[io]);
+                                log_ratio = (-P.beta_pair * Hn1 + lw_new) - (-P.beta_pair * Ho1 + lw_old);
                             }
                             // _accept! (importance_sampling.jl:80-85)
                             if (log_ratio > 0) accepted = true;
-                            else accepted = draw_less(hi, exp(log_ratio), [&]() {
+                            else accepted = draw_less_exp(hi, log_ratio, [&]() {
                                 const Philox4 rl = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t,
                                                                 (uint32_t)(i >> 3), lo_plane);
                                 return lane16(rl, lane);
                             });
                         }
-                        const int64_t iv = accepted ? in : io;
-                        if (KIND == MCX_FLAT_MUCA) {
-                            if (SMEM_HIST) atomicAdd(&s_hist[iv], 1u);
-                            else atomicAdd(P.hist + iv, 1ull);
-                        } else {
-                            lw[iv] -= P.logf;
-                        }
                         if (accepted) {
                             *p = (int8_t)s_new;
                             pair += dpair; spin += dspin; spin2 += dspin2; nacc += 1;
+                            io = in; lw_old = lw_new;
+                        }
+                        // record_visit! / Wang-Landau update at the visited bin (= io after the move)
+                        if (KIND == MCX_FLAT_MUCA) {
+                            if (SMEM_HIST) atomicAdd(&s_hist[io], 1u);
+                            else if (io == run_bin) run_cnt += 1;
+                            else {
+                                if (run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
+                                run_bin = io; run_cnt = 1;
+                            }
+                        } else {
+                            lw_old -= P.logf;
+                            lw[io] = lw_old;
                         }
                     }
         }
+        if (KIND == MCX_FLAT_MUCA && !SMEM_HIST && run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
         st[0] = pair; st[1] = spin; st[2] = spin2; st[3] = nacc;
     }
     if (SMEM_HIST) {
@@ -258,6 +308,15 @@ void launch_flat_sweep(mcx_flat *f, uint64_t sweep0, int nsweeps)
     P.beta_pair = f->beta_pair; P.logf = f->logf; P.J = lat->J;
     P.seed_lo = (uint32_t)lat->seed; P.seed_hi = (uint32_t)(lat->seed >> 32); P.first_chain = lat->first_chain;
     P.sweep0 = sweep0; P.nsweeps = nsweeps; P.policy = f->policy;
+    P.step_shift = -1;
+    for (int sh = 0; sh < 62; ++sh)
+        if (f->step == ((int64_t)1 << sh)) P.step_shift = sh;
+    {
+        // software prefetch only pays when the interleaved spins do not sit in L2 anyway
+        const char *e = getenv("MCX_FLAT_PREFETCH");
+        const double bytes = (double)lat->N * lat->nchains;
+        P.prefetch = e ? atoi(e) : (bytes > 48.0e6 ? 24 : 0);
+    }
     if (f->observable == MCX_OBS_ENERGY) {
         if (f->kind == MCX_FLAT_MUCA) launch_sweep_t<MCX_OBS_ENERGY, MCX_FLAT_MUCA>(f, P);
         else launch_sweep_t<MCX_OBS_ENERGY, MCX_FLAT_WANG_LANDAU>(f, P);
