@@ -277,6 +277,9 @@ class ReplicaExchange:
     def sweep_system_(self, sys, nsweeps):
         if self._pt is None or sys is not self._sys:
             self.attach(sys)
+        # exchanging every sweep: keep the energy sums current per flip; with longer intervals it is
+        # cheaper to sweep without bookkeeping and recompute the sums once, when they are published
+        sys.set_tracking(int(nsweeps) < 3)
         check(lib().mcx_sweep(sys.h_lat, int(nsweeps)))
         for a in self.replica.algs[self._first:self._first + self._count]:
             a.steps += int(nsweeps) * sys.N
