@@ -11,6 +11,7 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, int iters, uint32_t seed
 #pragma unroll
     for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 8 + i;
     uint32_t k0 = seed ^ 0x9E3779B9u;
+    uint32_t kt = k0 + threadIdx.x * 0x9E3779B9u;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -32,6 +33,16 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, int iters, uint32_t seed
                 a[i] = __byte_perm(a[i], a[(i + 1) & 7], 0x7531);
             } else if (MODE == 7) {        // SHF (funnel)
                 a[i] = __funnelshift_l(a[i], a[(i + 1) & 7], 8);
+            } else if (MODE == 8) {        // Philox-like with a per-thread (non-uniform) key
+                const uint64_t p = (uint64_t)a[i] * 0xD2511F53u;
+                a[i] = (uint32_t)(p >> 32) ^ (uint32_t)p ^ kt;
+            } else if (MODE == 9) {        // two WIDE per LOP3
+                const uint64_t p = (uint64_t)a[i] * 0xD2511F53u;
+                const uint64_t q = (uint64_t)(uint32_t)p * 0xCD9E8D57u;
+                a[i] = (uint32_t)(p >> 32) ^ (uint32_t)q ^ (uint32_t)(q >> 32);
+            } else if (MODE == 10) {       // WIDE only (result folded by IMAD lo)
+                const uint64_t p = (uint64_t)a[i] * 0xD2511F53u;
+                a[i] = (uint32_t)(p >> 32) * 3u + (uint32_t)p;
             }
         }
     }
@@ -76,5 +87,8 @@ int main()
     run<5>("IADD3", 1);
     run<6>("PRMT", 1);
     run<7>("SHF funnel", 1);
+    run<8>("WIDE + LOP3(3-in, reg key)", 2);
+    run<9>("2 WIDE + LOP3", 3);
+    run<10>("WIDE + IMAD", 2);
     return 0;
 }
