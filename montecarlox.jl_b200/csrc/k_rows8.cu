@@ -63,16 +63,61 @@ k_sweep_rows8(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__r
         Philox4 r2 = r0;
         if (MODEL == MCX_BLUME_CAPEL && RULE != MCX_HEATBATH)
             r2 = stream_block(seed_lo, seed_hi, chain_id, TAG_SWEEP, t, (uint32_t)blk, 2);
+        // fast pass: branch-free 16-bit decisions; any tie of the high halves (2^-16 per site)
+        // sends the whole group of eight through the exact rule below
         uint64_t Tn = 0;
+        bool tie = false;
+        SiteAcc fast;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int so = (int)((T >> (8 * k)) & 0xff), rk = (int)((raw >> (8 * k)) & 0xff);
-            const int sn = site_update<MODEL, RULE>(so, rk, nn, r0, r2, k, s_thi, s_tlo, [&](uint32_t plane) {
-                const Philox4 rl = stream_block(seed_lo, seed_hi, chain_id, TAG_SWEEP, t, (uint32_t)blk, plane);
-                return lane16(rl, k);
-            }, acc);
+            int sn;
+            if (MODEL == MCX_ISING) {
+                const uint32_t h = lane16(r0, k), th = s_thi[so * (nn + 1) + rk];
+                const int lt = h < th;
+                tie |= h == th;
+                sn = RULE == MCX_HEATBATH ? lt : (so ^ lt);
+                const int ch = sn != so, sgn = 2 * so - 1;
+                fast.dpair += ch * (-2 * sgn * (2 * rk - nn));
+                fast.dspin += ch * (-2 * sgn);
+                fast.nacc += ch;
+            } else if (RULE == MCX_HEATBATH) {
+                const uint32_t h = lane16(r0, k), t0 = s_thi[rk], t1 = s_thi[(2 * nn + 1) + rk];
+                tie |= (h == t0) | (h == t1);
+                sn = h < t0 ? 0 : (h < t1 ? 1 : 2);
+                const int d = sn - so;
+                fast.dpair += d * (rk - nn);
+                fast.dspin += d;
+                fast.dspin2 += (sn - 1) * (sn - 1) - (so - 1) * (so - 1);
+                fast.nacc += d != 0;
+            } else {
+                const int b = (int)(lane16(r0, k) >> 15);
+                const int prop = so == 0 ? (b ? 1 : 2) : so == 1 ? (b ? 0 : 2) : (b ? 0 : 1);
+                const uint32_t h = lane16(r2, k), th = s_thi[(so * 2 + b) * (2 * nn + 1) + rk];
+                tie |= h == th;
+                sn = h < th ? prop : so;
+                const int d = sn - so;
+                fast.dpair += d * (rk - nn);
+                fast.dspin += d;
+                fast.dspin2 += (sn - 1) * (sn - 1) - (so - 1) * (so - 1);
+                fast.nacc += d != 0;
+            }
             Tn |= (uint64_t)sn << (8 * k);
         }
+        if (tie) {
+            Tn = 0;
+            fast = SiteAcc();
+#pragma unroll 1
+            for (int k = 0; k < 8; ++k) {
+                const int so = (int)((T >> (8 * k)) & 0xff), rk = (int)((raw >> (8 * k)) & 0xff);
+                const int sn = site_update<MODEL, RULE>(so, rk, nn, r0, r2, k, s_thi, s_tlo, [&](uint32_t plane) {
+                    const Philox4 rl = stream_block(seed_lo, seed_hi, chain_id, TAG_SWEEP, t, (uint32_t)blk, plane);
+                    return lane16(rl, k);
+                }, fast);
+                Tn |= (uint64_t)sn << (8 * k);
+            }
+        }
+        acc.dpair += fast.dpair; acc.dspin += fast.dspin; acc.dspin2 += fast.dspin2; acc.nacc += fast.nacc;
         if (Tn != T) *reinterpret_cast<uint64_t *>(tgt + rb + col) = Tn;
     }
     flush_site_acc<MODEL>(acc, sums + (int64_t)chain * SUM_FIELDS);

@@ -84,6 +84,8 @@ if __name__ == "__main__":
     if "muca2d" in which:
         print(json.dumps(muca2d()))
     if "gen" in which:
-        print(json.dumps(canonical(1, [2048, 2048], 1, 20)))
-        print(json.dumps(canonical(0, [256, 256, 256], 1, 20)))
-        print(json.dumps(canonical(0, [1000, 1000], 1, 20)))
+        print(json.dumps(canonical(1, [8192, 8192], 1, 10)))
+        print(json.dumps(canonical(0, [512, 512, 512], 1, 10)))
+        print(json.dumps(canonical(1, [256, 256, 256], 1, 10)))
+        print(json.dumps(canonical(0, [8176, 8176], 1, 10)))
+        print(json.dumps(canonical(0, [1000, 1000], 64, 10)))
