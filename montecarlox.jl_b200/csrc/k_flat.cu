@@ -3,9 +3,11 @@
 // The acceptance of these ensembles depends on the chain's GLOBAL observable
 // (spin_flip!(sys, alg::AbstractImportanceSampling), SpinSystems/src/ising.jl:25-33 passes
 // E_new, E_old), so a chain is serial by construction and the parallelism is across chains only
-// (finding 4).  One thread owns one chain and visits sites 0..N-1 in order
-// (FLAT stream); spins are stored chain-interleaved, spins[site][chain], so the 32 chains of a warp
-// touch 32 consecutive bytes per site.  Per attempt (restating importance_sampling.jl:69-85,
+// (finding 4).  One WARP owns one chain and visits every site once per sweep in
+// checkerboard order (colour 0 slots ascending, then colour 1; FLAT stream): same-colour sites are not
+// neighbours, so the proposals, neighbour sums and random draws of a batch of 128 sites are prepared
+// by the 32 lanes in parallel and only the short acceptance recurrence runs serially on lane 0.  The
+// kernel works on the lattice's colour planes directly.  Per attempt (restating importance_sampling.jl:69-85,
 // ensembles/multicanonical.jl:25-30, algorithms/wang_landau.jl:29-37, binned_object.jl:22-24):
 //     log_ratio = lw[bin(x_new)] - lw[bin(x_old)]
 //     accepted  = log_ratio > 0 || rand < exp(log_ratio)
@@ -23,21 +25,21 @@ namespace mcx {
 
 namespace {
 
-constexpr int kFlatThreads = 32;          // one warp = 32 chains per block: spreads chains over SMs
+constexpr int kWarps = 4;                 // chains per block (one warp each)
+constexpr int kBatch = 128;               // same-colour slots prepared in parallel per step (4 per lane)
 constexpr int kSmemBins = 8192;           // 32 KB of uint32 counters
 
 struct FlatParams {
-    int8_t *spins;              // [N][nchains]
-    long long *state;           // [nchains][4] pair, spin, spin2, accepted
+    LatView L;
+    long long *sums;            // [nchains][SUM_FIELDS]
     double *logweight;          // muca: [nbins]; WL: [nchains][nbins]
     unsigned long long *hist;   // [nbins]
     int *error;
-    int64_t start, step, nbins, N;
-    int Lx, Ly, Lz, ndim, nchains;
+    int64_t start, step, nbins;
     double beta_pair, logf, J;
     uint32_t seed_lo, seed_hi, first_chain;
     uint64_t sweep0;
-    int nsweeps, policy, step_shift, prefetch;
+    int nsweeps, policy, step_shift;
 };
 
 // rand < exp(log_ratio) for rand = m * 2^-32, m = hi << 16 | lo, decided exactly but cheaply:
@@ -47,18 +49,18 @@ struct FlatParams {
 //     p * 2^16 is the low half fetched and the full 32-bit comparison made.
 // The result equals (double)m * 2^-32 < exp(log_ratio) in every case.
 template <class LoFn>
-__device__ __forceinline__ bool draw_less_exp(uint32_t hi, double log_ratio, LoFn lo_fn)
+__device__ __forceinline__ bool draw_less_exp(float hif, double log_ratio, LoFn lo_fn)
 {
     const float lf = (float)log_ratio;
     const float p16 = __expf(lf) * 65536.0f;
     const float eps = 3.0e-6f + fabsf(lf) * 1.0e-6f;       // > 4x the worst-case relative error of p16
-    if ((float)(hi + 1) <= p16 * (1.0f - eps)) return true;
-    if (hi > 0 && (float)hi >= p16 * (1.0f + eps)) return false;   // hi == 0: a denormal p could still win
-    const double p = exp(log_ratio), pd16 = p * 65536.0;
-    if ((double)(hi + 1) <= pd16) return true;
-    if ((double)hi >= pd16) return false;
+    if (hif + 1.0f <= p16 * (1.0f - eps)) return true;
+    if (hif > 0.0f && hif >= p16 * (1.0f + eps)) return false;   // hi == 0: a denormal p could still win
+    const double p = exp(log_ratio), pd16 = p * 65536.0, hid = (double)hif;
+    if (hid + 1.0 <= pd16) return true;
+    if (hid >= pd16) return false;
     const uint32_t lo = lo_fn();
-    return (double)((hi << 16) | lo) * (1.0 / 4294967296.0) < p;
+    return (hid * 65536.0 + (double)lo) * (1.0 / 4294967296.0) < p;
 }
 
 // div(x - start, step) truncating toward zero like Julia's div (binned_object.jl:22-24)
@@ -69,189 +71,200 @@ __device__ __forceinline__ int64_t bin_of(int64_t x, int64_t start, int64_t step
     return d / step;
 }
 
+// physical neighbour-spin sum of the site in slot q of colour `colour` (all neighbours sit in `oth`)
+__device__ __forceinline__ int neighbour_sum(const LatView &L, const uint8_t *oth, uint32_t q, int colour)
+{
+    const uint32_t half = (uint32_t)L.half;
+    const uint32_t row = q / half, j = q - row * half;
+    const uint32_t y = row % (uint32_t)L.Ly, z = row / (uint32_t)L.Ly;
+    const int x = (int)(2 * j + ((colour + y + z) & 1));
+    const int64_t rb = (int64_t)row * half;
+    const int xl = x == 0 ? L.Lx - 1 : x - 1, xr = x == L.Lx - 1 ? 0 : x + 1;
+    int raw = oth[rb + (xl >> 1)] + oth[rb + (xr >> 1)];
+    if (L.ndim > 1) {
+        const uint32_t yu = y == 0 ? L.Ly - 1 : y - 1, yd = y == (uint32_t)L.Ly - 1 ? 0 : y + 1;
+        raw += oth[((int64_t)z * L.Ly + yu) * half + j] + oth[((int64_t)z * L.Ly + yd) * half + j];
+    }
+    if (L.ndim > 2) {
+        const uint32_t zu = z == 0 ? L.Lz - 1 : z - 1, zd = z == (uint32_t)L.Lz - 1 ? 0 : z + 1;
+        raw += oth[((int64_t)zu * L.Ly + y) * half + j] + oth[((int64_t)zd * L.Ly + y) * half + j];
+    }
+    return L.model == MCX_ISING ? 2 * raw - L.nn : raw - L.nn;
+}
+
+// One warp per chain.  Per batch of 128 same-colour slots:
+//   phase 1 (32 lanes): Philox blocks -> 16-bit draws; per site the proposal and its deltas
+//                       (no two sites of one colour are neighbours, so these do not depend on the
+//                        decisions inside the batch);
+//   phase 2 (lane 0):   the serial recurrence in the global observable: bin lookup, log-ratio,
+//                       _accept!, record_visit! / Wang-Landau update, running sums;
+//   phase 3 (32 lanes): accepted sites are written back.
 template <int OBS, int KIND, bool SMEM_HIST>
-__global__ void __launch_bounds__(kFlatThreads) k_flat_sweep(FlatParams P)
+__global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
 {
     extern __shared__ uint32_t s_hist[];
+    __shared__ int32_t s_d[kWarps][kBatch];      // packed deltas of each prepared site
+    __shared__ float s_hi[kWarps][kBatch];       // high half of the site's Float64 draw, as a float (exact)
+    __shared__ uint8_t s_b[kWarps][kBatch];      // Bool draw (Blume-Capel proposal)
+    __shared__ uint8_t s_acc[kWarps][kBatch];    // accepted flag of each site of the batch
     if (SMEM_HIST) {
         for (int i = threadIdx.x; i < P.nbins; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
     }
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < P.nchains) {
-        const int nch = P.nchains;
-        int8_t *sp = P.spins + c;
-        long long *st = P.state + (int64_t)c * 4;
-        long long pair = st[0], spin = st[1], spin2 = st[2], nacc = st[3];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kWarps + w;
+    if (c < P.L.nchains) {
+        const LatView &L = P.L;
+        long long *st = P.sums + (int64_t)c * SUM_FIELDS;
+        // chain state lives in lane 0's registers
+        long long pair = st[SUM_PAIR], spin = st[SUM_SPIN], spin2 = L.model == MCX_ISING ? 2 * L.halfN : st[SUM_SPIN2], nacc = 0;
         double *lw = P.logweight + (KIND == MCX_FLAT_WANG_LANDAU ? (int64_t)c * P.nbins : 0);
         const uint32_t chain_id = P.first_chain + (uint32_t)c;
-        const int Lx = P.Lx, Ly = P.Ly, Lz = P.Lz;
-        const int64_t sx = nch, sy = (int64_t)Lx * nch, sz = (int64_t)Lx * Ly * nch;
         const int shift = P.step_shift;
-        // bin and log-weight of the current state are carried from attempt to attempt
         int64_t io = bin_of(OBS == MCX_OBS_ENERGY ? -pair : spin2, P.start, P.step, shift);
-        bool dead = io < 0 || io >= P.nbins;
-        if (dead) atomicExch(P.error, 1);
+        int dead = io < 0 || io >= P.nbins;
+        if (dead && lane == 0) atomicExch(P.error, 1);
         double lw_old = dead ? 0.0 : lw[io];
-        // run-length cache for the global histogram (a chain revisits its current bin many times)
         int64_t run_bin = io;
         unsigned long long run_cnt = 0;
-        const int64_t pf = (int64_t)P.prefetch * nch;     // prefetch distance in bytes of the interleaved array
-        const int64_t total = P.N * (int64_t)nch;
-        for (int sw = 0; sw < P.nsweeps && !dead; ++sw) {
-            const uint64_t t = P.sweep0 + (uint64_t)sw;
-            Philox4 r0{}, r2{};
-            int64_t i = 0;
-            for (int z = 0; z < Lz && !dead; ++z)
-                for (int y = 0; y < Ly && !dead; ++y)
-                    for (int x = 0; x < Lx; ++x, ++i) {
-                        const int lane = (int)(i & 7);
-                        if (lane == 0) {
-                            r0 = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, (uint32_t)(i >> 3), 0);
-                            if (OBS == MCX_OBS_SPIN2_WITH_PAIR_BOLTZMANN)
-                                r2 = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, (uint32_t)(i >> 3), 2);
-                        }
-                        int8_t *p = sp + i * nch;
-                        if (pf) {
-                            // lines first touched `prefetch` sites ahead: the site's own row of the next
-                            // y (and, in 3-D, the z+1 and z-1 planes); addresses wrap like the lattice
-                            int64_t a = i * nch + pf;
-                            if (a >= total) a -= total;
-                            int64_t ay = a + sy; if (ay >= total) ay -= total;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + ay));
-                            if (P.ndim > 2) {
-                                int64_t az = a + sz; if (az >= total) az -= total;
-                                int64_t aw = a - sz; if (aw < 0) aw += total;
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + az));
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp + aw));
-                            }
-                        }
-                        const int s = *p;
-                        int nb = p[x == 0 ? (Lx - 1) * sx : -sx] + p[x == Lx - 1 ? -(Lx - 1) * sx : sx];
-                        if (P.ndim > 1) nb += p[y == 0 ? (Ly - 1) * sy : -sy] + p[y == Ly - 1 ? -(Ly - 1) * sy : sy];
-                        if (P.ndim > 2) nb += p[z == 0 ? (Lz - 1) * sz : -sz] + p[z == Lz - 1 ? -(Lz - 1) * sz : sz];
+        const uint32_t halfN = (uint32_t)L.halfN;
+        constexpr uint32_t PF = OBS == MCX_OBS_ENERGY ? 0 : 2;     // plane of the Float64 draw's high half
 
-                        int s_new, dpair, dspin, dspin2;
-                        int64_t x_new;
-                        uint32_t hi;
-                        uint32_t lo_plane;
-                        if (OBS == MCX_OBS_ENERGY) {
-                            // flip_changes / delta_energy (ising.jl:187-198), integer path J = 1, h = 0
-                            s_new = -s; dpair = -2 * s * nb; dspin = -2 * s; dspin2 = 0;
-                            x_new = -pair - dpair;
-                            hi = lane16(r0, lane); lo_plane = 1;
-                        } else {
-                            // _propose_state + propose_changes (blume_capel.jl:21-30,235-241),
-                            // H = (J*sum_pair, sum_spins2) as in muca_BlumeCapel.jl:81-89
-                            const int b = (int)(lane16(r0, lane) >> 15);
-                            s_new = s == -1 ? (b ? 0 : 1) : s == 0 ? (b ? -1 : 1) : (b ? -1 : 0);
-                            dspin = s_new - s; dspin2 = s_new * s_new - s * s; dpair = dspin * nb;
-                            x_new = spin2 + dspin2;
-                            hi = lane16(r2, lane); lo_plane = 3;
-                        }
-                        // _binindex for integer bins: div(x - start, step) + 1 (binned_object.jl:22-24); 0-based here
-                        const int64_t in = bin_of(x_new, P.start, P.step, shift);
-                        const bool inside = in >= 0 && in < P.nbins;
-                        if (!inside && P.policy == 0) {                          // BoundsError
-                            atomicExch(P.error, 1);
-                            dead = true;
-                            break;
-                        }
-                        bool accepted = false;
-                        double lw_new = lw_old;
-                        if (inside) {
-                            lw_new = in == io ? lw_old : lw[in];
-                            double log_ratio;
-                            if (OBS == MCX_OBS_ENERGY) {
-                                log_ratio = lw_new - lw_old;
-                            } else {
-                                const double Ho1 = P.J * (P.J * (double)pair);
-                                const double Hn1 = Ho1 + P.J * (P.J * (double)dpair);
-                                log_ratio = (-P.beta_pair * Hn1 + lw_new) - (-P.beta_pair * Ho1 + lw_old);
+        for (int sw = 0; sw < P.nsweeps && !dead; ++sw)
+            for (int colour = 0; colour < 2 && !dead; ++colour) {
+                const uint64_t t = 2 * (P.sweep0 + (uint64_t)sw) + (uint64_t)colour;
+                uint8_t *tgt = plane_ptr(L, c, colour);
+                const uint8_t *oth = plane_ptr(L, c, colour ^ 1);
+                for (uint32_t qb = 0; qb < halfN && !dead; qb += kBatch) {
+                    const int cnt = (int)min((uint32_t)kBatch, halfN - qb);
+                    // ---- phase 1a: draws.  lanes 0-15: the Float64 plane; lanes 16-31: the Bool plane
+                    {
+                        const uint32_t plane = lane < 16 ? PF : 0;
+                        const int bl = lane & 15;
+                        if (lane < 16 || OBS != MCX_OBS_ENERGY) {
+                            const Philox4 r = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, (qb >> 3) + bl, plane);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint32_t v = lane16(r, k);
+                                if (lane < 16) s_hi[w][8 * bl + k] = (float)v;
+                                else s_b[w][8 * bl + k] = (uint8_t)(v >> 15);
                             }
-                            // _accept! (importance_sampling.jl:80-85)
-                            if (log_ratio > 0) accepted = true;
-                            else accepted = draw_less_exp(hi, log_ratio, [&]() {
-                                const Philox4 rl = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t,
-                                                                (uint32_t)(i >> 3), lo_plane);
-                                return lane16(rl, lane);
-                            });
-                        }
-                        if (accepted) {
-                            *p = (int8_t)s_new;
-                            pair += dpair; spin += dspin; spin2 += dspin2; nacc += 1;
-                            io = in; lw_old = lw_new;
-                        }
-                        // record_visit! / Wang-Landau update at the visited bin (= io after the move)
-                        if (KIND == MCX_FLAT_MUCA) {
-                            if (SMEM_HIST) atomicAdd(&s_hist[io], 1u);
-                            else if (io == run_bin) run_cnt += 1;
-                            else {
-                                if (run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
-                                run_bin = io; run_cnt = 1;
-                            }
-                        } else {
-                            lw_old -= P.logf;
-                            lw[io] = lw_old;
                         }
                     }
+                    __syncwarp();
+                    // ---- phase 1b: proposal and deltas of every site of the batch
+#pragma unroll
+                    for (int j = 0; j < kBatch / 32; ++j) {
+                        const int idx = 32 * j + lane;
+                        if (idx < cnt) {
+                            const uint32_t q = qb + idx;
+                            const int nb = neighbour_sum(L, oth, q, colour);
+                            const int enc = tgt[q];
+                            int32_t d;
+                            if (OBS == MCX_OBS_ENERGY) {
+                                // flip_changes / delta_energy (ising.jl:187-198), integer path J = 1, h = 0
+                                const int s = 2 * enc - 1;
+                                const int dE = 2 * s * nb;                       // = -dpair
+                                d = (dE & 0xff) | ((s & 0xff) << 8);
+                            } else {
+                                // _propose_state + propose_changes (blume_capel.jl:21-30,235-241)
+                                const int s = enc - 1, b = s_b[w][idx];
+                                const int s_new = s == -1 ? (b ? 0 : 1) : s == 0 ? (b ? -1 : 1) : (b ? -1 : 0);
+                                const int dspin = s_new - s, dspin2 = s_new * s_new - s * s, dpair = dspin * nb;
+                                d = (dspin & 0xff) | ((dspin2 & 0xff) << 8) | ((dpair & 0xff) << 16) | ((s_new + 1) << 24);
+                            }
+                            s_d[w][idx] = d;
+                        }
+                    }
+                    __syncwarp();
+                    // ---- phase 2: the chain's serial recurrence (lane 0)
+                    if (lane == 0) {
+                        for (int idx = 0; idx < cnt; ++idx) {
+                            const int32_t d = s_d[w][idx];
+                            int dpair, dspin, dspin2;
+                            int64_t x_new;
+                            if (OBS == MCX_OBS_ENERGY) {
+                                const int dE = (int8_t)(d & 0xff), s = (int8_t)((d >> 8) & 0xff);
+                                dpair = -dE; dspin = -2 * s; dspin2 = 0;
+                                x_new = -pair + dE;
+                            } else {
+                                dspin = (int8_t)(d & 0xff); dspin2 = (int8_t)((d >> 8) & 0xff); dpair = (int8_t)((d >> 16) & 0xff);
+                                x_new = spin2 + dspin2;          // H = (J*sum_pair, sum_spins2), muca_BlumeCapel.jl:81-89
+                            }
+                            // _binindex for integer bins: div(x - start, step) + 1 (binned_object.jl:22-24); 0-based here
+                            const int64_t in = bin_of(x_new, P.start, P.step, shift);
+                            const bool inside = in >= 0 && in < P.nbins;
+                            if (!inside && P.policy == 0) {                          // BoundsError
+                                atomicExch(P.error, 1);
+                                dead = 1;
+                                break;
+                            }
+                            bool accepted = false;
+                            double lw_new = lw_old;
+                            if (inside) {
+                                lw_new = in == io ? lw_old : lw[in];
+                                double log_ratio;
+                                if (OBS == MCX_OBS_ENERGY) {
+                                    log_ratio = lw_new - lw_old;
+                                } else {
+                                    const double Ho1 = P.J * (P.J * (double)pair);
+                                    const double Hn1 = Ho1 + P.J * (P.J * (double)dpair);
+                                    log_ratio = (-P.beta_pair * Hn1 + lw_new) - (-P.beta_pair * Ho1 + lw_old);
+                                }
+                                // _accept! (importance_sampling.jl:80-85)
+                                if (log_ratio > 0) accepted = true;
+                                else accepted = draw_less_exp(s_hi[w][idx], log_ratio, [&]() {
+                                    const uint32_t q = qb + idx;
+                                    const Philox4 rl = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, q >> 3, PF + 1);
+                                    return lane16(rl, (int)(q & 7));
+                                });
+                            }
+                            if (accepted) {
+                                pair += dpair; spin += dspin; spin2 += dspin2; nacc += 1;
+                                io = in; lw_old = lw_new;
+                            }
+                            s_acc[w][idx] = (uint8_t)accepted;
+                            // record_visit! / Wang-Landau update at the visited bin (= io after the move)
+                            if (KIND == MCX_FLAT_MUCA) {
+                                if (SMEM_HIST) atomicAdd(&s_hist[io], 1u);
+                                else if (io == run_bin) run_cnt += 1;
+                                else {
+                                    if (run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
+                                    run_bin = io; run_cnt = 1;
+                                }
+                            } else {
+                                lw_old -= P.logf;
+                                lw[io] = lw_old;
+                            }
+                        }
+                    }
+                    dead = __shfl_sync(0xffffffffu, dead, 0);
+                    __syncwarp();
+                    // ---- phase 3: write the accepted sites back
+#pragma unroll
+                    for (int j = 0; j < kBatch / 32; ++j) {
+                        const int idx = 32 * j + lane;
+                        if (idx < cnt && s_acc[w][idx]) {
+                            const uint32_t q = qb + idx;
+                            if (OBS == MCX_OBS_ENERGY) tgt[q] ^= 1;
+                            else tgt[q] = (uint8_t)(s_d[w][idx] >> 24);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        if (lane == 0) {
+            if (KIND == MCX_FLAT_MUCA && !SMEM_HIST && run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
+            st[SUM_PAIR] = pair; st[SUM_SPIN] = spin;
+            if (L.model != MCX_ISING) st[SUM_SPIN2] = spin2;
+            st[SUM_ACC] += nacc;
         }
-        if (KIND == MCX_FLAT_MUCA && !SMEM_HIST && run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
-        st[0] = pair; st[1] = spin; st[2] = spin2; st[3] = nacc;
     }
     if (SMEM_HIST) {
         __syncthreads();
         for (int i = threadIdx.x; i < P.nbins; i += blockDim.x)
             if (s_hist[i]) atomicAdd(P.hist + i, (unsigned long long)s_hist[i]);
     }
-}
-
-// planes (colour-split, encoded) <-> chain-interleaved physical spins
-__global__ void k_flat_load(LatView L, int8_t *__restrict__ il, int64_t N)
-{
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N * L.nchains) return;
-    const int c = (int)(idx % L.nchains);
-    const int64_t i = idx / L.nchains;
-    const int x = (int)(i % L.Lx);
-    const int64_t row = i / L.Lx;
-    const int y = (int)(row % L.Ly), z = (int)(row / L.Ly);
-    const int enc = plane_ptr(L, c, (x + y + z) & 1)[row * L.half + (x >> 1)];
-    il[idx] = L.model == MCX_ISING ? (int8_t)(2 * enc - 1) : (int8_t)(enc - 1);
-}
-
-__global__ void k_flat_store(LatView L, const int8_t *__restrict__ il, int64_t N)
-{
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= N * L.nchains) return;
-    const int c = (int)(idx % L.nchains);
-    const int64_t i = idx / L.nchains;
-    const int x = (int)(i % L.Lx);
-    const int64_t row = i / L.Lx;
-    const int y = (int)(row % L.Ly), z = (int)(row / L.Ly);
-    const int v = il[idx];
-    plane_ptr(L, c, (x + y + z) & 1)[row * L.half + (x >> 1)] = L.model == MCX_ISING ? (uint8_t)(v > 0) : (uint8_t)(v + 1);
-}
-
-__global__ void k_flat_state_in(const long long *__restrict__ sums, long long *__restrict__ state, int nchains, int64_t N,
-                                int model)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchains) return;
-    state[c * 4 + 0] = sums[c * SUM_FIELDS + SUM_PAIR];
-    state[c * 4 + 1] = sums[c * SUM_FIELDS + SUM_SPIN];
-    state[c * 4 + 2] = model == MCX_ISING ? N : sums[c * SUM_FIELDS + SUM_SPIN2];
-    state[c * 4 + 3] = 0;
-}
-
-__global__ void k_flat_state_out(long long *__restrict__ sums, const long long *__restrict__ state, int nchains)
-{
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nchains) return;
-    sums[c * SUM_FIELDS + SUM_PAIR] = state[c * 4 + 0];
-    sums[c * SUM_FIELDS + SUM_SPIN] = state[c * 4 + 1];
-    sums[c * SUM_FIELDS + SUM_SPIN2] = state[c * 4 + 2];
-    sums[c * SUM_FIELDS + SUM_ACC] += state[c * 4 + 3];
 }
 
 // update!(ens::MulticanonicalEnsemble; mode=:simple): lw -= (h > 0 ? log(h) : 0) (multicanonical.jl:32-44)
@@ -267,56 +280,33 @@ template <int OBS, int KIND>
 void launch_sweep_t(mcx_flat *f, const FlatParams &P)
 {
     mcx_lattice *lat = f->lat;
-    const int blocks = (lat->nchains + kFlatThreads - 1) / kFlatThreads;
+    const int blocks = (lat->nchains + kWarps - 1) / kWarps;
     const bool smem = KIND == MCX_FLAT_MUCA && f->nbins <= kSmemBins;
     if (smem)
-        k_flat_sweep<OBS, KIND, true><<<blocks, kFlatThreads, (size_t)f->nbins * sizeof(uint32_t), lat->ctx->stream>>>(P);
+        k_flat_warp<OBS, KIND, true><<<blocks, kWarps * 32, (size_t)f->nbins * sizeof(uint32_t), lat->ctx->stream>>>(P);
     else
-        k_flat_sweep<OBS, KIND, false><<<blocks, kFlatThreads, 0, lat->ctx->stream>>>(P);
+        k_flat_warp<OBS, KIND, false><<<blocks, kWarps * 32, 0, lat->ctx->stream>>>(P);
     lat->ctx->launches++;
 }
 
 }  // namespace
 
-void launch_flat_load(mcx_flat *f)
-{
-    mcx_lattice *lat = f->lat;
-    const int64_t n = lat->N * lat->nchains;
-    k_flat_load<<<(unsigned)((n + 255) / 256), 256, 0, lat->ctx->stream>>>(lat->view, f->d_spins, lat->N);
-    k_flat_state_in<<<(lat->nchains + 127) / 128, 128, 0, lat->ctx->stream>>>(lat->d_sums, f->d_state, lat->nchains, lat->N,
-                                                                            lat->model);
-    lat->ctx->launches += 2;
-}
-
-void launch_flat_store(mcx_flat *f)
-{
-    mcx_lattice *lat = f->lat;
-    const int64_t n = lat->N * lat->nchains;
-    k_flat_store<<<(unsigned)((n + 255) / 256), 256, 0, lat->ctx->stream>>>(lat->view, f->d_spins, lat->N);
-    k_flat_state_out<<<(lat->nchains + 127) / 128, 128, 0, lat->ctx->stream>>>(lat->d_sums, f->d_state, lat->nchains);
-    lat->ctx->launches += 2;
-}
+void launch_flat_load(mcx_flat *) {}     // the warp-per-chain kernel works on the colour planes directly
+void launch_flat_store(mcx_flat *) {}
 
 void launch_flat_sweep(mcx_flat *f, uint64_t sweep0, int nsweeps)
 {
     mcx_lattice *lat = f->lat;
     FlatParams P;
-    P.spins = f->d_spins; P.state = f->d_state; P.logweight = f->d_logweight;
+    P.L = lat->view; P.sums = lat->d_sums; P.logweight = f->d_logweight;
     P.hist = (unsigned long long *)f->d_histogram; P.error = f->d_error;
-    P.start = f->start; P.step = f->step; P.nbins = f->nbins; P.N = lat->N;
-    P.Lx = lat->dims[0]; P.Ly = lat->dims[1]; P.Lz = lat->dims[2]; P.ndim = lat->ndim; P.nchains = lat->nchains;
+    P.start = f->start; P.step = f->step; P.nbins = f->nbins;
     P.beta_pair = f->beta_pair; P.logf = f->logf; P.J = lat->J;
     P.seed_lo = (uint32_t)lat->seed; P.seed_hi = (uint32_t)(lat->seed >> 32); P.first_chain = lat->first_chain;
     P.sweep0 = sweep0; P.nsweeps = nsweeps; P.policy = f->policy;
     P.step_shift = -1;
     for (int sh = 0; sh < 62; ++sh)
         if (f->step == ((int64_t)1 << sh)) P.step_shift = sh;
-    {
-        // software prefetch only pays when the interleaved spins do not sit in L2 anyway
-        const char *e = getenv("MCX_FLAT_PREFETCH");
-        const double bytes = (double)lat->N * lat->nchains;
-        P.prefetch = e ? atoi(e) : (bytes > 48.0e6 ? 24 : 0);
-    }
     if (f->observable == MCX_OBS_ENERGY) {
         if (f->kind == MCX_FLAT_MUCA) launch_sweep_t<MCX_OBS_ENERGY, MCX_FLAT_MUCA>(f, P);
         else launch_sweep_t<MCX_OBS_ENERGY, MCX_FLAT_WANG_LANDAU>(f, P);
@@ -354,6 +344,7 @@ int32_t mcx_flat_create(mcx_lattice *lat, int32_t kind, int32_t observable, int6
     FREQ(observable == MCX_OBS_ENERGY || observable == MCX_OBS_SPIN2_WITH_PAIR_BOLTZMANN, MCX_ERR_ARGUMENT, "unknown observable");
     FREQ(bin_step > 0 && nbins >= 1, MCX_ERR_ARGUMENT, "bins need step > 0 and at least one bin");
     FREQ(out_of_range_policy == 0 || out_of_range_policy == 1, MCX_ERR_ARGUMENT, "policy must be 0 (BoundsError) or 1 (reject)");
+    FREQ(lat->view.halfN < ((int64_t)1 << 31), MCX_ERR_UNSUPPORTED, "flat-histogram chains support up to 2^32 sites per lattice");
     if (observable == MCX_OBS_ENERGY)
         FREQ(lat->model == MCX_ISING && lat->J == 1.0 && lat->h == 0.0, MCX_ERR_UNSUPPORTED,
              "the energy observable is the integer path: Ising with J = 1, h = 0");
@@ -369,8 +360,6 @@ int32_t mcx_flat_create(mcx_lattice *lat, int32_t kind, int32_t observable, int6
     cudaError_t e;
     if ((e = cudaMalloc((void **)&f->d_logweight, sizeof(double) * (size_t)nbins * f->ntables)) != cudaSuccess ||
         (e = cudaMalloc((void **)&f->d_histogram, sizeof(unsigned long long) * (size_t)nbins)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&f->d_spins, (size_t)lat->N * lat->nchains)) != cudaSuccess ||
-        (e = cudaMalloc((void **)&f->d_state, sizeof(long long) * 4 * (size_t)lat->nchains)) != cudaSuccess ||
         (e = cudaMalloc((void **)&f->d_error, sizeof(int))) != cudaSuccess) {
         mcx_flat_destroy(f);
         return mcx_set_error(MCX_ERR_CUDA, cudaGetErrorString(e));
@@ -387,7 +376,7 @@ int32_t mcx_flat_destroy(mcx_flat *f)
     if (!f) return MCX_OK;
     cudaSetDevice(f->lat->ctx->device);
     cudaStreamSynchronize(f->lat->ctx->stream);
-    cudaFree(f->d_logweight); cudaFree(f->d_histogram); cudaFree(f->d_spins); cudaFree(f->d_state); cudaFree(f->d_error);
+    cudaFree(f->d_logweight); cudaFree(f->d_histogram); cudaFree(f->d_error);
     delete f;
     return MCX_OK;
 }
@@ -464,16 +453,14 @@ int32_t mcx_flat_sweep(mcx_flat *f, int64_t nsweeps)
     mcx_lattice *lat = f->lat;
     FCUDA(cudaSetDevice(lat->ctx->device));
     if (lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
-    launch_flat_load(f);
     // shared-memory counters are 32-bit: bound the attempts one block can record per launch
-    const double per_sweep = 32.0 * (double)lat->N;
+    const double per_sweep = 4.0 * (double)lat->N;
     int64_t chunk = (int64_t)(4.0e9 / per_sweep);
     if (chunk < 1) chunk = 1;
     for (int64_t done = 0; done < nsweeps; done += chunk) {
         const int n = (int)((nsweeps - done) < chunk ? (nsweeps - done) : chunk);
         launch_flat_sweep(f, lat->sweep + (uint64_t)done, n);
     }
-    launch_flat_store(f);
     lat->sweep += (uint64_t)nsweeps;
     lat->steps += nsweeps * lat->N;
     FCUDA(cudaGetLastError());

@@ -753,16 +753,23 @@ int mcxo_flat_accept(mcxo_alg *a, mcxo_flat *f, int kind, int64_t x_new, int64_t
     return accepted;
 }
 
-/* Sequential-site flat-histogram sweeps: the reference's spin_flip!(sys, alg::ImportanceSampling)
- * (ising.jl:25-33; muca_BlumeCapel.jl:81-89 for the (pair, spin^2) tuple observable) applied at
- * sites 0..N-1 in order, stream positioned at (chain, FLAT, sweep, site). */
+/* Flat-histogram sweeps: the reference's spin_flip!(sys, alg::ImportanceSampling) (ising.jl:25-33;
+ * muca_BlumeCapel.jl:81-89 for the (pair, spin^2) tuple observable) applied once per site per sweep,
+ * one site after the other (the acceptance depends on the chain's global observable), in
+ * checkerboard order: all colour-0 sites in slot order, then all colour-1 sites.  The stream is
+ * positioned at (chain, FLAT, 2*sweep + colour, slot) with slot = row*(Lx/2) + (x>>1) as for SWEEP. */
 int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int observable,
                     double beta_pair, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps)
 {
     mcxo_rng r; r.seed = seed; r.chain = chain;
+    const int64_t Lx = s->dims[0], Ly = s->dims[1], half = Lx / 2;
     for (int64_t sw = 0; sw < nsweeps; ++sw)
+        for (int colour = 0; colour < 2; ++colour)
         for (int64_t i = 0; i < s->N; ++i) {
-            mcxo_rng_position(&r, MCXO_TAG_FLAT, sweep0 + (uint64_t)sw, (uint64_t)i);
+            const int64_t xx = i % Lx, row = i / Lx, yy = row % Ly, zz = row / Ly;
+            if (((xx + yy + zz) & 1) != colour) continue;
+            mcxo_rng_position(&r, MCXO_TAG_FLAT, 2 * (sweep0 + (uint64_t)sw) + (uint64_t)colour,
+                              (uint64_t)(row * half + (xx >> 1)));
             if (observable == 0) {
                 double dpair; int64_t dspin;
                 ising_flip_changes(s, i, &dpair, &dspin);

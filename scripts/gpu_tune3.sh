@@ -1,9 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-./scripts/ubench_pipes > gpurun_out/ubench_pipes.log 2>&1
-cat gpurun_out/ubench_pipes.log
 : > gpurun_out/tune3.log
-for LIBV in default SHF IMADSUB; do
+for LIBV in default SHF; do
   if [ "$LIBV" == "default" ]; then unset MCX_B200_LIB; else export MCX_B200_LIB=$PWD/montecarlox.jl_b200/lib/variants/libmcx_$LIBV.so; fi
   for rep in 1 2; do
     out=$(timeout 300 python bench.py --steps 2 --warmup 2 --sweeps-per-step 20 --no-pt --no-cpu 2>&1 | tail -1)
