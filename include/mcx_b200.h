@@ -183,7 +183,9 @@ int32_t mcx_pt_set_state(mcx_pt *pt, const int64_t *indices, const int64_t *step
  * ensembles/wang_landau.jl:23, reset! algorithms/multicanonical.jl:27-33,
  * merge_histograms!/distribute_logweight! parallel_multicanonical.jl:38-73.
  * Chains are serial in the global observable, so parallelism is across chains only; the
- * sweep visits sites 0..N-1 in order (FLAT stream).  Integer bins start:step:start+step*(n-1)
+ * sweep visits every site once, serially, in checkerboard order (all colour-0 slots ascending,
+ * then all colour-1 slots; FLAT stream), which lets a warp prepare the proposals of a batch of
+ * same-colour sites in parallel.  Integer bins start:step:start+step*(n-1)
  * (BinnedObject, binned_object.jl:13-24); an out-of-range lookup makes the next synchronising
  * call return MCX_ERR_BOUNDS (out_of_range_policy 0, the reference's behaviour,
  * test/test_multicanonical.jl:39-43) or is rejected as a move (policy 1: energy windows, which the
