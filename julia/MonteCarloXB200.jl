@@ -104,6 +104,9 @@ Random.rand(r::PhiloxRNG, ::Random.SamplerType{UInt64}) = r.site
 # ----------------------------------------------------------------------------------------------
 function sweep!(sys::SpinSystems.AbstractSpinSystem, alg, dims::Vector{Int}, sweep0::Integer, nsweeps::Integer)
     rng = alg.rng::PhiloxRNG
+    # canonical rules (local acceptance) use the SWEEP stream; flat-histogram ensembles
+    # (ImportanceSampling with a Multicanonical / WangLandau ensemble: ising.jl:25-33) the FLAT stream
+    tag = (alg isa MonteCarloX.AbstractMetropolis || alg isa MonteCarloX.HeatBath) ? TAG_SWEEP : TAG_FLAT
     Lx = dims[1]; Ly = length(dims) > 1 ? dims[2] : 1
     half = Lx ÷ 2
     for s in 0:nsweeps-1, colour in 0:1
@@ -111,7 +114,7 @@ function sweep!(sys::SpinSystems.AbstractSpinSystem, alg, dims::Vector{Int}, swe
         for i in 0:length(sys.spins)-1
             x = i % Lx; row = i ÷ Lx; y = row % Ly; z = row ÷ Ly
             ((x + y + z) & 1) == colour || continue
-            position!(rng, TAG_SWEEP, t, row * half + (x >> 1), i)
+            position!(rng, tag, t, row * half + (x >> 1), i)
             spin_flip!(sys, alg)           # reference code, untouched (ising.jl:35-58, blume_capel.jl:52-85)
         end
     end
