@@ -650,22 +650,16 @@ void launch_ring(mcx_lattice *lat, uint64_t t)
     lat->ctx->launches++;
 }
 
-// MCX_VARIANT (tuning hook): 0 = 5 CTAs/SM + register prefetch, 1 = 6 + prefetch, 2 = 8 + prefetch,
-// 3 = 6, loads at the top of the trip (default), 4 = 8 likewise, 5..8 = cp.async ring
-// (6 CTAs x 2 stages, 6 x 3, 8 x 2, 5 x 3)
+// MCX_VARIANT (tuning hook; every variant produces the same trajectories): default = 6 CTAs/SM with the
+// trip's loads issued before the Philox rounds; 0 = 5 CTAs/SM with a one-trip register prefetch;
+// 6 = 6 CTAs/SM with a 3-stage cp.async ring.  Measured in profiles/r01_tune_variants.log.
 template <int COLOUR, bool HEATBATH, bool TRACK>
 void launch_t(mcx_lattice *lat, uint64_t t)
 {
     const int variant = env_int("MCX_VARIANT", 3);
     switch (variant) {
     case 0: launch_v<COLOUR, HEATBATH, TRACK, 5, true>(lat, t); break;
-    case 1: launch_v<COLOUR, HEATBATH, TRACK, 6, true>(lat, t); break;
-    case 2: launch_v<COLOUR, HEATBATH, TRACK, 8, true>(lat, t); break;
-    case 4: launch_v<COLOUR, HEATBATH, TRACK, 8, false>(lat, t); break;
-    case 5: launch_ring<COLOUR, HEATBATH, TRACK, 6, 2>(lat, t); break;
     case 6: launch_ring<COLOUR, HEATBATH, TRACK, 6, 3>(lat, t); break;
-    case 7: launch_ring<COLOUR, HEATBATH, TRACK, 8, 2>(lat, t); break;
-    case 8: launch_ring<COLOUR, HEATBATH, TRACK, 5, 3>(lat, t); break;
     default: launch_v<COLOUR, HEATBATH, TRACK, 6, false>(lat, t); break;
     }
 }
@@ -739,6 +733,13 @@ bool launch_recompute_ising2d(mcx_lattice *lat)
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8) return false;
+    // small lattices: a chain yields fewer than one CTA of 16-byte segments x strips, so most lanes of
+    // this kernel would idle; the rows-of-8 kernel (8 sites per thread) fills the machine instead
+    {
+        const int R = pick_rows_per_strip(lat->view.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
+        const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
+        if (G < 96 && getenv("MCX_VARIANT") == nullptr && getenv("MCX_ROWS_PER_STRIP") == nullptr) return false;
+    }
     if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
     return true;
 }

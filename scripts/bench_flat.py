@@ -89,3 +89,5 @@ if __name__ == "__main__":
         print(json.dumps(canonical(1, [256, 256, 256], 1, 10)))
         print(json.dumps(canonical(0, [8176, 8176], 1, 10)))
         print(json.dumps(canonical(0, [1000, 1000], 64, 10)))
+        print(json.dumps(canonical(0, [64, 64], 16384, 20)))
+        print(json.dumps(canonical(0, [128, 128], 4096, 20)))

@@ -68,7 +68,7 @@ def test_fast_kernel_equals_generic_kernel(m, L):
     outs = []
     keys = ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP", "MCX_VARIANT")
     envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_FORCE_GENERIC": "2"}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
-    envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in range(9) for r in ("4", "16")]
+    envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in (0, 3, 6) for r in ("4", "16")]
     for env in envs:
         for k in keys:
             os.environ.pop(k, None)
