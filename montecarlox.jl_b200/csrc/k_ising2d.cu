@@ -102,7 +102,11 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
     const uint32_t tw[4] = {tq.x, tq.y, tq.z, tq.w};
     const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};   // word k: sites 2k, 2k+1
     uint32_t nw[4];
-    uint32_t tie = 0;
+    // r = (h15 | 0x8000) - t15 per 16-bit half: bit 15 set <=> h15 >= t15 (not surely accepted); as a
+    // signed halfword r is most negative (0x8000) exactly on a tie, so one packed signed min
+    // (VIMNMX3.S16x2) accumulates the tie test for the whole thread-row.
+    uint32_t tie_min = 0x7fff7fffu;
+    int rejected = 0;                                            // minus the number of not-accepted sites
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
         const uint32_t idx4 = tw[w] * 20u + nup[w] * 4u;        // byte b = 4 * (5 s + nup) of site 4w+b
@@ -110,22 +114,22 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
         const uint32_t ttB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (idx4 >> 16));
         const uint32_t hA = (shr1_fma(rw[2 * w]) & 0x7fff7fffu) | 0x80008000u;
         const uint32_t hB = (shr1_fma(rw[2 * w + 1]) & 0x7fff7fffu) | 0x80008000u;
-#ifndef MCX_OPT_ALUSUB
-        uint32_t rA, rB, qA, qB;   // subtractions issued as IMAD: measured +3% (the ALU pipe is the contended one)
+#ifdef MCX_OPT_ALUSUB
+        const uint32_t rA = hA - ttA, rB = hB - ttB;
+#else
+        uint32_t rA, rB;   // subtractions issued as IMAD
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rA) : "r"(ttA), "r"(hA));
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rB) : "r"(ttB), "r"(hB));
-        asm("mad.lo.u32 %0, %1, 1, 0xfffeffff;" : "=r"(qA) : "r"(rA));
-        asm("mad.lo.u32 %0, %1, 1, 0xfffeffff;" : "=r"(qB) : "r"(rB));
-#else
-        const uint32_t rA = hA - ttA, rB = hB - ttB;
-        const uint32_t qA = rA - 0x00010001u, qB = rB - 0x00010001u;
 #endif
-        tie |= (rA & ~qA) | (rB & ~qB);
-        const uint32_t P = __byte_perm(rA, rB, 0x7531);          // bit 7 of byte b: site 4w+b NOT accepted
-        const uint32_t F = (~P & 0x80808080u) >> 7;              // 0x01 per accepted site
-        nw[w] = HEATBATH ? F : (tw[w] ^ F);
+        tie_min = __vmins2(__vmins2(tie_min, rA), rB);
+        // bytes 1,3 of rA and rB with sign replication: 0xFF per site that is NOT accepted, else 0x00
+        uint32_t P;   // prmt with the selector msb set replicates the byte's sign bit (__byte_perm masks that bit off)
+        asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(P) : "r"(rA), "r"(rB));
+        nw[w] = HEATBATH ? (~P & 0x01010101u) : (tw[w] ^ (~P & 0x01010101u));
+        if (!HEATBATH && !TRACK) rejected = __dp4a((int)P, 0x01010101, rejected);
     }
-    if (tie & 0x80008000u) {
+    const bool tie = ((tie_min & 0x7fffu) == 0u) || ((tie_min & 0x7fff0000u) == 0u);
+    if (tie) {
         // rare (2^-15 per site): settle the whole thread-row with the full 32-bit draws
         const Philox4 la = philox4x32_10(blk, t_lo, c2lo, chain_id, seed_lo, seed_hi);
         const Philox4 lb = philox4x32_10(blk + 1, t_lo, c2lo, chain_id, seed_lo, seed_hi);
@@ -133,23 +137,27 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
         nw[0] = ex.x; nw[1] = ex.y; nw[2] = ex.z; nw[3] = ex.w;
     }
     if (active) {
-        uint32_t fsum = 0, ssum = 0, nsum = 0, snsum = 0;
+        if (!HEATBATH && !TRACK && !tie) {
+            acc.flips += (uint32_t)(16 + rejected);            // accepted == flipped for Metropolis / Glauber
+        } else {
+            uint32_t fsum = 0, ssum = 0, nsum = 0, snsum = 0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t Fc = nw[w] ^ tw[w];               // changed sites, 0x01 per byte
-            fsum += Fc;
-            if (TRACK) {
-                const uint32_t SF = tw[w] & Fc;
-                ssum += SF;
-                nsum += nup[w] & (Fc * 255u);
-                snsum += nup[w] & (SF * 255u);
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t Fc = nw[w] ^ tw[w];               // changed sites, 0x01 per byte
+                fsum += Fc;
+                if (TRACK) {
+                    const uint32_t SF = tw[w] & Fc;
+                    ssum += SF;
+                    nsum += nup[w] & (Fc * 255u);
+                    snsum += nup[w] & (SF * 255u);
+                }
             }
-        }
-        acc.flips = __dp4a(fsum, 0x01010101u, acc.flips);
-        if (TRACK) {
-            acc.s = __dp4a(ssum, 0x01010101u, (uint32_t)acc.s);
-            acc.n = __dp4a(nsum, 0x01010101u, (uint32_t)acc.n);
-            acc.sn = __dp4a(snsum, 0x01010101u, (uint32_t)acc.sn);
+            acc.flips = __dp4a(fsum, 0x01010101u, acc.flips);
+            if (TRACK) {
+                acc.s = __dp4a(ssum, 0x01010101u, (uint32_t)acc.s);
+                acc.n = __dp4a(nsum, 0x01010101u, (uint32_t)acc.n);
+                acc.sn = __dp4a(snsum, 0x01010101u, (uint32_t)acc.sn);
+            }
         }
     }
     return make_uint4(nw[0], nw[1], nw[2], nw[3]);
