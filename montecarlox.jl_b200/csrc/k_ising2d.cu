@@ -82,8 +82,18 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
                                             const uint32_t *s_pair, const uint32_t *s_thi, const uint32_t *s_tlo,
                                             Acc &acc, const bool active)
 {
+#ifdef MCX_OPT_NOCOMPUTE
+    // memory-pattern ceiling probe (never shipped): same loads and stores, no RNG, no decision
+    return make_uint4(tq.x ^ (U.x & C.x & D.x & side), tq.y ^ (U.y & C.y & D.y), tq.z ^ (U.z & C.z & D.z), tq.w ^ (U.w & C.w & D.w & blk));
+#endif
+#ifdef MCX_OPT_NOPHILOX
+    // cost-split probe (never shipped): everything but the generator
+    const Philox4 ra = Philox4{blk * 0x9E3779B9u ^ seed_lo, blk * 0x85EBCA6Bu + t_lo, blk * 0xC2B2AE35u ^ chain_id, blk * 0x27D4EB2Fu + c2};
+    const Philox4 rb = Philox4{ra.x * 0x165667B1u, ra.y * 0x9E3779B1u, ra.z * 0x85EBCA77u, ra.w * 0xC2B2AE3Du};
+#else
     const Philox4 ra = philox4x32_10(blk, t_lo, c2, chain_id, seed_lo, seed_hi);
     const Philox4 rb = philox4x32_10(blk + 1, t_lo, c2, chain_id, seed_lo, seed_hi);
+#endif
 
     uint32_t S[4];
     if (PARITY == 0) {
@@ -278,10 +288,17 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             if (edgeB) sB = sideB;
             const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
                                                                  seed_hi, s_pair, s_thi, s_tlo, acc, active);
+#ifndef MCX_OPT_INTERLEAVE_ROWS
+            // finish (and store) row a before starting row b: fewer live registers, measured +4 %
+            if (active) *reinterpret_cast<uint4 *>(pt) = Na;
+            asm volatile("" ::: "memory");
+#endif
             const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
                                                                      seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
             if (active) {
+#ifdef MCX_OPT_INTERLEAVE_ROWS
                 *reinterpret_cast<uint4 *>(pt) = Na;
+#endif
                 *reinterpret_cast<uint4 *>(pt + half) = Nb;
             }
             U = D; C = E;
