@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
         int dead = io < 0 || io >= P.nbins;
         if (dead && lane == 0) atomicExch(P.error, 1);
         double lw_old = dead ? 0.0 : lw[io];
+        // Boltzmann part of the two-component observable: H1 = J * sum_pair_interactions (a Float64 in the
+        // reference, blume_capel.jl:123) carried as a running double; exact for integer-valued J
+        double Ho1 = P.J * (P.J * (double)pair);
         int64_t run_bin = io;
         unsigned long long run_cnt = 0;
         const uint32_t halfN = (uint32_t)L.halfN;
@@ -200,15 +203,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                                 break;
                             }
                             bool accepted = false;
-                            double lw_new = lw_old;
+                            double lw_new = lw_old, Hn1 = Ho1;
                             if (inside) {
                                 lw_new = in == io ? lw_old : lw[in];
                                 double log_ratio;
                                 if (OBS == MCX_OBS_ENERGY) {
                                     log_ratio = lw_new - lw_old;
                                 } else {
-                                    const double Ho1 = P.J * (P.J * (double)pair);
-                                    const double Hn1 = Ho1 + P.J * (P.J * (double)dpair);
+                                    Hn1 = Ho1 + P.J * (P.J * (double)dpair);
                                     log_ratio = (-P.beta_pair * Hn1 + lw_new) - (-P.beta_pair * Ho1 + lw_old);
                                 }
                                 // _accept! (importance_sampling.jl:80-85)
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                             }
                             if (accepted) {
                                 pair += dpair; spin += dspin; spin2 += dspin2; nacc += 1;
-                                io = in; lw_old = lw_new;
+                                io = in; lw_old = lw_new; Ho1 = Hn1;
                             }
                             s_acc[w][idx] = (uint8_t)accepted;
                             // record_visit! / Wang-Landau update at the visited bin (= io after the move)

@@ -616,6 +616,25 @@ int env_int(const char *name, int dflt)
     return v && *v ? atoi(v) : dflt;
 }
 
+int pick_rows_per_strip(int Ly, int want);
+
+// Strip height: 16 rows unless that leaves fewer than ~4 work items per resident CTA (batched small
+// lattices, replicas sharded over many GPUs); then shorter strips keep the persistent grid balanced.
+int auto_rows_per_strip(const mcx_lattice *lat)
+{
+    const int forced = env_int("MCX_ROWS_PER_STRIP", 0);
+    if (forced > 0) return pick_rows_per_strip(lat->view.Ly, forced);
+    const int64_t nseg = lat->view.half >> 4;
+    const int64_t ctas = (int64_t)lat->ctx->sm_count * 6;
+    int R = 16;
+    for (; R > 4; R >>= 1) {
+        const int r = pick_rows_per_strip(lat->view.Ly, R);
+        const int64_t items = ((int64_t)(lat->view.Ly / r) * nseg + kThreads - 1) / kThreads * lat->nchains;
+        if (items >= 4 * ctas) break;
+    }
+    return pick_rows_per_strip(lat->view.Ly, R);
+}
+
 int pick_rows_per_strip(int Ly, int want)
 {
     // largest even divisor of Ly that is <= want
@@ -628,7 +647,7 @@ template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
 void launch_v(mcx_lattice *lat, uint64_t t)
 {
     const LatView &L = lat->view;
-    const int R = pick_rows_per_strip(L.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
+    const int R = auto_rows_per_strip(lat);
     const int nstrips = L.Ly / R;
     const int nseg = L.half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
@@ -653,7 +672,7 @@ template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, int STAGES>
 void launch_ring(mcx_lattice *lat, uint64_t t)
 {
     const LatView &L = lat->view;
-    const int R = pick_rows_per_strip(L.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
+    const int R = auto_rows_per_strip(lat);
     const int nstrips = L.Ly / R;
     const int nseg = L.half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
@@ -761,7 +780,7 @@ bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
     // small lattices: a chain yields fewer than one CTA of 16-byte segments x strips, so most lanes of
     // this kernel would idle; the rows-of-8 kernel (8 sites per thread) fills the machine instead
     {
-        const int R = pick_rows_per_strip(lat->view.Ly, env_int("MCX_ROWS_PER_STRIP", 16));
+        const int R = pick_rows_per_strip(lat->view.Ly, env_int("MCX_ROWS_PER_STRIP", 16));   // small-lattice test uses 16
         const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
         if (G < 96 && getenv("MCX_VARIANT") == nullptr && getenv("MCX_ROWS_PER_STRIP") == nullptr) return false;
     }

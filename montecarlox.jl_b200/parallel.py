@@ -68,7 +68,11 @@ class GPUBackend:
         """all-gather equal slices of a 1-D tensor in place (each rank owns [first, first+count))."""
         if not self._dist or self.size == 1:
             return
-        self._dist.all_gather_into_tensor(tensor, tensor[first:first + count].clone(), group=self.group)
+        # in place: the input is this rank's slice of the output (NCCL's in-place all-gather layout)
+        if tensor.is_cuda:
+            self._dist.all_gather_into_tensor(tensor, tensor[first:first + count], group=self.group)
+        else:   # gloo (CPU tests) wants distinct buffers
+            self._dist.all_gather_into_tensor(tensor, tensor[first:first + count].clone(), group=self.group)
 
     def all_reduce_sum(self, tensor):
         if not self._dist or self.size == 1:
