@@ -660,6 +660,8 @@ void launch_v(mcx_lattice *lat, uint64_t t)
         if (resident < 1) resident = 1;
     }
     const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
+    // persistent grid: every SM gets its full complement of CTAs (trimming the grid so that all CTAs
+    // run the same number of items was measured 8 % slower: SMs with fewer CTAs do not finish sooner)
     int grid = lat->ctx->sm_count * ctas_per_sm;
     if (grid > nitems) grid = nitems;
     kern<<<grid, kThreads, 0, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums,
@@ -686,6 +688,8 @@ void launch_ring(mcx_lattice *lat, uint64_t t)
         if (resident < 1) resident = 1;
     }
     const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
+    // persistent grid: every SM gets its full complement of CTAs (trimming the grid so that all CTAs
+    // run the same number of items was measured 8 % slower: SMs with fewer CTAs do not finish sooner)
     int grid = lat->ctx->sm_count * ctas_per_sm;
     if (grid > nitems) grid = nitems;
     kern<<<grid, kThreads, 0, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums,
