@@ -175,6 +175,17 @@ __device__ __forceinline__ uint4 update_row(const uint4 tq, const uint4 U, const
 
 __device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
+#ifdef MCX_OPT_TRACE
+// timing probe (scripts/trace_ctas.py): per CTA {start ns, end ns, SM id, items done} of the last launch
+__device__ unsigned long long g_trace[4 * 4096];
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+#endif
+
 template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
@@ -192,8 +203,15 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
     const uint32_t t_lo = (uint32_t)t;
     const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
     const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
+#ifdef MCX_OPT_TRACE
+    const unsigned long long trace_t0 = globaltimer_ns();
+    int trace_items = 0;
+#endif
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+#ifdef MCX_OPT_TRACE
+        ++trace_items;
+#endif
         const int chain = item / blocks_per_chain;
         const int label = labels[chain];
         if (label != cur_label) {
@@ -323,6 +341,17 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             }
         }
     }
+#ifdef MCX_OPT_TRACE
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < 4096) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_trace[4 * blockIdx.x + 0] = trace_t0;
+        g_trace[4 * blockIdx.x + 1] = globaltimer_ns();
+        g_trace[4 * blockIdx.x + 2] = smid;
+        g_trace[4 * blockIdx.x + 3] = (unsigned long long)trace_items;
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -793,3 +822,11 @@ bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
 }
 
 }  // namespace mcx
+
+#ifdef MCX_OPT_TRACE
+extern "C" int mcx_debug_trace(unsigned long long *out, int nctas)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, mcx::g_trace, sizeof(unsigned long long) * 4 * (size_t)nctas);
+}
+#endif
