@@ -376,12 +376,22 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     REQUIRE(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     if (lat->track_sums && lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
+    // test hooks: MCX_FORCE_GENERIC=1 -> shape-generic kernel, =2 -> rows-of-8 kernel
+    const char *fg = getenv("MCX_FORCE_GENERIC");
+    const int force = fg ? atoi(fg) : 0;
     for (int64_t s = 0; s < nsweeps; ++s) {
+        // series of sweeps over small lattices: one launch with the lattice resident in shared memory
+        if (force == 0) {
+            const int64_t chunk = nsweeps - s < 16384 ? nsweeps - s : 16384;
+            if (launch_sweeps_resident(lat, chunk)) {
+                if (!lat->track_sums) lat->sums_dirty = true;
+                lat->sweep += (uint64_t)chunk;
+                s += chunk - 1;
+                continue;
+            }
+        }
         for (int colour = 0; colour < 2; ++colour) {
             const uint64_t t = 2 * lat->sweep + (uint64_t)colour;
-            // test hooks: MCX_FORCE_GENERIC=1 -> shape-generic kernel, =2 -> rows-of-8 kernel
-            const char *fg = getenv("MCX_FORCE_GENERIC");
-            const int force = fg ? atoi(fg) : 0;
             if (force == 1) launch_sweep_generic(lat, colour, t);
             else if (force == 2 && launch_sweep_rows8(lat, colour, t)) {}
             else if (launch_sweep_ising2d(lat, colour, t)) { if (!lat->track_sums) lat->sums_dirty = true; }

@@ -69,6 +69,8 @@ void launch_sweep_generic(mcx_lattice *lat, int colour, uint64_t t);
 
 // k_ising2d.cu
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t);   // false: shape not supported
+// k_resident.cu: nsweeps whole sweeps of lat->sweep .. in one launch, lattice resident in cluster shared memory
+bool launch_sweeps_resident(mcx_lattice *lat, int64_t nsweeps);         // false: not applicable, nothing launched
 bool launch_recompute_ising2d(mcx_lattice *lat);
 bool launch_pack_ising2d(mcx_lattice *lat);
 bool launch_unpack_ising2d(mcx_lattice *lat);
