@@ -31,8 +31,9 @@ namespace {
 constexpr int kThreads = 128;
 
 #ifdef MCX_OPT_TRACE
-// timing probe (scripts/trace_ctas.py): per CTA {start ns, end ns, SM id, items done} of the last launch
-__device__ unsigned long long g_trace[4 * 4096];
+// timing probe (scripts/trace_ctas.py): per CTA {start ns, end ns, SM id, items done} of the last launch,
+// followed by the start time of each of its first 8 items
+__device__ unsigned long long g_trace[12 * 4096];
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long v;
@@ -65,6 +66,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
 #ifdef MCX_OPT_TRACE
+        if (threadIdx.x == 0 && blockIdx.x < 4096 && trace_items < 8) g_trace[12 * blockIdx.x + 4 + trace_items] = globaltimer_ns();
         ++trace_items;
 #endif
         const int chain = item / blocks_per_chain;
@@ -201,10 +203,10 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
     if (threadIdx.x == 0 && blockIdx.x < 4096) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        g_trace[4 * blockIdx.x + 0] = trace_t0;
-        g_trace[4 * blockIdx.x + 1] = globaltimer_ns();
-        g_trace[4 * blockIdx.x + 2] = smid;
-        g_trace[4 * blockIdx.x + 3] = (unsigned long long)trace_items;
+        g_trace[12 * blockIdx.x + 0] = trace_t0;
+        g_trace[12 * blockIdx.x + 1] = globaltimer_ns();
+        g_trace[12 * blockIdx.x + 2] = smid;
+        g_trace[12 * blockIdx.x + 3] = (unsigned long long)trace_items;
     }
 #endif
 }
@@ -682,6 +684,6 @@ bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
 extern "C" int mcx_debug_trace(unsigned long long *out, int nctas)
 {
     cudaDeviceSynchronize();
-    return (int)cudaMemcpyFromSymbol(out, mcx::g_trace, sizeof(unsigned long long) * 4 * (size_t)nctas);
+    return (int)cudaMemcpyFromSymbol(out, mcx::g_trace, sizeof(unsigned long long) * 12 * (size_t)nctas);
 }
 #endif

@@ -29,13 +29,16 @@ def main():
     alg = m.Metropolis(rng, beta=0.44)
     m.sweep_(sys_, alg, args.sweeps)
     n = 888
-    buf = np.zeros(4 * n, dtype=np.uint64)
+    buf = np.zeros(12 * n, dtype=np.uint64)
     f = lib().mcx_debug_trace
     f.argtypes = [C.c_void_p, C.c_int]
     rc = f(buf.ctypes.data, n)
     assert rc == 0, rc
-    tr = buf.reshape(n, 4)
-    tr = tr[tr[:, 1] > 0]
+    full = buf.reshape(n, 12)
+    tr = full[:, :4]
+    keep = tr[:, 1] > 0
+    full = full[keep]
+    tr = tr[keep]
     t0 = tr[:, 0].min()
     st = (tr[:, 0] - t0).astype(np.int64)
     en = (tr[:, 1] - t0).astype(np.int64)
@@ -53,6 +56,22 @@ def main():
     print("SMs", len(ends), "items/SM min %d max %d" % (items.min(), items.max()),
           "SM first start ns: max %d" % starts.max(), " SM last end ns: min %d p50 %d max %d" % (ends.min(), np.median(ends), ends.max()))
     print("mean SM busy span / kernel span: %.3f" % ((ends - starts).mean() / en.max()))
+    # per-item durations: item k of a CTA runs from its start to the next item's start (or the CTA's end)
+    durs, sms, order = [], [], []
+    for row in full:
+        k = int(row[3])
+        ts = [int(row[4 + i]) for i in range(min(k, 8))] + [int(row[1])]
+        for i in range(len(ts) - 1):
+            durs.append(ts[i + 1] - ts[i]); sms.append(int(row[2])); order.append(i)
+    durs, sms, order = np.array(durs), np.array(sms), np.array(order)
+    for i in np.unique(order):
+        d = durs[order == i]
+        print("item #%d of a CTA: n=%d duration ns p10 %d p50 %d p90 %d max %d" % (i, len(d), np.percentile(d, 10), np.median(d), np.percentile(d, 90), d.max()))
+    per_sm = np.array([durs[sms == s_].mean() for s_ in np.unique(sms)])
+    print("mean item duration per SM: min %d p50 %d max %d  (spread %.1f %%)" % (per_sm.min(), np.median(per_sm), per_sm.max(), 100 * (per_sm.max() / per_sm.min() - 1)))
+    slow = np.unique(sms)[np.argsort(per_sm)[-8:]]
+    fast = np.unique(sms)[np.argsort(per_sm)[:8]]
+    print("slowest SMs", slow.tolist(), "fastest SMs", fast.tolist())
 
 
 if __name__ == "__main__":
