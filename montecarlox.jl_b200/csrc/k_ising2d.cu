@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #endif
 
-template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
+template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH, bool FULL>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
           const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
@@ -89,7 +89,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             cur_label = label;
         }
         const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
-        const bool active = g0 < G;
+        const bool active = FULL ? true : g0 < G;                 // FULL: G % kThreads == 0, no idle lanes
         const int64_t g = active ? g0 : G - 1;
         const int strip = (int)(g / nseg);
         const int seg = (int)(g - (int64_t)strip * nseg);
@@ -539,10 +539,13 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     const int64_t G = (int64_t)nstrips * nseg;
     const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
     const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
-    auto kern = k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH>;
+    // the shipped variant also exists with the idle-lane predicate compiled out (+2.8 %, r01_tune_allactive.log)
+    constexpr bool kHasFull = MINB == 6 && !PREFETCH;
+    const bool full = kHasFull && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
+    auto kern = full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull> : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false>;
     static thread_local int resident = 0;
     if (!resident) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false>, kThreads, 0);
         if (resident < 1) resident = 1;
     }
     const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);

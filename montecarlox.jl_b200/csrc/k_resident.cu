@@ -294,6 +294,8 @@ bool launch_sweeps_resident(mcx_lattice *lat, int64_t nsweeps)
     if (nsweeps < 1 || nsweeps > kResMaxSweepsPerLaunch) return false;
     const int mode = res_env_int("MCX_RESIDENT", -1);
     if (mode == 0) return false;
+    // the tuning hooks of the streaming kernel select that kernel
+    if (mode != 1 && (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP") || getenv("MCX_FULL"))) return false;
     if (mode != 1) {
         const int64_t kResidentMaxSites = (int64_t)32 << 20;
         if (nsweeps < 2 || (int64_t)lat->nchains * lat->N > kResidentMaxSites) return false;

@@ -62,12 +62,13 @@ def test_ising2d_bit_exact(m, oracle, L, rule):
         _check(sys_, s_or, a_or, alg, nsweeps)
 
 
-@pytest.mark.parametrize("L", [64, 128])
+@pytest.mark.parametrize("L", [64, 128, 512])
 def test_fast_kernel_equals_generic_kernel(m, L):
     """same trajectories from the vectorised and the generic kernels, any strip height"""
     outs = []
-    keys = ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP", "MCX_VARIANT")
-    envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_FORCE_GENERIC": "2"}, {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
+    keys = ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP", "MCX_VARIANT", "MCX_RESIDENT", "MCX_FULL")
+    envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_RESIDENT": "0"}, {"MCX_FULL": "0"}, {"MCX_FULL": "1"}, {"MCX_FORCE_GENERIC": "2"},
+            {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
     envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in (0, 3, 6) for r in ("4", "16")]
     for env in envs:
         for k in keys:
