@@ -146,6 +146,24 @@ int32_t mcx_recompute(mcx_lattice *lat);                                 /* ener
  * off: sweeps only count accepted moves; the sums are recomputed from the spins on the next
  * read (same values, fewer instructions per attempt). */
 int32_t mcx_set_tracking(mcx_lattice *lat, int32_t on);
+/* ---- slab decomposition: one lattice over several GPUs (not in the reference, whose
+ * IsingLatticeOptim (ising.jl:430-461) is a single Vector{Int8}) -----------------------------------------
+ * A handle created for dims = [Lx, Ly_local] becomes rows [row_offset, row_offset + Ly_local) of a lattice
+ * with global_Ly rows.  The half-sweep kernel reads the row above / below the slab directly from the
+ * neighbour handle's device memory (same process: mcx_slab_attach_local; other process / GPU: the 128-byte
+ * token of mcx_slab_export, opened with CUDA IPC and read over NVLink).  Randomness is positioned by global
+ * row, so trajectories equal those of the unsplit lattice.  Remote slabs are advanced by mcx_sweep (device
+ * flags order the half-sweeps between GPUs, no host synchronisation); local slabs by calling
+ * mcx_slab_half_sweep on every slab of the lattice in turn.  Observables, upload, download and init act on
+ * the slab's own rows; sums are the slab's share (add them over slabs). */
+int32_t mcx_slab_configure(mcx_lattice *lat, int32_t global_Ly, int32_t row_offset);
+int32_t mcx_slab_export(mcx_lattice *lat, void *handle128);
+int32_t mcx_slab_attach_ipc(mcx_lattice *lat, const void *up_handle128, const void *dn_handle128);
+int32_t mcx_slab_attach_local(mcx_lattice *lat, mcx_lattice *up, mcx_lattice *dn);
+int32_t mcx_slab_half_sweep(mcx_lattice *lat);
+/* synchronises the stream; timed_out != 0 if a wait for a neighbour gave up (20 s) */
+int32_t mcx_slab_status(mcx_lattice *lat, int32_t *timed_out, uint64_t *half_sweeps_done);
+
 /* device pointer of the int64 [nchains][4] accumulator block {pair, spin, spin2, accepted}
  * for zero-copy plumbing (collectives) by the host runtime */
 int32_t mcx_lattice_device_sums(mcx_lattice *lat, void **device_ptr);

@@ -15,7 +15,7 @@ from .ising2d_exact import distribution_exact_ising2D, distribution_from_logdos,
 from .checkpointing import CheckpointSession, checkpoint_, finalize_, init_checkpoint, restore_checkpoint
 from .measurements import (integrated_autocorrelation_time, integrated_autocorrelation_times,
                            optimize_exchange_interval_, sweep_series_, tau_int)
-from .parallel import (GPUBackend, ParallelChains, ParallelTempering, ReplicaExchange, ThreadsBackend,
+from .parallel import (GPUBackend, ParallelChains, ParallelTempering, ReplicaExchange, SlabIsing, ThreadsBackend,
                        attempt_exchange_pair_, exchange_log_ratio, partition_slots, philox_family, set_betas,
                        update_)
 from .rng import PhiloxRNG, exchange_u, philox4x32_10

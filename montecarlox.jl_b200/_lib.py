@@ -62,6 +62,12 @@ SIGNATURES = {
     "mcx_reset_counters": (_i32, [_vp]),
     "mcx_recompute": (_i32, [_vp]),
     "mcx_set_tracking": (_i32, [_vp, _i32]),
+    "mcx_slab_configure": (_i32, [_vp, _i32, _i32]),
+    "mcx_slab_export": (_i32, [_vp, _vp]),
+    "mcx_slab_attach_ipc": (_i32, [_vp, _vp, _vp]),
+    "mcx_slab_attach_local": (_i32, [_vp, _vp, _vp]),
+    "mcx_slab_half_sweep": (_i32, [_vp]),
+    "mcx_slab_status": (_i32, [_vp, _vp, _vp]),
     "mcx_lattice_device_sums": (_i32, [_vp, _P(_vp)]),
     "mcx_pt_create": (_i32, [_vp, _i32, _i32, _vp, _P(_vp)]),
     "mcx_pt_destroy": (_i32, [_vp]),

@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #endif
 
-template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH, bool FULL>
+template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH, bool FULL, bool SLAB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
           const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
@@ -109,10 +109,13 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         const int colA = COLOUR == 0 ? colL : colR;
         const int colB = COLOUR == 0 ? colR : colL;
 
+        // the row above row 0 / below row Ly - 1: the own plane (periodic) or, for a slab, the neighbours' planes
+        const uint8_t *oth_dn = SLAB ? plane_ptr_of(L.dn_planes, L, chain, COLOUR ^ 1) : oth;
+        const uint8_t *oth_up = SLAB ? plane_ptr_of(L.up_planes, L, chain, COLOUR ^ 1) : oth;
         const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
         const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, current even row
         uint8_t *pt = tgt + (int64_t)row0 * half + col;           // target plane, current even row
-        uint4 U = ldg128(oth + (int64_t)rowU * half + col);
+        uint4 U = ldg128((SLAB && row0 == 0 ? oth_up : oth) + (int64_t)rowU * half + col);
         uint4 C = ldg128(po + col);
         uint4 D, Ta, Tb;
         uint32_t sideA = 0, sideB = 0;
@@ -122,7 +125,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             if (edgeA) sideA = po[colA];
             if (edgeB) sideB = po[half + colB];
         }
-        uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
+        uint32_t blk = (uint32_t)(((int64_t)(row0 + (SLAB ? L.row_offset : 0)) * half + col) >> 3);
         const uint32_t blk_step = (uint32_t)(half >> 3);
         Acc acc;
 
@@ -130,7 +133,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         for (int r = 0; r < R; r += 2) {
             const int row = row0 + r;
             // E = other row below the odd row; wraps only at the very last row of the lattice
-            const uint8_t *pe = (row + 2 == L.Ly) ? oth : po + 2 * (int64_t)half;
+            const uint8_t *pe = (row + 2 == L.Ly) ? oth_dn : po + 2 * (int64_t)half;
             const uint4 E = ldg128(pe + col);
             uint4 Dn, Tan, Tbn;
             uint32_t sideAn = 0, sideBn = 0;
@@ -384,8 +387,8 @@ k_recompute2d(LatView L, long long *__restrict__ sums, int64_t segs_per_chain)
         const int ru = row == 0 ? L.Ly - 1 : row - 1, rd = row == L.Ly - 1 ? 0 : row + 1;
         const uint4 T = ldg128(p0 + (int64_t)row * half + col);
         const uint4 C = ldg128(p1 + (int64_t)row * half + col);
-        const uint4 U = ldg128(p1 + (int64_t)ru * half + col);
-        const uint4 D = ldg128(p1 + (int64_t)rd * half + col);
+        const uint4 U = ldg128((row == 0 ? plane_ptr_of(L.up_planes, L, chain, 1) : p1) + (int64_t)ru * half + col);
+        const uint4 D = ldg128((row == L.Ly - 1 ? plane_ptr_of(L.dn_planes, L, chain, 1) : p1) + (int64_t)rd * half + col);
         uint32_t S[4];
         if ((row & 1) == 0) {       // colour-0 sites of an even row sit at x = 2j: neighbours j-1, j
             const uint32_t side = p1[(int64_t)row * half + ((seg == 0 ? half : col) - 1)];
@@ -479,7 +482,7 @@ k_init2d(LatView L, int mode, uint32_t seed_lo, uint32_t seed_hi, uint32_t first
         const int row = (int)(g / nseg), seg = (int)(g - (int64_t)row * nseg);
         uint32_t bits = mode == MCX_INIT_UP ? 0xffffffffu : 0u;
         if (mode == MCX_INIT_RANDOM) {
-            const int64_t i = (int64_t)row * L.Lx + seg * 32;
+            const int64_t i = (int64_t)(row + L.row_offset) * L.Lx + seg * 32;
             const Philox4 p = stream_block(seed_lo, seed_hi, first_chain + chain, TAG_INIT, 0, (uint32_t)(i >> 7), 0);
             const int w = (int)((i >> 5) & 3);
             bits = w == 0 ? p.x : w == 1 ? p.y : w == 2 ? p.z : p.w;
@@ -540,12 +543,16 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
     const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
     // the shipped variant also exists with the idle-lane predicate compiled out (+2.8 %, r01_tune_allactive.log)
+    // and with the halo rows taken from the neighbour slabs (k_slab.cu)
     constexpr bool kHasFull = MINB == 6 && !PREFETCH;
-    const bool full = kHasFull && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
-    auto kern = full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull> : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false>;
+    const bool slab = kHasFull && lat->slab != nullptr;
+    const bool full = kHasFull && !slab && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
+    auto kern = slab ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, kHasFull>
+              : full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, false>
+                     : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>;
     static thread_local int resident = 0;
     if (!resident) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>, kThreads, 0);
         if (resident < 1) resident = 1;
     }
     const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
@@ -593,7 +600,7 @@ void launch_ring(mcx_lattice *lat, uint64_t t)
 template <int COLOUR, bool HEATBATH, bool TRACK>
 void launch_t(mcx_lattice *lat, uint64_t t)
 {
-    const int variant = env_int("MCX_VARIANT", 3);
+    const int variant = lat->slab ? 3 : env_int("MCX_VARIANT", 3);
     switch (variant) {
     case 0: launch_v<COLOUR, HEATBATH, TRACK, 5, true>(lat, t); break;
     case 6: launch_ring<COLOUR, HEATBATH, TRACK, 6, 3>(lat, t); break;
@@ -675,7 +682,7 @@ bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
     {
         const int R = pick_rows_per_strip(lat->view.Ly, env_int("MCX_ROWS_PER_STRIP", 16));   // small-lattice test uses 16
         const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
-        if (G < 96 && getenv("MCX_VARIANT") == nullptr && getenv("MCX_ROWS_PER_STRIP") == nullptr) return false;
+        if (G < 96 && !lat->slab && getenv("MCX_VARIANT") == nullptr && getenv("MCX_ROWS_PER_STRIP") == nullptr) return false;
     }
     if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
     return true;

@@ -290,7 +290,7 @@ bool plan_and_launch(mcx_lattice *lat, int64_t nsweeps, bool dry_run)
 // stream faster (1200 vs ~850 attempts/ns).
 bool launch_sweeps_resident(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8) return false;
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
     if (nsweeps < 1 || nsweeps > kResMaxSweepsPerLaunch) return false;
     const int mode = res_env_int("MCX_RESIDENT", -1);
     if (mode == 0) return false;

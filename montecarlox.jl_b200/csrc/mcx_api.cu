@@ -146,6 +146,7 @@ static void lattice_free(mcx_lattice *lat)
 {
     if (!lat) return;
     cudaSetDevice(lat->ctx->device);
+    slab_free(lat);
     cudaFree(lat->view.planes);
     cudaFree(lat->d_sums);
     cudaFree(lat->d_thi);
@@ -196,6 +197,7 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
         lattice_free(lat);
         return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
+    v.up_planes = v.dn_planes = v.planes; v.row_offset = 0; v.pad_ = 0;
     cudaMemsetAsync(lat->d_labels, 0, sizeof(int32_t) * (size_t)nchains, ctx->stream);
     cudaMemsetAsync(lat->d_sums, 0, sizeof(long long) * SUM_FIELDS * (size_t)nchains, ctx->stream);
     // constructors start all-up (ising.jl:118, blume_capel.jl:156)
@@ -376,6 +378,17 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     REQUIRE(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     if (lat->track_sums && lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
+    if (lat->slab) {
+        // a slab of a taller lattice: half-sweeps ordered against the neighbour GPUs by device flags
+        REQUIRE(lat->slab->attached && lat->slab->remote, MCX_ERR_STATE,
+                "slabs attached inside one process advance in lockstep through mcx_slab_half_sweep");
+        REQUIRE(lat->slab->colour == 0, MCX_ERR_STATE, "slab is in the middle of a sweep");
+        for (int64_t s = 0; s < 2 * nsweeps; ++s) {
+            const int32_t st = slab_half_sweep(lat);
+            if (st != MCX_OK) return fail(st, "slab half-sweep could not be launched");
+        }
+        return check_launch(lat->ctx);
+    }
     // test hooks: MCX_FORCE_GENERIC=1 -> shape-generic kernel, =2 -> rows-of-8 kernel
     const char *fg = getenv("MCX_FORCE_GENERIC");
     const int force = fg ? atoi(fg) : 0;

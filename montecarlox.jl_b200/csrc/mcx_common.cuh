@@ -70,11 +70,20 @@ struct LatView {
     int64_t halfN;          // sites per colour plane
     int32_t Lx, Ly, Lz, half;   // half = Lx/2
     int32_t ndim, nn, model, nchains;
+    // slab decomposition (k_slab.cu): this view holds rows [row_offset, row_offset + Ly) of a taller
+    // lattice; the row above row 0 / below row Ly-1 lives in the plane arrays of the neighbour slabs
+    // (same shape and strides).  Not a slab: up_planes == dn_planes == planes, row_offset == 0.
+    uint8_t *up_planes, *dn_planes;
+    int32_t row_offset, pad_;
 };
 
 __device__ __forceinline__ uint8_t *plane_ptr(const LatView &L, int chain, int colour)
 {
     return L.planes + ((int64_t)chain * 2 + colour) * L.plane_stride;
+}
+__device__ __forceinline__ const uint8_t *plane_ptr_of(const uint8_t *planes, const LatView &L, int chain, int colour)
+{
+    return planes + ((int64_t)chain * 2 + colour) * L.plane_stride;
 }
 
 // per-chain accumulator block

@@ -11,6 +11,18 @@ struct mcx_ctx {
     uint64_t launches;
 };
 
+// slab decomposition state of a lattice handle (k_slab.cu)
+struct mcx_slab {
+    int global_Ly;
+    bool attached, remote;             // remote: neighbours live in other processes (IPC), ordered by device flags
+    int colour;                        // colour of the next half-sweep
+    unsigned long long epoch;          // half-sweeps completed since attach
+    unsigned long long *d_flags;       // [2]: half-sweeps completed by the up / down neighbour (they write it)
+    unsigned long long *up_flags, *dn_flags;   // the neighbours' d_flags
+    int *d_err;                        // raised by a wait that gave up
+    void *ipc_opened[4];
+};
+
 struct mcx_lattice {
     mcx_ctx *ctx;
     mcx::LatView view;
@@ -30,6 +42,7 @@ struct mcx_lattice {
     bool fast2d;                // Lx % 32 == 0 && ndim == 2: row-aligned 128-bit kernels apply
     bool track_sums;            // fast kernels accumulate pair/spin sums per flip (else recompute lazily)
     bool sums_dirty;            // pair/spin sums are stale (untracked sweeps ran)
+    mcx_slab *slab;             // non-null: this handle is a slab of a taller lattice
 };
 
 struct mcx_pt {
@@ -69,6 +82,10 @@ void launch_sweep_generic(mcx_lattice *lat, int colour, uint64_t t);
 
 // k_ising2d.cu
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t);   // false: shape not supported
+// k_slab.cu
+int32_t slab_half_sweep(mcx_lattice *lat);
+void slab_free(mcx_lattice *lat);
+
 // k_resident.cu: nsweeps whole sweeps of lat->sweep .. in one launch, lattice resident in cluster shared memory
 bool launch_sweeps_resident(mcx_lattice *lat, int64_t nsweeps);         // false: not applicable, nothing launched
 bool launch_recompute_ising2d(mcx_lattice *lat);

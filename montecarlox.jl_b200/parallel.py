@@ -387,3 +387,157 @@ def set_betas(nreplicas, bmin, bmax, mode="uniform"):
 
 def update_(obj, *args, **kwargs):
     return obj.update_(*args, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# slab decomposition: one lattice over several GPUs (beyond the reference, whose
+# IsingLatticeOptim (SpinSystems/src/ising.jl:430-461) is one Vector{Int8} in one address space)
+# ---------------------------------------------------------------------------------------------------
+class SlabIsing:
+    """A 2-D Ising lattice `dims = [Lx, Ly]` (J = 1, h = 0) split by rows into equal slabs.
+
+    With a multi-rank `GPUBackend` every rank holds one slab on its GPU; the half-sweep kernel reads the
+    neighbour rows straight from the neighbour GPU's memory (CUDA IPC mapping, NVLink) and device flags
+    order the half-sweeps, so `sweep_` never synchronises the host.  With a single rank, `nslabs`
+    handles on one GPU advance in lockstep (what the single-GPU parity test drives).  Either way the
+    trajectory is bit-identical to `Ising(dims)` on one GPU with the same PhiloxRNG."""
+
+    def __init__(self, dims, backend=None, nslabs=None, ctx=None):
+        import ctypes as C
+        from ._lib import check, lib
+        from .spin_systems import Ising
+        self.backend = backend or GPUBackend()
+        self.dims = [int(d) for d in dims]
+        Lx, Ly = self.dims
+        self.N = Lx * Ly
+        self.remote = self.backend.size > 1
+        n = self.backend.size if self.remote else int(nslabs or 1)
+        if Ly % (2 * n) != 0:
+            raise ValueError("Ly = %d does not split into %d slabs of an even number of rows" % (Ly, n))
+        self.nslabs, self.rows = n, Ly // n
+        mine = [self.backend.rank] if self.remote else list(range(n))
+        self.parts = [Ising([Lx, self.rows], ctx=ctx) for _ in mine]
+        for p, k in zip(self.parts, mine):
+            check(lib().mcx_slab_configure(p.h_lat, Ly, k * self.rows))
+        if self.remote:
+            buf = C.create_string_buffer(128)
+            check(lib().mcx_slab_export(self.parts[0].h_lat, buf))
+            handles = self._all_gather_bytes(buf.raw)
+            r = self.backend.rank
+            up, dn = handles[(r - 1) % n], handles[(r + 1) % n]
+            check(lib().mcx_slab_attach_ipc(self.parts[0].h_lat, up, dn))
+            self.backend.barrier()
+        else:
+            for k, p in enumerate(self.parts):
+                check(lib().mcx_slab_attach_local(p.h_lat, self.parts[(k - 1) % n].h_lat, self.parts[(k + 1) % n].h_lat))
+
+    def _all_gather_bytes(self, raw):
+        import torch
+        dist = self.backend._dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.backend.group) == "nccl" else torch.device("cpu")
+        mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        out = torch.empty(self.backend.size * len(raw), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, mine, group=self.backend.group)
+        flat = out.cpu().numpy().tobytes()
+        return [flat[i * len(raw):(i + 1) * len(raw)] for i in range(self.backend.size)]
+
+    def _sync_all(self):
+        for p in self.parts:
+            p.sync()
+        self.backend.barrier()
+
+    def _recompute(self):
+        from ._lib import check, lib
+        self._sync_all()                       # every slab's rows are final before anyone reads halo rows
+        for p in self.parts:
+            check(lib().mcx_recompute(p.h_lat))
+        self._sync_all()
+
+    def init_(self, type, rng=None):
+        for p in self.parts:
+            p.init_(type, rng=rng)
+        self._recompute()
+        return self
+
+    def set_tracking(self, on):
+        self._tracking = bool(on)
+        for p in self.parts:
+            p.set_tracking(on)
+
+    def _fresh_sums(self):
+        """untracked sums are recomputed from the spins, which reads halo rows: only between sweeps of ALL slabs"""
+        if not getattr(self, "_tracking", True):
+            self._recompute()
+
+    def sweep_(self, alg, nsweeps=1):
+        from ._lib import check, lib
+        for p in self.parts:
+            p._bind_alg(alg)
+        self._fresh_sums()
+        before = sum(int(p._sums()[3].sum()) for p in self.parts)
+        if self.remote:
+            check(lib().mcx_sweep(self.parts[0].h_lat, int(nsweeps)))
+        else:
+            for _ in range(2 * int(nsweeps)):
+                for p in self.parts:
+                    check(lib().mcx_slab_half_sweep(p.h_lat))
+        alg.steps += int(nsweeps) * self.N
+        if hasattr(alg, "accepted"):
+            self._fresh_sums()
+            alg.accepted += self._reduce(sum(int(p._sums()[3].sum()) for p in self.parts) - before)
+
+    def _reduce(self, value):
+        if not self.remote:
+            return int(value)
+        import torch
+        dist = self.backend._dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.backend.group) == "nccl" else torch.device("cpu")
+        t = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+        self.backend.all_reduce_sum(t)
+        return int(t.item())
+
+    def status(self):
+        """(timed_out, half_sweeps_done) of this rank's slab(s); synchronises."""
+        import ctypes as C
+        from ._lib import check, lib
+        out = []
+        for p in self.parts:
+            t, e = C.c_int32(), C.c_uint64()
+            check(lib().mcx_slab_status(p.h_lat, C.byref(t), C.byref(e)))
+            out.append((t.value, e.value))
+        return out
+
+    def pair_sum(self):
+        self._fresh_sums()
+        return self._reduce(sum(int(p._sums()[0].sum()) for p in self.parts))
+
+    def magnetization(self, full=False):
+        if full:
+            self._recompute()
+        self._fresh_sums()
+        return self._reduce(sum(int(p._sums()[1].sum()) for p in self.parts))
+
+    def energy(self, full=False):
+        if full:
+            self._recompute()
+        return -self.pair_sum()
+
+    @property
+    def local_spins(self):
+        """this rank's rows (reference site order inside the slab)"""
+        import numpy as np
+        return np.concatenate([p.spins.reshape(-1) for p in self.parts])
+
+    @property
+    def spins(self):
+        """the whole lattice on every rank (gathers over ranks)"""
+        import numpy as np
+        loc = self.local_spins
+        if not self.remote:
+            return loc
+        parts = self._all_gather_bytes(loc.tobytes())
+        return np.concatenate([np.frombuffer(b, dtype=np.int8) for b in parts])
+
+    def close(self):
+        for p in self.parts:
+            p.sync()

@@ -1,0 +1,119 @@
+"""GPU parity of the slab decomposition (k_slab.cu): a lattice split by rows into slabs whose half-sweeps
+read the neighbour rows from the neighbour handle's memory must reproduce the unsplit lattice bit for bit."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BETA_C = 0.440686793509772
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mcx_b200
+    mcx_b200.lib()
+    return mcx_b200
+
+
+def _alg(m, rule, seed):
+    rng = m.PhiloxRNG(seed, 2)
+    return (m.Metropolis, m.Glauber, m.HeatBath)[rule](rng, beta=BETA_C)
+
+
+@pytest.mark.parametrize("dims,nslabs", [([256, 256], 2), ([256, 256], 4), ([1024, 96], 3), ([64, 512], 8), ([512, 64], 1)])
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_local_slabs_equal_whole_lattice(m, dims, nslabs, rule):
+    nsweeps = 5
+    os.environ["MCX_RESIDENT"] = "0"
+    try:
+        whole = m.Ising(dims)
+        a0 = _alg(m, rule, 77)
+        whole.init_("random", rng=a0.rng)
+        m.sweep_(whole, a0, nsweeps)
+    finally:
+        os.environ.pop("MCX_RESIDENT", None)
+    for tracking in (True, False):
+        slabs = m.SlabIsing(dims, nslabs=nslabs)
+        slabs.set_tracking(tracking)
+        a1 = _alg(m, rule, 77)
+        slabs.init_("random", rng=a1.rng)
+        slabs.sweep_(a1, nsweeps)
+        assert np.array_equal(slabs.spins, whole.spins)
+        assert slabs.pair_sum() == whole.pair_sum()
+        assert slabs.magnetization() == whole.magnetization()
+        assert slabs.energy(full=True) == whole.energy(full=True)
+        assert a1.steps == a0.steps
+        if rule != 2:
+            assert a1.accepted == a0.accepted
+        assert all(t == 0 and e == 2 * nsweeps for t, e in slabs.status())
+
+
+def test_slab_argument_errors(m):
+    s = m.Ising([64, 64])
+    from mcx_b200._lib import check, lib
+    with pytest.raises(ValueError):
+        check(lib().mcx_slab_configure(s.h_lat, 128, 3))        # odd offset
+    with pytest.raises(ValueError):
+        check(lib().mcx_slab_configure(s.h_lat, 64, 32))        # sticks out of the global lattice
+    with pytest.raises(Exception):
+        check(lib().mcx_slab_half_sweep(s.h_lat))                # not a slab
+    with pytest.raises(ValueError):
+        m.SlabIsing([64, 60], nslabs=4)                          # 15 rows per slab
+    b = m.BlumeCapel([64, 64])
+    with pytest.raises(Exception):
+        check(lib().mcx_slab_configure(b.h_lat, 128, 0))
+
+
+_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+ngpu = torch.cuda.device_count()
+torch.cuda.set_device(rank %% ngpu)
+dist.init_process_group("gloo", rank=rank, world_size=world)
+import mcx_b200 as m
+ctx = m.Context(rank %% ngpu)
+dims, nsweeps = [256, 64 * world], 3
+s = m.SlabIsing(dims, backend=m.GPUBackend(), ctx=ctx)
+rng = m.PhiloxRNG(123, 1)
+alg = m.Metropolis(rng, beta=0.44)
+s.init_("random", rng=rng)
+s.sweep_(alg, nsweeps)
+s.sweep_(alg, 1)
+spins, pair, mag = s.spins, s.pair_sum(), s.magnetization()
+st = s.status()
+if rank == 0:
+    os.environ["MCX_RESIDENT"] = "0"
+    w = m.Ising(dims, ctx=ctx)
+    a = m.Metropolis(m.PhiloxRNG(123, 1), beta=0.44)
+    w.init_("random", rng=a.rng)
+    m.sweep_(w, a, nsweeps + 1)
+    ok = bool(np.array_equal(spins, w.spins)) and pair == w.pair_sum() and mag == w.magnetization() and alg.accepted == a.accepted
+    print(json.dumps({"ok": ok, "status": st, "pair": int(pair), "ref_pair": int(w.pair_sum()), "acc": int(alg.accepted), "ref_acc": int(a.accepted)}))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ipc_slabs_across_processes(m, world, tmp_path):
+    """one process per slab (sharing this GPU when the box has fewer GPUs than ranks): CUDA IPC mapping of
+    the neighbour's planes, device flags for the ordering -- the multi-GPU path end to end"""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    port = 29600 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    assert res["ok"], res
+    assert all(t == 0 for t, _ in res["status"]), res
