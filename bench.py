@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--track", type=int, default=0, help="1: keep energy/magnetisation sums current per flip")
     ap.add_argument("--no-pt", action="store_true", help="skip the auxiliary parallel-tempering measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-slab", action="store_true", help="skip the auxiliary slab-decomposition measurement (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -305,6 +306,14 @@ def run_ours(args):
         except Exception as e:   # auxiliary metric must not take the headline down
             out["pt"] = {"error": repr(e)}
 
+    # ---- auxiliary: ONE lattice split by rows over the ranks (slab decomposition, halo rows read over NVLink)
+    if world > 1 and not args.no_slab:
+        try:
+            out["slab_strong"] = bench_slab(m, ctx, world, barrier, max_over_ranks, stream, [L, L], 20)
+            out["slab_weak"] = bench_slab(m, ctx, world, barrier, max_over_ranks, stream, [L, L * world], 20)
+        except Exception as e:
+            out["slab_strong"] = {"error": repr(e)}
+
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
             out["cpu_baseline"] = cpu_baseline(args, 1, args.cpu_seconds)
@@ -314,6 +323,34 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_slab(m, ctx, world, barrier, max_over_ranks, stream, dims, sweeps):
+    """attempts/ns of ONE [Lx, Ly] lattice whose rows are split over the ranks; every half-sweep reads two halo
+    rows from the neighbour GPUs' memory and is ordered against them by device flags (k_slab.cu)"""
+    import torch
+    from mcx_b200._lib import check, lib
+    s = m.SlabIsing(dims, backend=m.GPUBackend(), ctx=ctx)
+    s.set_tracking(False)
+    rng = m.PhiloxRNG(42, 0)
+    alg = m.Metropolis(rng, beta=BETA_C)
+    s.init_("random", rng=rng)
+    part = s.parts[0]
+    part._bind_alg(alg)
+    check(lib().mcx_sweep(part.h_lat, 5))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    check(lib().mcx_sweep(part.h_lat, sweeps))
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    timed_out = max(t for t, _ in s.status())
+    n = dims[0] * dims[1]
+    return {"metric": METRIC, "value": sweeps * n / (ms * 1e6), "unit": UNIT, "dims": dims, "rows_per_gpu": dims[1] // world,
+            "sweeps": sweeps, "us_per_half_sweep": ms * 1e3 / (2 * sweeps), "energy_per_site": s.energy(full=True) / n,
+            "wait_timed_out": int(timed_out),
+            "halo": "2 rows x %d B per half-sweep per GPU, peer loads over NVLink (CUDA IPC), no copies" % (dims[0] // 2)}
 
 
 def bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, L=1024, n=256, rounds=200, every=1):

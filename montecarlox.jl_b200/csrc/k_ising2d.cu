@@ -30,6 +30,36 @@ namespace {
 
 constexpr int kThreads = 128;
 
+// Cross-GPU ordering of a slab's half-sweep t (k_slab.cu): its boundary strips may start once both
+// neighbours have finished the boundary strips of their half-sweep t - 1 ...
+__device__ __forceinline__ void slab_wait(unsigned long long *ctl, uint64_t t)
+{
+    const volatile unsigned long long *f = ctl;
+    const unsigned long long need = t - f[SLAB_T0];
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (f[SLAB_FLAG_UP] < need || f[SLAB_FLAG_DN] < need) {
+        __nanosleep(100);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) { ctl[SLAB_ERR] = 1; break; }     // 20 s: give up rather than hang the GPU
+    }
+    __threadfence_system();
+}
+// ... and the last of the nb boundary CTAs to finish tells both neighbours.
+__device__ __forceinline__ void slab_signal(unsigned long long *ctl, uint64_t t, unsigned nb)
+{
+    __threadfence();
+    const unsigned arrived = atomicAdd((unsigned *)(ctl + SLAB_ARRIVED), 1u);
+    if (arrived + 1 == nb) {
+        *(volatile unsigned *)(ctl + SLAB_ARRIVED) = 0;
+        const unsigned long long value = t - ((volatile unsigned long long *)ctl)[SLAB_T0] + 1;
+        __threadfence_system();
+        *(volatile unsigned long long *)ctl[SLAB_UP_SLOT] = value;
+        *(volatile unsigned long long *)ctl[SLAB_DN_SLOT] = value;
+        __threadfence_system();
+    }
+}
+
 #ifdef MCX_OPT_TRACE
 // timing probe (scripts/trace_ctas.py): per CTA {start ns, end ns, SM id, items done} of the last launch,
 // followed by the start time of each of its first 8 items
@@ -91,8 +121,20 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
         const bool active = FULL ? true : g0 < G;                 // FULL: G % kThreads == 0, no idle lanes
         const int64_t g = active ? g0 : G - 1;
-        const int strip = (int)(g / nseg);
+        int strip = (int)(g / nseg);
         const int seg = (int)(g - (int64_t)strip * nseg);
+        // Slab of a taller lattice: the two strips that touch the neighbour slabs come first (strip order
+        // rotated by one), so that their rows are final -- and the neighbours told so -- while the interior
+        // is still being swept.  Only the CTAs holding them wait for the neighbours' previous half-sweep.
+        bool boundary_item = false;
+        if (SLAB) {
+            strip = strip == 0 ? nstrips - 1 : strip - 1;
+            boundary_item = L.slab_ctl != nullptr && (int64_t)item * kThreads < 2 * (int64_t)nseg;
+            if (boundary_item) {
+                if (threadIdx.x == 0) slab_wait(L.slab_ctl, t);
+                __syncthreads();
+            }
+        }
         const int row0 = strip * R;                               // even
         const uint32_t chain_id = first_chain + (uint32_t)chain;
 
@@ -199,6 +241,10 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
                 if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
                 if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
             }
+        }
+        if (SLAB && boundary_item) {
+            __syncthreads();
+            if (threadIdx.x == 0) slab_signal(L.slab_ctl, t, (unsigned)((2 * (int64_t)nseg + kThreads - 1) / kThreads));
         }
     }
 #ifdef MCX_OPT_TRACE
@@ -546,10 +592,11 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     // and with the halo rows taken from the neighbour slabs (k_slab.cu)
     constexpr bool kHasFull = MINB == 6 && !PREFETCH;
     const bool slab = kHasFull && lat->slab != nullptr;
-    const bool full = kHasFull && !slab && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
-    auto kern = slab ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, kHasFull>
-              : full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, false>
-                     : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>;
+    const bool full = kHasFull && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
+    auto kern = slab ? (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, kHasFull>
+                             : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, kHasFull>)
+                     : (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, false>
+                             : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>);
     static thread_local int resident = 0;
     if (!resident) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>, kThreads, 0);

@@ -7,13 +7,15 @@
 // of the neighbour GPU's process mapped through CUDA IPC and read over NVLink (attach_ipc).  16 bytes per
 // thread of a strip's first / last row are all that ever cross the link.
 //
-// Ordering between GPUs.  Half-sweep e of a slab may start once both neighbours have FINISHED half-sweep
-// e - 1: they have then written the rows it reads and are done reading the rows it overwrites.  Every slab
-// owns two 64-bit progress counters in its own memory; a neighbour bumps "its" counter with a one-thread
-// kernel queued behind each of its half-sweeps (system-scope fence, store over NVLink), and a one-thread
-// kernel queued in front of each half-sweep spins on the two local counters.  Everything is stream-ordered;
-// the host never synchronises.  A wait that lasts 20 s gives up and raises an error flag instead of
-// hanging the GPU.
+// Ordering between GPUs.  The boundary strips of half-sweep e of a slab may start once both neighbours have
+// FINISHED the boundary strips of half-sweep e - 1: they have then written the rows it reads and are done
+// reading the rows it overwrites.  Every slab owns a control block in its own memory (LatView::slab_ctl)
+// with one 64-bit progress counter per neighbour.  Inside the half-sweep kernel the strip order is rotated so
+// that the two boundary strips are the first items; only the CTAs that hold them poll the two local counters
+// (the interior never waits), and the last of them to finish bumps "its" counter in both neighbours' blocks
+// (system-scope fence, one 8-byte store over NVLink) while the interior is still being swept -- so by the
+// time a neighbour's next half-sweep starts, its wait is already satisfied.  No extra launches, no host
+// synchronisation.  A wait that lasts 20 s gives up and raises an error flag instead of hanging the GPU.
 //
 // Randomness is positioned by GLOBAL row (LatView::row_offset), so the trajectory of the split lattice is
 // bit-identical to the same lattice on one GPU (tests/test_gpu_slab.py).
@@ -24,48 +26,15 @@
 
 namespace mcx {
 
-namespace {
-
-__global__ void k_slab_wait(const volatile unsigned long long *flags, unsigned long long need, int *err)
-{
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (flags[0] < need || flags[1] < need) {
-        __nanosleep(200);
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) { *err = 1; break; }
-    }
-    __threadfence_system();
-}
-
-__global__ void k_slab_signal(volatile unsigned long long *up_slot, volatile unsigned long long *dn_slot,
-                              unsigned long long value)
-{
-    __threadfence_system();
-    *up_slot = value;
-    *dn_slot = value;
-    __threadfence_system();
-}
-
-}  // namespace
-
 // one colour of the current sweep of a slab, with the cross-GPU ordering when the neighbours are remote
 int32_t slab_half_sweep(mcx_lattice *lat)
 {
     mcx_slab *s = lat->slab;
-    cudaStream_t st = lat->ctx->stream;
-    if (s->remote) {
-        k_slab_wait<<<1, 1, 0, st>>>(s->d_flags, s->epoch, s->d_err);
-        lat->ctx->launches++;
-    }
     const uint64_t t = 2 * lat->sweep + (uint64_t)s->colour;
+    // remote neighbours: the kernel's boundary CTAs wait for / signal the neighbour GPUs (LatView::slab_ctl)
     if (!launch_sweep_ising2d(lat, s->colour, t)) return MCX_ERR_UNSUPPORTED;
     if (!lat->track_sums) lat->sums_dirty = true;
     s->epoch += 1;
-    if (s->remote) {
-        k_slab_signal<<<1, 1, 0, st>>>(s->up_flags + 1, s->dn_flags + 0, s->epoch);
-        lat->ctx->launches++;
-    }
     if (s->colour == 1) { lat->sweep += 1; lat->steps += lat->N; }
     s->colour ^= 1;
     return MCX_OK;
@@ -77,8 +46,7 @@ void slab_free(mcx_lattice *lat)
     if (!s) return;
     for (void *p : s->ipc_opened)
         if (p) cudaIpcCloseMemHandle(p);
-    cudaFree(s->d_flags);
-    cudaFree(s->d_err);
+    cudaFree(s->d_ctl);
     delete s;
     lat->slab = nullptr;
 }
@@ -100,6 +68,7 @@ int32_t mcx_slab_configure(mcx_lattice *lat, int32_t global_Ly, int32_t row_offs
     SREQ(lat->fast2d && lat->model == MCX_ISING && lat->storage == MCX_STORAGE_INT8, MCX_ERR_UNSUPPORTED,
          "slabs need a 2-D Ising int8 lattice with Lx % 32 == 0");
     SREQ(!lat->slab, MCX_ERR_STATE, "lattice is already a slab");
+    SREQ(lat->nchains == 1, MCX_ERR_UNSUPPORTED, "a slab handle holds one chain");
     SREQ(row_offset >= 0 && row_offset % 2 == 0 && lat->view.Ly % 2 == 0 && row_offset + lat->view.Ly <= global_Ly,
          MCX_ERR_ARGUMENT, "a slab is an even number of rows at an even offset inside the global lattice");
     SCUDA(cudaSetDevice(lat->ctx->device));
@@ -108,14 +77,11 @@ int32_t mcx_slab_configure(mcx_lattice *lat, int32_t global_Ly, int32_t row_offs
     memset(s, 0, sizeof(*s));
     s->global_Ly = global_Ly;
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&s->d_flags, 2 * sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMalloc((void **)&s->d_err, sizeof(int))) != cudaSuccess) {
-        cudaFree(s->d_flags);
+    if ((e = cudaMalloc((void **)&s->d_ctl, SLAB_CTL_WORDS * sizeof(unsigned long long))) != cudaSuccess) {
         delete s;
         return mcx_set_error(MCX_ERR_CUDA, cudaGetErrorString(e));
     }
-    SCUDA(cudaMemset(s->d_flags, 0, 2 * sizeof(unsigned long long)));
-    SCUDA(cudaMemset(s->d_err, 0, sizeof(int)));
+    SCUDA(cudaMemset(s->d_ctl, 0, SLAB_CTL_WORDS * sizeof(unsigned long long)));
     lat->slab = s;
     lat->view.row_offset = row_offset;
     return MCX_OK;
@@ -128,7 +94,7 @@ int32_t mcx_slab_export(mcx_lattice *lat, void *handle128)
     SCUDA(cudaSetDevice(lat->ctx->device));
     cudaIpcMemHandle_t h[2];
     SCUDA(cudaIpcGetMemHandle(&h[0], lat->view.planes));
-    SCUDA(cudaIpcGetMemHandle(&h[1], lat->slab->d_flags));
+    SCUDA(cudaIpcGetMemHandle(&h[1], lat->slab->d_ctl));
     memcpy(handle128, h, 128);
     return MCX_OK;
 }
@@ -152,9 +118,14 @@ int32_t mcx_slab_attach_ipc(mcx_lattice *lat, const void *up_handle128, const vo
         SCUDA(cudaIpcOpenMemHandle(&s->ipc_opened[3], h[1], cudaIpcMemLazyEnablePeerAccess));
     }
     lat->view.up_planes = (uint8_t *)s->ipc_opened[0];
-    s->up_flags = (unsigned long long *)s->ipc_opened[1];
     lat->view.dn_planes = (uint8_t *)(same ? s->ipc_opened[0] : s->ipc_opened[2]);
-    s->dn_flags = (unsigned long long *)(same ? s->ipc_opened[1] : s->ipc_opened[3]);
+    // I am the up neighbour's DOWN neighbour and the down neighbour's UP neighbour
+    unsigned long long *up_ctl = (unsigned long long *)s->ipc_opened[1];
+    unsigned long long *dn_ctl = (unsigned long long *)(same ? s->ipc_opened[1] : s->ipc_opened[3]);
+    unsigned long long ctl[SLAB_CTL_WORDS] = {0, 0, 2 * lat->sweep, (unsigned long long)(uintptr_t)(up_ctl + SLAB_FLAG_DN),
+                                              (unsigned long long)(uintptr_t)(dn_ctl + SLAB_FLAG_UP), 0, 0, 0};
+    SCUDA(cudaMemcpy(s->d_ctl, ctl, sizeof(ctl), cudaMemcpyHostToDevice));
+    lat->view.slab_ctl = s->d_ctl;
     s->remote = true;
     s->attached = true;
     return MCX_OK;
@@ -189,10 +160,10 @@ int32_t mcx_slab_status(mcx_lattice *lat, int32_t *timed_out, uint64_t *half_swe
 {
     SREQ(lat && lat->slab, MCX_ERR_ARGUMENT, "needs a configured slab");
     SCUDA(cudaSetDevice(lat->ctx->device));
-    int err = 0;
-    SCUDA(cudaMemcpyAsync(&err, lat->slab->d_err, sizeof(int), cudaMemcpyDeviceToHost, lat->ctx->stream));
+    unsigned long long err = 0;
+    SCUDA(cudaMemcpyAsync(&err, lat->slab->d_ctl + SLAB_ERR, sizeof(err), cudaMemcpyDeviceToHost, lat->ctx->stream));
     SCUDA(cudaStreamSynchronize(lat->ctx->stream));
-    if (timed_out) *timed_out = err;
+    if (timed_out) *timed_out = (int32_t)err;
     if (half_sweeps_done) *half_sweeps_done = lat->slab->epoch;
     return MCX_OK;
 }

@@ -197,7 +197,7 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
         lattice_free(lat);
         return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
-    v.up_planes = v.dn_planes = v.planes; v.row_offset = 0; v.pad_ = 0;
+    v.up_planes = v.dn_planes = v.planes; v.row_offset = 0; v.pad_ = 0; v.slab_ctl = nullptr;
     cudaMemsetAsync(lat->d_labels, 0, sizeof(int32_t) * (size_t)nchains, ctx->stream);
     cudaMemsetAsync(lat->d_sums, 0, sizeof(long long) * SUM_FIELDS * (size_t)nchains, ctx->stream);
     // constructors start all-up (ising.jl:118, blume_capel.jl:156)

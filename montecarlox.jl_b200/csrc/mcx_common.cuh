@@ -75,7 +75,13 @@ struct LatView {
     // (same shape and strides).  Not a slab: up_planes == dn_planes == planes, row_offset == 0.
     uint8_t *up_planes, *dn_planes;
     int32_t row_offset, pad_;
+    // slabs whose neighbours are other processes / GPUs: control block in this slab's memory (k_slab.cu);
+    // null otherwise.  [0], [1]: half-sweeps whose boundary rows the up / down neighbour has finished (they
+    // write it); [2]: half-sweep index at attach; [3], [4]: addresses of "my" counters in the up / down
+    // neighbour's block; [5]: arrival counter of the boundary CTAs; [6]: raised when a wait gave up.
+    unsigned long long *slab_ctl;
 };
+enum { SLAB_FLAG_UP = 0, SLAB_FLAG_DN = 1, SLAB_T0 = 2, SLAB_UP_SLOT = 3, SLAB_DN_SLOT = 4, SLAB_ARRIVED = 5, SLAB_ERR = 6, SLAB_CTL_WORDS = 8 };
 
 __device__ __forceinline__ uint8_t *plane_ptr(const LatView &L, int chain, int colour)
 {

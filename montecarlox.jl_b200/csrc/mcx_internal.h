@@ -17,9 +17,7 @@ struct mcx_slab {
     bool attached, remote;             // remote: neighbours live in other processes (IPC), ordered by device flags
     int colour;                        // colour of the next half-sweep
     unsigned long long epoch;          // half-sweeps completed since attach
-    unsigned long long *d_flags;       // [2]: half-sweeps completed by the up / down neighbour (they write it)
-    unsigned long long *up_flags, *dn_flags;   // the neighbours' d_flags
-    int *d_err;                        // raised by a wait that gave up
+    unsigned long long *d_ctl;         // control block, layout in mcx_common.cuh (LatView::slab_ctl)
     void *ipc_opened[4];
 };
 
