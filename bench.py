@@ -119,7 +119,7 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """per-launch dram bytes of the dominant kernel from the committed ncu capture, if any"""
+    """dram bytes of one half-sweep of the dominant kernel (all its band launches) from the committed ncu capture, if any"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
@@ -228,7 +228,7 @@ def run_ours(args):
     obs = [np.empty(1, dtype=np.int64) for _ in range(5)]
 
     def step():
-        check(lib().mcx_sweep(h, S))                                   # 2*S half-sweep launches
+        check(lib().mcx_sweep(h, S))                                   # 2*S half-sweeps
         check(lib().mcx_observables(h, *[o.ctypes.data for o in obs]))  # the step's result (syncs)
 
     for _ in range(args.warmup):
@@ -248,27 +248,33 @@ def run_ours(args):
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.launch_count() - launches0
 
-    # dominant kernel alone (roofline): 2*S launches of the half-sweep kernel, nothing else in between
+    # dominant kernel alone (roofline): 2*S half-sweeps of k_ising2d, nothing else in between.  A half-sweep of a
+    # big lattice is issued as `bands` launches of the same kernel on as many streams (row bands whose tails
+    # overlap), so the unit timed here is the half-sweep = bands launches, N/2 attempts.
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nk = 2 * S
+    lk0 = ctx.launch_count()
     k0.record(stream)
     check(lib().mcx_sweep(h, S))
     k1.record(stream)
     torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1) / nk
+    launches_per_half_sweep = (ctx.launch_count() - lk0) / nk
     clocks = sampler.stop()
 
     value = world * args.steps * S * N / (ms * 1e6)
     peak, peak_src = measured_peak()
-    bytes_per_launch = 3 * (N // 2)                                   # 3 B/attempt x N/2 attempts
+    bytes_per_launch = 3 * (N // 2)                                   # 3 B/attempt x N/2 attempts per half-sweep
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "k_ising2d (half-sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "bytes_per_attempt": 3,
-                "attempts_per_launch": N // 2, "kernel_ms": kernel_ms,
+                "attempts_per_launch": (N // 2) / launches_per_half_sweep, "launches_per_half_sweep": launches_per_half_sweep,
+                "attempts_per_half_sweep": N // 2, "kernel_ms": kernel_ms,
+                "kernel_ms_is": "one half-sweep (all its concurrent band launches), CUDA events on the launching stream",
                 "kernel_attempts_per_ns": (N // 2) / (kernel_ms * 1e6),
-                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "traffic": (traffic.get("dram_bytes_per_half_sweep") or traffic.get("dram_bytes_per_launch")) if traffic else None,
                 "traffic_source": traffic.get("source") if traffic else None}
 
     # ---- e2e: the public API with HOST buffers; H2D of the step's input and D2H of its result inside the timed region

@@ -578,20 +578,49 @@ int pick_rows_per_strip(int Ly, int want)
     return 2;
 }
 
+// chain sub-range and stream of the launch being issued (launch_sweeps_ising2d_grouped); default: whole batch
+struct LaunchRange {
+    int chain0 = 0, nchains = -1;
+    int row0 = 0, nrows = -1;              // row band [row0, row0 + nrows) of the lattice (whole lattice: nrows < 0)
+    int R = 0;                             // strip height of a band launch
+    cudaStream_t stream = nullptr;
+    bool use_stream = false;
+};
+static thread_local LaunchRange g_range;
+
 template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
 void launch_v(mcx_lattice *lat, uint64_t t)
 {
-    const LatView &L = lat->view;
-    const int R = auto_rows_per_strip(lat);
+    // a chain sub-range is the same launch on shifted base pointers: every per-chain array is indexed from them
+    LatView L = lat->view;
+    const int c0 = g_range.chain0, nch = g_range.nchains < 0 ? lat->nchains : g_range.nchains;
+    L.planes += (int64_t)c0 * 2 * L.plane_stride;
+    L.up_planes += (int64_t)c0 * 2 * L.plane_stride;
+    L.dn_planes += (int64_t)c0 * 2 * L.plane_stride;
+    L.nchains = nch;
+    // a row band is a slab of the lattice whose "neighbour slabs" are the rows around it in the same planes:
+    // the SLAB kernel variant runs it unchanged (k_slab.cu explains the three base pointers)
+    const bool band = g_range.nrows > 0;
+    if (band) {
+        const int Ly = lat->view.Ly, y0 = g_range.row0, nr = g_range.nrows;
+        const int64_t half = L.half;
+        L.up_planes = L.planes + ((int64_t)((y0 - 1 + Ly) % Ly) - (nr - 1)) * half;     // its row nr - 1 is global row y0 - 1
+        L.dn_planes = L.planes + (int64_t)((y0 + nr) % Ly) * half;                      // its row 0 is global row y0 + nr
+        L.planes += (int64_t)y0 * half;
+        L.Ly = nr;
+        L.row_offset = y0;
+    }
+    cudaStream_t stream = g_range.use_stream ? g_range.stream : lat->ctx->stream;
+    const int R = band ? g_range.R : auto_rows_per_strip(lat);
     const int nstrips = L.Ly / R;
     const int nseg = L.half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
     const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
-    const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
+    const int nitems = (int)((int64_t)blocks_per_chain * nch);
     // the shipped variant also exists with the idle-lane predicate compiled out (+2.8 %, r01_tune_allactive.log)
     // and with the halo rows taken from the neighbour slabs (k_slab.cu)
     constexpr bool kHasFull = MINB == 6 && !PREFETCH;
-    const bool slab = kHasFull && lat->slab != nullptr;
+    const bool slab = kHasFull && (lat->slab != nullptr || band);
     const bool full = kHasFull && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
     auto kern = slab ? (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, kHasFull>
                              : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, kHasFull>)
@@ -607,9 +636,9 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     // run the same number of items was measured 8 % slower: SMs with fewer CTAs do not finish sooner)
     int grid = lat->ctx->sm_count * ctas_per_sm;
     if (grid > nitems) grid = nitems;
-    kern<<<grid, kThreads, 0, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums,
-                                                 (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain, R,
-                                                 nstrips, blocks_per_chain, nitems);
+    kern<<<grid, kThreads, 0, stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels + c0, lat->d_sums + (int64_t)c0 * SUM_FIELDS,
+                                       (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain + (uint32_t)c0, R,
+                                       nstrips, blocks_per_chain, nitems);
     lat->ctx->launches++;
 }
 
@@ -718,6 +747,105 @@ bool launch_recompute_ising2d(mcx_lattice *lat)
     if (blocks > cap) blocks = cap;
     k_recompute2d<<<dim3((unsigned)blocks, (unsigned)lat->nchains), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_sums, segs);
     lat->ctx->launches++;
+    return true;
+}
+
+static bool aux_streams(mcx_ctx *ctx)
+{
+    if (ctx->aux_ready) return true;
+    for (int i = 0; i < 8; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->aux_join[i], cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+    if (cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+    ctx->aux_ready = true;
+    return true;
+}
+
+bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
+{
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
+    if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
+    // worth it only while a launch is a few items per resident CTA (its tail is then a third of its span)
+    const int groups_env = env_int("MCX_GROUPS", -1);
+    if (groups_env == 0 || groups_env == 1) return false;
+    const int R = auto_rows_per_strip(lat);
+    const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
+    if (G < 96) return false;                                          // rows-of-8 territory
+    const int64_t items = (G + kThreads - 1) / kThreads * lat->nchains;
+    const int64_t ctas = (int64_t)lat->ctx->sm_count * 6;
+    int groups = groups_env > 1 ? groups_env : 4;
+    if (groups > 8) groups = 8;
+    if (groups > lat->nchains) groups = lat->nchains;
+    if (groups_env < 0)
+        while (groups > 1 && items / groups < ctas / 4) --groups;     // a group's launch should still fill a good part of the SMs
+    if (groups < 2) return false;
+    mcx_ctx *ctx = lat->ctx;
+    if (!aux_streams(ctx)) return false;
+    cudaEventRecord(ctx->aux_fork, ctx->stream);
+    for (int g = 0; g < groups; ++g) cudaStreamWaitEvent(ctx->aux[g], ctx->aux_fork, 0);
+    // group-major would serialise the groups on the host side; interleave so that their launches alternate
+    for (int64_t s = 0; s < nsweeps; ++s)
+        for (int colour = 0; colour < 2; ++colour)
+            for (int g = 0; g < groups; ++g) {
+                const int c0 = (int)((int64_t)lat->nchains * g / groups), c1 = (int)((int64_t)lat->nchains * (g + 1) / groups);
+                g_range.chain0 = c0; g_range.nchains = c1 - c0; g_range.stream = ctx->aux[g]; g_range.use_stream = true;
+                const uint64_t t = 2 * (lat->sweep + (uint64_t)s) + (uint64_t)colour;
+                if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
+            }
+    g_range = LaunchRange();
+    for (int g = 0; g < groups; ++g) {
+        cudaEventRecord(ctx->aux_join[g], ctx->aux[g]);
+        cudaStreamWaitEvent(ctx->stream, ctx->aux_join[g], 0);
+    }
+    return true;
+}
+
+bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
+{
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->nchains != 1) return false;
+    if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
+    const int bands_env = env_int("MCX_BANDS", -1);
+    if (bands_env == 0 || bands_env == 1) return false;
+    // 8 bands (the hardware queues a process gets by default) of 16-row strips, each at least ~100 CTA items:
+    // measured +8 % at L = 8192, +17 % at 16384, +10 % at 32768; 2 bands gain nothing (each waits for the other),
+    // 4 bands gain less, shorter strips or smaller bands lose (profiles/r01_bands_groups.md).  MCX_BANDS forces a count.
+    const int Ly = lat->view.Ly;
+    const bool forced = bands_env > 1;
+    int bands = forced ? (bands_env > 8 ? 8 : bands_env) : 8;
+    const int R = 16;
+    if (Ly % (R * bands) != 0) return false;
+    const int64_t items_per_band = ((int64_t)(Ly / bands / R) * (lat->view.half >> 4) + kThreads - 1) / kThreads;
+    if (!forced && items_per_band < 100) bands = 0;
+    if (!bands) return false;
+    const int nr = Ly / bands;
+    mcx_ctx *ctx = lat->ctx;
+    if (!aux_streams(ctx)) return false;
+    cudaEventRecord(ctx->aux_fork, ctx->stream);
+    for (int b = 0; b < bands; ++b) cudaStreamWaitEvent(ctx->aux[b], ctx->aux_fork, 0);
+    for (int64_t s = 0; s < nsweeps; ++s)
+        for (int colour = 0; colour < 2; ++colour) {
+            const bool first = s == 0 && colour == 0;
+            // half-sweep h of band b needs half-sweep h - 1 of bands b - 1, b, b + 1 (b: stream order).  All waits of
+            // this half-sweep are queued before any of its records, so they refer to the previous half-sweep's.
+            if (!first)
+                for (int b = 0; b < bands; ++b) {
+                    cudaStreamWaitEvent(ctx->aux[b], ctx->aux_join[(b + bands - 1) % bands], 0);
+                    cudaStreamWaitEvent(ctx->aux[b], ctx->aux_join[(b + 1) % bands], 0);
+                }
+            for (int b = 0; b < bands; ++b) {
+                g_range = LaunchRange();
+                g_range.row0 = b * nr; g_range.nrows = nr; g_range.R = R; g_range.stream = ctx->aux[b]; g_range.use_stream = true;
+                const uint64_t t = 2 * (lat->sweep + (uint64_t)s) + (uint64_t)colour;
+                if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
+                cudaEventRecord(ctx->aux_join[b], ctx->aux[b]);
+            }
+        }
+    g_range = LaunchRange();
+    for (int b = 0; b < bands; ++b) cudaStreamWaitEvent(ctx->stream, ctx->aux_join[b], 0);
     return true;
 }
 

@@ -93,6 +93,10 @@ int32_t mcx_ctx_destroy(mcx_ctx *ctx)
     if (!ctx) return MCX_OK;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux_ready) {
+        for (int i = 0; i < 8; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->aux_join[i]); }
+        cudaEventDestroy(ctx->aux_fork);
+    }
     delete ctx;
     return MCX_OK;
 }
@@ -392,16 +396,25 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     // test hooks: MCX_FORCE_GENERIC=1 -> shape-generic kernel, =2 -> rows-of-8 kernel
     const char *fg = getenv("MCX_FORCE_GENERIC");
     const int force = fg ? atoi(fg) : 0;
-    for (int64_t s = 0; s < nsweeps; ++s) {
-        // series of sweeps over small lattices: one launch with the lattice resident in shared memory
-        if (force == 0) {
+    bool try_series = force == 0;        // whole-series launchers (resident kernel, chain groups) still worth asking
+    for (int64_t s = 0; s < nsweeps;) {
+        if (try_series) {
+            // series of sweeps over small lattices: one launch with the lattice resident in shared memory
             const int64_t chunk = nsweeps - s < 16384 ? nsweeps - s : 16384;
             if (launch_sweeps_resident(lat, chunk)) {
                 if (!lat->track_sums) lat->sums_dirty = true;
                 lat->sweep += (uint64_t)chunk;
-                s += chunk - 1;
+                s += chunk;
                 continue;
             }
+            // chain groups (batches) or row bands (one big lattice) on auxiliary streams overlap each other's launch tails
+            if (lat->nchains > 1 ? launch_sweeps_ising2d_grouped(lat, nsweeps - s) : launch_sweeps_ising2d_banded(lat, nsweeps - s)) {
+                if (!lat->track_sums) lat->sums_dirty = true;
+                lat->sweep += (uint64_t)(nsweeps - s);
+                s = nsweeps;
+                continue;
+            }
+            try_series = false;
         }
         for (int colour = 0; colour < 2; ++colour) {
             const uint64_t t = 2 * lat->sweep + (uint64_t)colour;
@@ -411,6 +424,7 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
             else if (!launch_sweep_rows8(lat, colour, t)) launch_sweep_generic(lat, colour, t);
         }
         lat->sweep += 1;
+        s += 1;
     }
     lat->steps += nsweeps * lat->N;
     return check_launch(lat->ctx);

