@@ -85,6 +85,43 @@ def test_fast_kernel_equals_generic_kernel(m, L):
         assert np.array_equal(o[0], outs[0][0]) and o[1:] == outs[0][1:]
 
 
+@pytest.mark.parametrize("dims,nchains,envs", [
+    ([1024, 1024], 1, [{"MCX_BANDS": "2"}, {"MCX_BANDS": "4"}, {"MCX_BANDS": "8"}]),
+    ([2048, 512], 1, [{"MCX_BANDS": "4"}]),
+    ([512, 512], 6, [{"MCX_GROUPS": "2"}, {"MCX_GROUPS": "4"}, {"MCX_GROUPS": "6"}]),
+])
+def test_bands_and_groups_equal_plain_launches(m, dims, nchains, envs):
+    """a half-sweep issued as several overlapping launches (row bands of one lattice, chain groups of a
+    batch) gives the trajectory of the single launch, sums and counters included"""
+    keys = ("MCX_BANDS", "MCX_GROUPS", "MCX_RESIDENT")
+
+    def run(rule, track, env):
+        for k in keys:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        s = m.Ising(dims, nchains=nchains)
+        s.set_tracking(track)
+        alg = _make_alg(m, rule, BETA_C, 11, 0)
+        s.init_("random", rng=alg.rng)
+        l0 = s.ctx.launch_count()
+        m.sweep_(s, alg, 4)
+        m.sweep_(s, alg, 1)
+        out = (s.spins.copy(), np.array(s.pair_sum()), np.array(s.magnetization()), np.array(s.accepted()))
+        return out, s.ctx.launch_count() - l0
+
+    try:
+        for rule in (0, 2):
+            for track in (True, False):
+                ref, l_ref = run(rule, track, {"MCX_BANDS": "0", "MCX_GROUPS": "0", "MCX_RESIDENT": "0"})
+                for env in envs:
+                    got, l_got = run(rule, track, dict(env, MCX_RESIDENT="0"))
+                    assert l_got > l_ref, "the banded / grouped path was not taken"
+                    assert all(np.array_equal(a, b) for a, b in zip(ref, got)), (rule, track, env)
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
 def test_ising2d_untracked_sums_match(m, oracle):
     L, nsweeps = 128, 5
     s_or, a_or = _oracle_run(oracle, oracle.ISING, [L, L], 0, BETA_C, 1, 0, 0, 5, 0, nsweeps)
