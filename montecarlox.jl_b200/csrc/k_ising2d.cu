@@ -32,30 +32,31 @@ constexpr int kThreads = 128;
 
 // Cross-GPU ordering of a slab's half-sweep t (k_slab.cu): its boundary strips may start once both
 // neighbours have finished the boundary strips of their half-sweep t - 1 ...
-__device__ __forceinline__ void slab_wait(unsigned long long *ctl, uint64_t t)
+__device__ __forceinline__ void slab_wait(unsigned long long *ctl, uint64_t t, int sides)
 {
     const volatile unsigned long long *f = ctl;
     const unsigned long long need = t - f[SLAB_T0];
     unsigned long long t0, t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (f[SLAB_FLAG_UP] < need || f[SLAB_FLAG_DN] < need) {
+    while (((sides & 1) && f[SLAB_FLAG_UP] < need) || ((sides & 2) && f[SLAB_FLAG_DN] < need)) {
         __nanosleep(100);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 20000000000ull) { ctl[SLAB_ERR] = 1; break; }     // 20 s: give up rather than hang the GPU
     }
     __threadfence_system();
 }
-// ... and the last of the nb boundary CTAs to finish tells both neighbours.
-__device__ __forceinline__ void slab_signal(unsigned long long *ctl, uint64_t t, unsigned nb)
+// ... and the last of the nb boundary CTAs to finish tells the neighbour(s).
+__device__ __forceinline__ void slab_signal(unsigned long long *ctl, uint64_t t, unsigned nb, int sides)
 {
     __threadfence();
-    const unsigned arrived = atomicAdd((unsigned *)(ctl + SLAB_ARRIVED), 1u);
+    unsigned *counter = (unsigned *)(ctl + (sides == 2 ? SLAB_ARRIVED_DN : SLAB_ARRIVED));
+    const unsigned arrived = atomicAdd(counter, 1u);
     if (arrived + 1 == nb) {
-        *(volatile unsigned *)(ctl + SLAB_ARRIVED) = 0;
+        *(volatile unsigned *)counter = 0;
         const unsigned long long value = t - ((volatile unsigned long long *)ctl)[SLAB_T0] + 1;
         __threadfence_system();
-        *(volatile unsigned long long *)ctl[SLAB_UP_SLOT] = value;
-        *(volatile unsigned long long *)ctl[SLAB_DN_SLOT] = value;
+        if (sides & 1) *(volatile unsigned long long *)ctl[SLAB_UP_SLOT] = value;
+        if (sides & 2) *(volatile unsigned long long *)ctl[SLAB_DN_SLOT] = value;
         __threadfence_system();
     }
 }
@@ -131,7 +132,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             strip = strip == 0 ? nstrips - 1 : strip - 1;
             boundary_item = L.slab_ctl != nullptr && (int64_t)item * kThreads < 2 * (int64_t)nseg;
             if (boundary_item) {
-                if (threadIdx.x == 0) slab_wait(L.slab_ctl, t);
+                if (threadIdx.x == 0) slab_wait(L.slab_ctl, t, L.slab_sides);
                 __syncthreads();
             }
         }
@@ -244,7 +245,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         }
         if (SLAB && boundary_item) {
             __syncthreads();
-            if (threadIdx.x == 0) slab_signal(L.slab_ctl, t, (unsigned)((2 * (int64_t)nseg + kThreads - 1) / kThreads));
+            if (threadIdx.x == 0) slab_signal(L.slab_ctl, t, (unsigned)((2 * (int64_t)nseg + kThreads - 1) / kThreads), L.slab_sides);
         }
     }
 #ifdef MCX_OPT_TRACE
@@ -604,11 +605,18 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     if (band) {
         const int Ly = lat->view.Ly, y0 = g_range.row0, nr = g_range.nrows;
         const int64_t half = L.half;
-        L.up_planes = L.planes + ((int64_t)((y0 - 1 + Ly) % Ly) - (nr - 1)) * half;     // its row nr - 1 is global row y0 - 1
-        L.dn_planes = L.planes + (int64_t)((y0 + nr) % Ly) * half;                      // its row 0 is global row y0 + nr
+        const bool top = y0 == 0, bottom = y0 + nr == Ly;
+        // the band's "neighbour slabs": the rows around it in the same planes, except that the first / last band
+        // of a slab of a taller lattice keeps the slab's own neighbour on that side (and orders itself against it)
+        uint8_t *up = lat->slab && top ? L.up_planes + (int64_t)(Ly - nr) * half
+                                       : L.planes + ((int64_t)((y0 - 1 + Ly) % Ly) - (nr - 1)) * half;   // its row nr - 1 is row y0 - 1
+        uint8_t *dn = lat->slab && bottom ? L.dn_planes : L.planes + (int64_t)((y0 + nr) % Ly) * half;   // its row 0 is row y0 + nr
+        L.up_planes = up; L.dn_planes = dn;
         L.planes += (int64_t)y0 * half;
         L.Ly = nr;
-        L.row_offset = y0;
+        L.row_offset += y0;
+        L.slab_sides = (top ? 1 : 0) | (bottom ? 2 : 0);
+        if (!L.slab_sides) L.slab_ctl = nullptr;
     }
     cudaStream_t stream = g_range.use_stream ? g_range.stream : lat->ctx->stream;
     const int R = band ? g_range.R : auto_rows_per_strip(lat);
@@ -806,7 +814,8 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 
 bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->nchains != 1) return false;
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->nchains != 1) return false;
+    if (lat->slab && !(lat->slab->attached && lat->slab->remote)) return false;      // in-process slabs advance in lockstep
     if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
     const int bands_env = env_int("MCX_BANDS", -1);
     if (bands_env == 0 || bands_env == 1) return false;

@@ -201,7 +201,7 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
         lattice_free(lat);
         return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
-    v.up_planes = v.dn_planes = v.planes; v.row_offset = 0; v.pad_ = 0; v.slab_ctl = nullptr;
+    v.up_planes = v.dn_planes = v.planes; v.row_offset = 0; v.slab_sides = 3; v.slab_ctl = nullptr;
     cudaMemsetAsync(lat->d_labels, 0, sizeof(int32_t) * (size_t)nchains, ctx->stream);
     cudaMemsetAsync(lat->d_sums, 0, sizeof(long long) * SUM_FIELDS * (size_t)nchains, ctx->stream);
     // constructors start all-up (ising.jl:118, blume_capel.jl:156)
@@ -387,6 +387,14 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
         REQUIRE(lat->slab->attached && lat->slab->remote, MCX_ERR_STATE,
                 "slabs attached inside one process advance in lockstep through mcx_slab_half_sweep");
         REQUIRE(lat->slab->colour == 0, MCX_ERR_STATE, "slab is in the middle of a sweep");
+        // a tall slab: row bands on auxiliary streams, the first / last band ordered against the neighbour GPUs
+        if (nsweeps > 0 && launch_sweeps_ising2d_banded(lat, nsweeps)) {
+            if (!lat->track_sums) lat->sums_dirty = true;
+            lat->sweep += (uint64_t)nsweeps;
+            lat->steps += nsweeps * lat->N;
+            lat->slab->epoch += 2 * (uint64_t)nsweeps;
+            return check_launch(lat->ctx);
+        }
         for (int64_t s = 0; s < 2 * nsweeps; ++s) {
             const int32_t st = slab_half_sweep(lat);
             if (st != MCX_OK) return fail(st, "slab half-sweep could not be launched");

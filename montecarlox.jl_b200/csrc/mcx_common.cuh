@@ -74,14 +74,16 @@ struct LatView {
     // lattice; the row above row 0 / below row Ly-1 lives in the plane arrays of the neighbour slabs
     // (same shape and strides).  Not a slab: up_planes == dn_planes == planes, row_offset == 0.
     uint8_t *up_planes, *dn_planes;
-    int32_t row_offset, pad_;
+    int32_t row_offset;
+    int32_t slab_sides;     // which neighbour GPUs this launch orders itself against: 1 = up, 2 = down (bands: one side each)
     // slabs whose neighbours are other processes / GPUs: control block in this slab's memory (k_slab.cu);
     // null otherwise.  [0], [1]: half-sweeps whose boundary rows the up / down neighbour has finished (they
     // write it); [2]: half-sweep index at attach; [3], [4]: addresses of "my" counters in the up / down
-    // neighbour's block; [5]: arrival counter of the boundary CTAs; [6]: raised when a wait gave up.
+    // neighbour's block; [5]: arrival counter of the boundary CTAs (launches ordered against the up side or
+    // both); [6]: raised when a wait gave up; [7]: arrival counter of launches ordered against the down side only.
     unsigned long long *slab_ctl;
 };
-enum { SLAB_FLAG_UP = 0, SLAB_FLAG_DN = 1, SLAB_T0 = 2, SLAB_UP_SLOT = 3, SLAB_DN_SLOT = 4, SLAB_ARRIVED = 5, SLAB_ERR = 6, SLAB_CTL_WORDS = 8 };
+enum { SLAB_FLAG_UP = 0, SLAB_FLAG_DN = 1, SLAB_T0 = 2, SLAB_UP_SLOT = 3, SLAB_DN_SLOT = 4, SLAB_ARRIVED = 5, SLAB_ERR = 6, SLAB_ARRIVED_DN = 7, SLAB_CTL_WORDS = 8 };
 
 __device__ __forceinline__ uint8_t *plane_ptr(const LatView &L, int chain, int colour)
 {

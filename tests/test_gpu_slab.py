@@ -79,7 +79,7 @@ torch.cuda.set_device(rank %% ngpu)
 dist.init_process_group("gloo", rank=rank, world_size=world)
 import mcx_b200 as m
 ctx = m.Context(rank %% ngpu)
-dims, nsweeps = [256, 64 * world], 3
+dims, nsweeps = [256, 128 * world], 3
 s = m.SlabIsing(dims, backend=m.GPUBackend(), ctx=ctx)
 rng = m.PhiloxRNG(123, 1)
 alg = m.Metropolis(rng, beta=0.44)
@@ -101,16 +101,20 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_ipc_slabs_across_processes(m, world, tmp_path):
+@pytest.mark.parametrize("world,bands", [(2, None), (3, None), (2, "2"), (2, "4")])
+def test_ipc_slabs_across_processes(m, world, bands, tmp_path):
     """one process per slab (sharing this GPU when the box has fewer GPUs than ranks): CUDA IPC mapping of
     the neighbour's planes, device flags for the ordering -- the multi-GPU path end to end"""
     script = tmp_path / "worker.py"
     script.write_text(_WORKER % {"root": ROOT})
-    port = 29600 + world
+    port = 29600 + world + (10 * int(bands) if bands else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    env = dict(os.environ)
+    env.pop("MCX_BANDS", None)
+    if bands:                      # every slab additionally split into row bands on auxiliary streams
+        env["MCX_BANDS"] = bands
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     import json
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
