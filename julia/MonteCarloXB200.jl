@@ -305,4 +305,37 @@ function index(rx::DeviceReplicaExchange)                    # replica_exchange.
     return idx
 end
 
+# ----------------------------------------------------------------------------------------------
+# 5. One lattice over several GPUs (beyond the reference: IsingLatticeOptim, ising.jl:430-461, is one
+#    Vector{Int8}).  Each rank holds a slab of rows; the half-sweep kernel reads the rows above / below
+#    the slab straight from the neighbour GPU's memory (CUDA IPC, NVLink), device flags order the
+#    half-sweeps, and `sweep!` is the ordinary one.  `allgather_bytes` is whatever the host runtime
+#    offers (MPI.Allgather on a UInt8 buffer).
+# ----------------------------------------------------------------------------------------------
+struct SlabIsing
+    part::DeviceIsing          # this rank's rows
+    dims::Vector{Int}          # global [Lx, Ly]
+    backend::GPUBackend
+end
+
+function SlabIsing(ctx::DeviceCtx, dims::Vector{Int}, backend::GPUBackend, allgather_bytes)
+    Lx, Ly = dims
+    n, r = backend.size, backend.rank
+    Ly % (2n) == 0 || throw(ArgumentError("Ly = $Ly does not split into $n slabs of an even number of rows"))
+    rows = Ly ÷ n
+    part = DeviceIsing(ctx, [Lx, rows])
+    check(ccall((:mcx_slab_configure, libmcx), Int32, (Ptr{Cvoid}, Int32, Int32), part.h, Ly, r * rows))
+    token = Vector{UInt8}(undef, 128)
+    GC.@preserve token check(ccall((:mcx_slab_export, libmcx), Int32, (Ptr{Cvoid}, Ptr{UInt8}), part.h, token))
+    all = allgather_bytes(token)                       # 128 bytes per rank, rank order
+    up, dn = all[mod(r - 1, n) + 1], all[mod(r + 1, n) + 1]
+    GC.@preserve up dn check(ccall((:mcx_slab_attach_ipc, libmcx), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{UInt8}), part.h, up, dn))
+    return SlabIsing(part, dims, backend)
+end
+
+sweep!(sys::SlabIsing, alg, nsweeps::Integer=1) = sweep!(sys.part, alg, nsweeps)
+# energy / magnetization of the whole lattice: sum of the slabs' shares (the host reduces, e.g. MPI.Allreduce)
+local_pair_sum(sys::SlabIsing) = sums(sys.part)[1]
+local_spin_sum(sys::SlabIsing) = sums(sys.part)[2]
+
 end # module
