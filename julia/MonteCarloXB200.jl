@@ -320,7 +320,7 @@ end
 
 function SlabIsing(ctx::DeviceCtx, dims::Vector{Int}, backend::GPUBackend, allgather_bytes)
     Lx, Ly = dims
-    n, r = backend.size, backend.rank
+    n, r = backend.nranks, backend.rank
     Ly % (2n) == 0 || throw(ArgumentError("Ly = $Ly does not split into $n slabs of an even number of rows"))
     rows = Ly ÷ n
     part = DeviceIsing(ctx, [Lx, rows])
