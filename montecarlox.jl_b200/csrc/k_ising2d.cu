@@ -26,6 +26,8 @@
 
 namespace mcx {
 
+thread_local LaunchRange g_launch_range;
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -579,31 +581,23 @@ int pick_rows_per_strip(int Ly, int want)
     return 2;
 }
 
-// chain sub-range and stream of the launch being issued (launch_sweeps_ising2d_grouped); default: whole batch
-struct LaunchRange {
-    int chain0 = 0, nchains = -1;
-    int row0 = 0, nrows = -1;              // row band [row0, row0 + nrows) of the lattice (whole lattice: nrows < 0)
-    int R = 0;                             // strip height of a band launch
-    cudaStream_t stream = nullptr;
-    bool use_stream = false;
-};
-static thread_local LaunchRange g_range;
+
 
 template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
 void launch_v(mcx_lattice *lat, uint64_t t)
 {
     // a chain sub-range is the same launch on shifted base pointers: every per-chain array is indexed from them
     LatView L = lat->view;
-    const int c0 = g_range.chain0, nch = g_range.nchains < 0 ? lat->nchains : g_range.nchains;
+    const int c0 = g_launch_range.chain0, nch = g_launch_range.nchains < 0 ? lat->nchains : g_launch_range.nchains;
     L.planes += (int64_t)c0 * 2 * L.plane_stride;
     L.up_planes += (int64_t)c0 * 2 * L.plane_stride;
     L.dn_planes += (int64_t)c0 * 2 * L.plane_stride;
     L.nchains = nch;
     // a row band is a slab of the lattice whose "neighbour slabs" are the rows around it in the same planes:
     // the SLAB kernel variant runs it unchanged (k_slab.cu explains the three base pointers)
-    const bool band = g_range.nrows > 0;
+    const bool band = g_launch_range.nrows > 0;
     if (band) {
-        const int Ly = lat->view.Ly, y0 = g_range.row0, nr = g_range.nrows;
+        const int Ly = lat->view.Ly, y0 = g_launch_range.row0, nr = g_launch_range.nrows;
         const int64_t half = L.half;
         const bool top = y0 == 0, bottom = y0 + nr == Ly;
         // the band's "neighbour slabs": the rows around it in the same planes, except that the first / last band
@@ -618,8 +612,8 @@ void launch_v(mcx_lattice *lat, uint64_t t)
         L.slab_sides = (top ? 1 : 0) | (bottom ? 2 : 0);
         if (!L.slab_sides) L.slab_ctl = nullptr;
     }
-    cudaStream_t stream = g_range.use_stream ? g_range.stream : lat->ctx->stream;
-    const int R = band ? g_range.R : auto_rows_per_strip(lat);
+    cudaStream_t stream = g_launch_range.use_stream ? g_launch_range.stream : lat->ctx->stream;
+    const int R = band ? g_launch_range.R : auto_rows_per_strip(lat);
     const int nstrips = L.Ly / R;
     const int nseg = L.half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
@@ -775,7 +769,9 @@ static bool aux_streams(mcx_ctx *ctx)
 
 bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
+    if (!lat->fast2d || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
+    const bool bc = lat->model == MCX_BLUME_CAPEL;
+    if (bc && (lat->rule == MCX_HEATBATH || env_int("MCX_BC2D", 1) == 0)) return false;      // k_bc2d's own conditions
     if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
     // worth it only while a launch is a few items per resident CTA (its tail is then a third of its span)
     const int groups_env = env_int("MCX_GROUPS", -1);
@@ -800,11 +796,12 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
         for (int colour = 0; colour < 2; ++colour)
             for (int g = 0; g < groups; ++g) {
                 const int c0 = (int)((int64_t)lat->nchains * g / groups), c1 = (int)((int64_t)lat->nchains * (g + 1) / groups);
-                g_range.chain0 = c0; g_range.nchains = c1 - c0; g_range.stream = ctx->aux[g]; g_range.use_stream = true;
+                g_launch_range.chain0 = c0; g_launch_range.nchains = c1 - c0; g_launch_range.stream = ctx->aux[g]; g_launch_range.use_stream = true;
                 const uint64_t t = 2 * (lat->sweep + (uint64_t)s) + (uint64_t)colour;
-                if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
+                if (bc) launch_sweep_bc2d(lat, colour, t);
+                else if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
             }
-    g_range = LaunchRange();
+    g_launch_range = LaunchRange();
     for (int g = 0; g < groups; ++g) {
         cudaEventRecord(ctx->aux_join[g], ctx->aux[g]);
         cudaStreamWaitEvent(ctx->stream, ctx->aux_join[g], 0);
@@ -846,14 +843,14 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
                     cudaStreamWaitEvent(ctx->aux[b], ctx->aux_join[(b + 1) % bands], 0);
                 }
             for (int b = 0; b < bands; ++b) {
-                g_range = LaunchRange();
-                g_range.row0 = b * nr; g_range.nrows = nr; g_range.R = R; g_range.stream = ctx->aux[b]; g_range.use_stream = true;
+                g_launch_range = LaunchRange();
+                g_launch_range.row0 = b * nr; g_launch_range.nrows = nr; g_launch_range.R = R; g_launch_range.stream = ctx->aux[b]; g_launch_range.use_stream = true;
                 const uint64_t t = 2 * (lat->sweep + (uint64_t)s) + (uint64_t)colour;
                 if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
                 cudaEventRecord(ctx->aux_join[b], ctx->aux[b]);
             }
         }
-    g_range = LaunchRange();
+    g_launch_range = LaunchRange();
     for (int b = 0; b < bands; ++b) cudaStreamWaitEvent(ctx->stream, ctx->aux_join[b], 0);
     return true;
 }

@@ -75,6 +75,17 @@ struct mcx_flat {
 
 namespace mcx {
 
+// chain sub-range, row band and stream of the launch being issued by the series launchers (k_ising2d.cu);
+// default: the whole batch on the context's stream.  Read by the half-sweep launchers of k_ising2d.cu / k_bc2d.cu.
+struct LaunchRange {
+    int chain0 = 0, nchains = -1;
+    int row0 = 0, nrows = -1;              // row band [row0, row0 + nrows) of the lattice (whole lattice: nrows < 0)
+    int R = 0;                             // strip height of a band launch
+    cudaStream_t stream = nullptr;
+    bool use_stream = false;
+};
+extern thread_local LaunchRange g_launch_range;
+
 // k_generic.cu
 void launch_pack(mcx_lattice *lat);      // staging (reference order, -1/0/+1) -> colour planes
 void launch_unpack(mcx_lattice *lat);    // colour planes -> staging
@@ -90,6 +101,9 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps);
 // nsweeps sweeps of one big lattice with its rows dealt into bands on auxiliary streams; a band's half-sweep
 // waits (events) only for its own and its two neighbour bands' previous half-sweep; false: not applicable
 bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps);
+// k_bc2d.cu: vectorised 2-D Blume-Capel half-sweep (Metropolis / Glauber, Lx % 32 == 0)
+bool launch_sweep_bc2d(mcx_lattice *lat, int colour, uint64_t t);       // false: not applicable, nothing launched
+
 // k_slab.cu
 int32_t slab_half_sweep(mcx_lattice *lat);
 void slab_free(mcx_lattice *lat);

@@ -157,6 +157,51 @@ def test_ising3d_bit_exact(m, oracle, rule, dims):
     _check(sys_, s_or, a_or, alg, 10)
 
 
+@pytest.mark.parametrize("dims", [[64, 64], [256, 64], [32, 128], [512, 256]])
+@pytest.mark.parametrize("rule", [0, 1])
+def test_blume_capel_vectorised_kernel(m, oracle, dims, rule):
+    """k_bc2d (packed 15-bit decisions, four Philox blocks per thread-row) against the oracle and against the
+    rows-of-8 kernel, tracked and untracked sums, several couplings"""
+    for beta, J, D, h, tracking in ((0.8, 1, 0, 0, True), (1.1, 1.0, 0.5, 0.0, False), (0.6, 1.0, 0.2, 0.1, True), (2.5, 1, 1.9, 0, True)):
+        nsweeps = 6
+        outs = []
+        for env in ({}, {"MCX_BC2D": "0"}):
+            os.environ.pop("MCX_BC2D", None)
+            os.environ.update(env)
+            sys_ = m.BlumeCapel(dims, J=J, D=D, h=h)
+            sys_.set_tracking(tracking)
+            alg = _make_alg(m, rule, beta, 77, 2)
+            sys_.init_("random", rng=alg.rng)
+            m.sweep_(sys_, alg, nsweeps)
+            outs.append((sys_.spins.copy(), sys_.pair_sum(), sys_.magnetization(), sys_.spin2_sum(), alg.accepted))
+        os.environ.pop("MCX_BC2D", None)
+        assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]
+        s_or, a_or = _oracle_run(oracle, oracle.BLUME_CAPEL, dims, rule, beta, J, h, D, 77, 2, nsweeps)
+        assert np.array_equal(outs[0][0], s_or.spins)
+        assert outs[0][1] == s_or.pair_count() and outs[0][2] == s_or.magnetization(full=True) and outs[0][3] == s_or.spin2_sum()
+        assert outs[0][4] == a_or.accepted
+
+
+def test_blume_capel_vectorised_batched_labels(m, oracle):
+    """chains with different tables (labels) and chain ids in one k_bc2d launch"""
+    dims, n, nsweeps = [64, 64], 5, 5
+    betas = [0.5, 0.8, 1.0, 1.3, 2.0]
+    sys_ = m.BlumeCapel(dims, J=1, D=0.3, nchains=n)
+    tables = np.stack([m.build_table(1, 0, 2, b, 1.0, 0.0, 0.3) for b in betas])
+    sys_.set_rule(0, tables)
+    labels = [4, 0, 3, 1, 2]
+    sys_.set_labels(labels)
+    sys_.set_rng(4711, 0)
+    sys_.init_("random", rng=m.PhiloxRNG(4711, 0))
+    m.lib().mcx_sweep(sys_.h_lat, nsweeps)
+    got = sys_.spins
+    for c in range(n):
+        s_or, a_or = _oracle_run(oracle, oracle.BLUME_CAPEL, dims, 0, betas[labels[c]], 1.0, 0.0, 0.3, 4711, c, nsweeps)
+        assert np.array_equal(got[c], s_or.spins)
+        assert sys_.pair_sum()[c] == s_or.pair_count() and sys_.spin2_sum()[c] == s_or.spin2_sum()
+        assert sys_.accepted()[c] == a_or.accepted
+
+
 @pytest.mark.parametrize("dims", [[8, 8], [32, 16], [6, 4, 8], [64, 12], [16, 6, 4]])
 @pytest.mark.parametrize("rule", [0, 1, 2])
 def test_blume_capel_bit_exact(m, oracle, dims, rule):
