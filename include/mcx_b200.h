@@ -183,6 +183,15 @@ int32_t mcx_pt_destroy(mcx_pt *pt);
  * host runtime all-gathers the buffer in place (NCCL) between publish and exchange. */
 int32_t mcx_pt_energy_buffer(mcx_pt *pt, void **device_ptr);
 int32_t mcx_pt_publish(mcx_pt *pt);
+/* All-gather by peer stores instead of a collective call (replaces the Allgather of replica_exchange.jl:239):
+ * every rank exports a 128-byte token (CUDA IPC handles of its energy buffer and arrival counters), the host
+ * runtime hands all tokens, in rank order, to mcx_pt_attach_peers.  From then on mcx_pt_publish stores this
+ * rank's energies straight into every rank's buffer over NVLink and bumps its arrival counter there, and
+ * mcx_pt_exchange waits on the device until every rank's energies of the round have arrived (two buffers by
+ * round parity; a wait that lasts 20 s gives up and is reported by mcx_pt_peer_status). */
+int32_t mcx_pt_export(mcx_pt *pt, void *handle128);
+int32_t mcx_pt_attach_peers(mcx_pt *pt, int32_t nranks, int32_t rank, const void *handles /* [nranks][128] */);
+int32_t mcx_pt_peer_status(mcx_pt *pt, int32_t *timed_out);
 /* update!(rx, xs): all pairs of the current stage decided on the device with
  * u = EXCHANGE stream of the lower slot (replica_exchange.jl:168), labels swapped, stage toggled */
 int32_t mcx_pt_exchange(mcx_pt *pt);

@@ -22,12 +22,32 @@ __global__ void k_pt_publish(const long long *__restrict__ sums, double *__restr
     x[first_slot + c] = e;
 }
 
+// thread 0 of a block: wait until every rank has published round `value`; 20 s give up and raise *err
+__device__ __forceinline__ void pt_wait_all(const unsigned long long *arrived, int nranks, unsigned long long value, int *err)
+{
+    const volatile unsigned long long *a = arrived;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int r = 0; r < nranks; ++r)
+        while (a[r] < value) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) { *err = 1; return; }
+        }
+    __threadfence_system();
+}
+
 __global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__restrict__ betas,
-                              const double *__restrict__ x, int32_t *__restrict__ index,
+                              const double *x, int32_t *__restrict__ index,
                               int32_t *__restrict__ slot_of, long long *__restrict__ steps,
                               long long *__restrict__ accepted, int32_t *__restrict__ labels, int nlocal,
-                              int first_slot, uint32_t seed_lo, uint32_t seed_hi)
+                              int first_slot, uint32_t seed_lo, uint32_t seed_hi, const unsigned long long *arrived,
+                              int nranks, int *err)
 {
+    if (arrived) {      // energies arrive by peer stores: wait for every rank's publish of this round
+        if (threadIdx.x == 0) pt_wait_all(arrived, nranks, round + 1, err);
+        __syncthreads();
+    }
     // 0-based pair k joins ladder indices k and k+1; stage 0 takes k = 0,2,4,.. (reference first=1)
     for (int k = (stage & 1) + 2 * (blockIdx.x * blockDim.x + threadIdx.x); k < n - 1;
          k += 2 * blockDim.x * gridDim.x) {
@@ -37,7 +57,8 @@ __global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__
         const Philox4 p = stream_block(seed_lo, seed_hi, (uint32_t)ri, TAG_EXCHANGE, round, 0, 0);
         const uint64_t w = ((uint64_t)p.y << 32) | p.x;
         const double u = (double)(w >> 11) * (1.0 / 9007199254740992.0);
-        const double bi = betas[k], bj = betas[k + 1], xi = x[ri], xj = x[rj];
+        const double bi = betas[k], bj = betas[k + 1];
+        const double xi = ((const volatile double *)x)[ri], xj = ((const volatile double *)x)[rj];
         // exchange_log_ratio (:110-113) with logweight(E) = -beta*E (ensembles/boltzmann.jl:28)
         const double lr = ((-bi * xj) - (-bi * xi)) + ((-bj * xi) - (-bj * xj));
         const bool acc = (lr > 0) || (u < exp(lr));
@@ -51,12 +72,43 @@ __global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__
     }
 }
 
+// The same energies stored straight into every rank's buffer (peer memory over NVLink), then this rank's
+// arrival counter bumped on every rank: the all-gather of replica_exchange.jl:239 fused into the publish.
+__global__ void k_pt_publish_peers(const long long *__restrict__ sums, double *const *__restrict__ peer_x,
+                                   unsigned long long *const *__restrict__ peer_arrived, int nranks, int rank, int nlocal,
+                                   int first_slot, int offset, unsigned long long value, double J, double h, double D, int model)
+{
+    for (int c = threadIdx.x; c < nlocal; c += blockDim.x) {
+        const long long *s = sums + (int64_t)c * SUM_FIELDS;
+        double e = -(J * (double)s[SUM_PAIR]);
+        if (h != 0.0) e -= h * (double)s[SUM_SPIN];
+        if (model == MCX_BLUME_CAPEL) e += D * (double)s[SUM_SPIN2];
+        for (int r = 0; r < nranks; ++r) peer_x[r][offset + first_slot + c] = e;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < nranks) {
+        *(volatile unsigned long long *)(peer_arrived[threadIdx.x] + rank) = value;
+        __threadfence_system();
+    }
+}
+
 void launch_pt_publish(mcx_pt *pt)
 {
+    if (pt->peers) {
+        mcx_lattice *lat = pt->lat;
+        k_pt_publish_peers<<<1, 256, 0, lat->ctx->stream>>>(lat->d_sums, pt->d_peer_x, pt->d_peer_arrived, pt->nranks, pt->rank,
+                                                          lat->nchains, pt->first_slot, (int)(pt->round & 1) * pt->n,
+                                                          pt->round + 1, lat->J, lat->h, lat->D, lat->model);
+        lat->ctx->launches++;
+        return;
+    }
+    {
     mcx_lattice *lat = pt->lat;
     k_pt_publish<<<(lat->nchains + 127) / 128, 128, 0, lat->ctx->stream>>>(
         lat->d_sums, pt->d_x, lat->nchains, pt->first_slot, lat->J, lat->h, lat->D, lat->model);
     lat->ctx->launches++;
+    }
 }
 
 void launch_pt_exchange(mcx_pt *pt)
@@ -65,9 +117,9 @@ void launch_pt_exchange(mcx_pt *pt)
     const int npairs = (pt->n - 1 + 1) / 2;
     const int blocks = npairs > 0 ? (npairs + 127) / 128 : 1;
     k_pt_exchange<<<blocks, 128, 0, lat->ctx->stream>>>(
-        pt->n, pt->stage, pt->round, pt->d_betas, pt->d_x, pt->d_index, pt->d_slot_of, pt->d_steps,
-        pt->d_accepted, lat->d_labels, lat->nchains, pt->first_slot, (uint32_t)lat->seed,
-        (uint32_t)(lat->seed >> 32));
+        pt->n, pt->stage, pt->round, pt->d_betas, pt->d_x + (pt->peers ? (pt->round & 1) * pt->n : 0), pt->d_index, pt->d_slot_of,
+        pt->d_steps, pt->d_accepted, lat->d_labels, lat->nchains, pt->first_slot, (uint32_t)lat->seed,
+        (uint32_t)(lat->seed >> 32), pt->peers ? pt->d_arrived : nullptr, pt->nranks, pt->d_err);
     lat->ctx->launches++;
 }
 

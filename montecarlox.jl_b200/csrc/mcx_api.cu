@@ -565,7 +565,9 @@ int32_t mcx_pt_create(mcx_lattice *lat, int32_t n_global, int32_t first_slot, co
     const size_t n = (size_t)n_global;
     cudaError_t e;
     if ((e = cudaMalloc((void **)&pt->d_betas, n * sizeof(double))) != cudaSuccess ||
-        (e = cudaMalloc((void **)&pt->d_x, n * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_x, 2 * n * sizeof(double))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_arrived, kMaxPtRanks * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc((void **)&pt->d_err, sizeof(int))) != cudaSuccess ||
         (e = cudaMalloc((void **)&pt->d_index, n * sizeof(int32_t))) != cudaSuccess ||
         (e = cudaMalloc((void **)&pt->d_slot_of, n * sizeof(int32_t))) != cudaSuccess ||
         (e = cudaMalloc((void **)&pt->d_steps, n * sizeof(long long))) != cudaSuccess ||
@@ -574,7 +576,9 @@ int32_t mcx_pt_create(mcx_lattice *lat, int32_t n_global, int32_t first_slot, co
         return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     CUDA_TRY(cudaMemcpy(pt->d_betas, betas, n * sizeof(double), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemset(pt->d_x, 0, n * sizeof(double)));
+    CUDA_TRY(cudaMemset(pt->d_x, 0, 2 * n * sizeof(double)));
+    CUDA_TRY(cudaMemset(pt->d_arrived, 0, kMaxPtRanks * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(pt->d_err, 0, sizeof(int)));
     lat->first_chain = (uint32_t)first_slot;
     lat->track_sums = true;
     *out = pt;
@@ -586,8 +590,11 @@ int32_t mcx_pt_destroy(mcx_pt *pt)
     if (!pt) return MCX_OK;
     cudaSetDevice(pt->lat->ctx->device);
     cudaStreamSynchronize(pt->lat->ctx->stream);
+    for (void *p : pt->ipc_opened)
+        if (p) cudaIpcCloseMemHandle(p);
     cudaFree(pt->d_betas); cudaFree(pt->d_x); cudaFree(pt->d_index); cudaFree(pt->d_slot_of);
-    cudaFree(pt->d_steps); cudaFree(pt->d_accepted);
+    cudaFree(pt->d_steps); cudaFree(pt->d_accepted); cudaFree(pt->d_arrived); cudaFree(pt->d_err);
+    cudaFree(pt->d_peer_x); cudaFree(pt->d_peer_arrived);
     delete pt;
     return MCX_OK;
 }
@@ -632,6 +639,8 @@ int32_t mcx_pt_set_state(mcx_pt *pt, const int64_t *indices, const int64_t *step
     CUDA_TRY(cudaMemcpy(lat->d_labels, idx.data() + pt->first_slot, sizeof(int32_t) * lat->nchains, cudaMemcpyHostToDevice));
     if (steps) CUDA_TRY(cudaMemcpy(pt->d_steps, steps, sizeof(long long) * (pt->n - 1), cudaMemcpyHostToDevice));
     if (accepted) CUDA_TRY(cudaMemcpy(pt->d_accepted, accepted, sizeof(long long) * (pt->n - 1), cudaMemcpyHostToDevice));
+    // arrival counters of the peer-store all-gather count rounds: start over (all ranks restore, then barrier)
+    CUDA_TRY(cudaMemset(pt->d_arrived, 0, kMaxPtRanks * sizeof(unsigned long long)));
     pt->stage = (int)stage;
     pt->round = (uint64_t)round;
     return MCX_OK;
@@ -641,6 +650,55 @@ int32_t mcx_pt_energy_buffer(mcx_pt *pt, void **device_ptr)
 {
     REQUIRE(pt && device_ptr, MCX_ERR_ARGUMENT, "NULL argument");
     *device_ptr = pt->d_x;
+    return MCX_OK;
+}
+
+// all-gather by peer stores: a 128-byte token (CUDA IPC handles of the energy buffer and the arrival counters) ...
+int32_t mcx_pt_export(mcx_pt *pt, void *handle128)
+{
+    REQUIRE(pt && handle128, MCX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
+    cudaIpcMemHandle_t h[2];
+    CUDA_TRY(cudaIpcGetMemHandle(&h[0], pt->d_x));
+    CUDA_TRY(cudaIpcGetMemHandle(&h[1], pt->d_arrived));
+    memcpy(handle128, h, 128);
+    return MCX_OK;
+}
+
+// ... and the tokens of all ranks, in rank order (this rank's own entry is not opened)
+int32_t mcx_pt_attach_peers(mcx_pt *pt, int32_t nranks, int32_t rank, const void *handles)
+{
+    REQUIRE(pt && handles, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(nranks >= 1 && nranks <= kMaxPtRanks && rank >= 0 && rank < nranks, MCX_ERR_ARGUMENT, "bad rank %d of %d", rank, nranks);
+    REQUIRE(!pt->peers, MCX_ERR_STATE, "peers already attached");
+    CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
+    std::vector<double *> px(nranks);
+    std::vector<unsigned long long *> pa(nranks);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) { px[r] = pt->d_x; pa[r] = pt->d_arrived; continue; }
+        cudaIpcMemHandle_t h[2];
+        memcpy(h, (const char *)handles + (size_t)r * 128, 128);
+        CUDA_TRY(cudaIpcOpenMemHandle(&pt->ipc_opened[2 * r], h[0], cudaIpcMemLazyEnablePeerAccess));
+        CUDA_TRY(cudaIpcOpenMemHandle(&pt->ipc_opened[2 * r + 1], h[1], cudaIpcMemLazyEnablePeerAccess));
+        px[r] = (double *)pt->ipc_opened[2 * r];
+        pa[r] = (unsigned long long *)pt->ipc_opened[2 * r + 1];
+    }
+    CUDA_TRY(cudaMalloc((void **)&pt->d_peer_x, sizeof(double *) * nranks));
+    CUDA_TRY(cudaMalloc((void **)&pt->d_peer_arrived, sizeof(unsigned long long *) * nranks));
+    CUDA_TRY(cudaMemcpy(pt->d_peer_x, px.data(), sizeof(double *) * nranks, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(pt->d_peer_arrived, pa.data(), sizeof(unsigned long long *) * nranks, cudaMemcpyHostToDevice));
+    pt->nranks = nranks; pt->rank = rank; pt->peers = true;
+    return MCX_OK;
+}
+
+int32_t mcx_pt_peer_status(mcx_pt *pt, int32_t *timed_out)
+{
+    REQUIRE(pt && timed_out, MCX_ERR_ARGUMENT, "NULL argument");
+    CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, pt->d_err, sizeof(int), cudaMemcpyDeviceToHost, pt->lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(pt->lat->ctx->stream));
+    *timed_out = err;
     return MCX_OK;
 }
 

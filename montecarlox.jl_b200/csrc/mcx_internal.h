@@ -57,7 +57,18 @@ struct mcx_pt {
     long long *d_steps, *d_accepted;   // [n-1]
     int stage;
     uint64_t round;
+    // all-gather by peer stores (mcx_pt_attach_peers): d_x holds two buffers of n energies (round parity);
+    // the publish kernel stores this rank's slice into every rank's buffer over NVLink and bumps its arrival
+    // counter there, the exchange kernel waits for all counters -- no collective call, no host sync
+    bool peers;
+    int nranks, rank;
+    unsigned long long *d_arrived;     // [kMaxPtRanks] rounds published by each rank (they write it)
+    double **d_peer_x;                 // [nranks] every rank's d_x (own included)
+    unsigned long long **d_peer_arrived;   // [nranks] every rank's d_arrived
+    int *d_err;
+    void *ipc_opened[2 * 64];
 };
+constexpr int kMaxPtRanks = 64;
 
 struct mcx_flat {
     mcx_lattice *lat;

@@ -8,6 +8,7 @@ per-replica energies cross NVLink (one all-gather per exchange); the swap decisi
 identically on every rank from a counter-based u, and labels move, not lattices
 (replica_exchange.jl:133)."""
 import ctypes as C
+import os
 import math
 from fractions import Fraction
 
@@ -276,6 +277,15 @@ class ReplicaExchange:
         self._pt, self._sys, self._first, self._count = h, sys, first, count
         self._betas = betas
         self._xbuf = None
+        self._peers = False
+        if isinstance(self.backend, GPUBackend) and self.backend.size > 1 and os.environ.get("MCX_PT_P2P", "1") != "0":
+            # energies travel by peer stores over NVLink (CUDA IPC), no collective call per exchange
+            buf = C.create_string_buffer(128)
+            check(lib().mcx_pt_export(h, buf))
+            tokens = b"".join(_all_gather_bytes(self.backend, buf.raw))
+            check(lib().mcx_pt_attach_peers(h, self.backend.size, self.backend.rank, tokens))
+            self._peers = True
+            self.backend.barrier()
         return self
 
     def sweep_system_(self, sys, nsweeps):
@@ -300,7 +310,7 @@ class ReplicaExchange:
         if self._pt is None:
             raise AssertionError("update_(rx) without energies needs rx.attach(sys) first")
         check(lib().mcx_pt_publish(self._pt))
-        if isinstance(self.backend, GPUBackend) and self.backend.size > 1:
+        if isinstance(self.backend, GPUBackend) and self.backend.size > 1 and not self._peers:
             self.backend.all_gather_inplace(self._x_tensor(), self._first, self._count)
         check(lib().mcx_pt_exchange(self._pt))
         self._dirty = True
@@ -322,7 +332,25 @@ class ReplicaExchange:
     def energies(self):
         """per-slot energies as last published (all ranks)."""
         self._sys.sync()
+        if self._peers:        # two buffers by round parity; the last published round is round - 1
+            import torch
+            p = C.c_void_p()
+            check(lib().mcx_pt_energy_buffer(self._pt, C.byref(p)))
+            both = _as_torch(p.value, 2 * self.size, torch.float64, self._sys.ctx.device)
+            self._pull_round()
+            off = ((self.round - 1) & 1) * self.size
+            return both[off:off + self.size].cpu().numpy().copy()
         return self._x_tensor().cpu().numpy().copy()
+
+    def _pull_round(self):
+        st, rd = C.c_int64(), C.c_int64()
+        check(lib().mcx_pt_state(self._pt, None, None, None, C.byref(st), C.byref(rd)))
+        self.stage, self.round = st.value, rd.value
+
+    def peer_status(self):
+        t = C.c_int32()
+        check(lib().mcx_pt_peer_status(self._pt, C.byref(t)))
+        return t.value
 
     def close(self):
         h, self._pt = self._pt, None
@@ -393,6 +421,18 @@ def update_(obj, *args, **kwargs):
 # slab decomposition: one lattice over several GPUs (beyond the reference, whose
 # IsingLatticeOptim (SpinSystems/src/ising.jl:430-461) is one Vector{Int8} in one address space)
 # ---------------------------------------------------------------------------------------------------
+def _all_gather_bytes(backend, raw):
+    """equal-length byte strings of all ranks, in rank order (handle exchange; NCCL or gloo)"""
+    import torch
+    dist = backend._dist
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(backend.group) == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+    out = torch.empty(backend.size * len(raw), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=backend.group)
+    flat = out.cpu().numpy().tobytes()
+    return [flat[i * len(raw):(i + 1) * len(raw)] for i in range(backend.size)]
+
+
 class SlabIsing:
     """A 2-D Ising lattice `dims = [Lx, Ly]` (J = 1, h = 0) split by rows into equal slabs.
 
@@ -432,14 +472,7 @@ class SlabIsing:
                 check(lib().mcx_slab_attach_local(p.h_lat, self.parts[(k - 1) % n].h_lat, self.parts[(k + 1) % n].h_lat))
 
     def _all_gather_bytes(self, raw):
-        import torch
-        dist = self.backend._dist
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(self.backend.group) == "nccl" else torch.device("cpu")
-        mine = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-        out = torch.empty(self.backend.size * len(raw), dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(out, mine, group=self.backend.group)
-        flat = out.cpu().numpy().tobytes()
-        return [flat[i * len(raw):(i + 1) * len(raw)] for i in range(self.backend.size)]
+        return _all_gather_bytes(self.backend, raw)
 
     def _sync_all(self):
         for p in self.parts:

@@ -121,3 +121,63 @@ def test_ipc_slabs_across_processes(m, world, bands, tmp_path):
     res = json.loads(line)
     assert res["ok"], res
     assert all(t == 0 for t, _ in res["status"]), res
+
+
+_PT_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+ngpu = torch.cuda.device_count()
+torch.cuda.set_device(rank %% ngpu)
+dist.init_process_group("gloo", rank=rank, world_size=world)
+import mcx_b200 as m
+ctx = m.Context(rank %% ngpu)
+L, n, rounds, seed = 64, 12, 16, 2025
+betas = m.set_betas(n, 0.3, 0.6, "uniform")
+
+def run(backend, every):
+    pt = m.ParallelTempering(betas, seed=seed, backend=backend)
+    first, count = backend.slots(n)
+    reps = m.Ising([L, L], nchains=count, ctx=ctx)
+    pt.attach(reps)
+    reps.init_("random", rng=m.PhiloxRNG(seed, first))
+    for _ in range(rounds):
+        m.sweep_(reps, pt, every)
+        m.update_(pt)
+    out = (list(map(int, pt.index())), list(map(int, pt.steps)), list(map(int, pt.accepted)), [float(e) for e in pt.energies()])
+    return out, pt
+
+res = {}
+for every in (1, 3):
+    (idx, steps, acc, en), pt = run(m.GPUBackend(), every)
+    assert pt._peers, "peer-store all-gather not attached"
+    assert pt.peer_status() == 0
+    dist.barrier()
+    if rank == 0:
+        class One(m.GPUBackend):        # the same ladder on one rank, no collective at all
+            rank = property(lambda self: 0); size = property(lambda self: 1)
+            def slots(self, n_global): return 0, n_global
+            def barrier(self): pass
+        (idx1, steps1, acc1, en1), _ = run(One(), every)
+        res[every] = bool(idx == idx1 and steps == steps1 and acc == acc1 and en == en1 and sum(acc) > 0)
+    dist.barrier()
+if rank == 0:
+    print(json.dumps({"ok": all(res.values()), "res": {str(k): v for k, v in res.items()}}))
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pt_peer_store_allgather_across_processes(m, world, tmp_path):
+    """parallel tempering over several processes with the energies exchanged by peer stores (CUDA IPC) and
+    device-side arrival counters instead of a collective: ladder state and energies equal the one-rank run"""
+    script = tmp_path / "pt_worker.py"
+    script.write_text(_PT_WORKER % {"root": ROOT})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29650 + world), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["ok"], res
