@@ -387,7 +387,9 @@ def bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, L=1024, n=256
     return {"metric": "pt_sweeps_per_s", "value": sweeps / (ms * 1e-3), "unit": "PT sweeps/s (all %d replicas swept once)" % n,
             "attempts_per_ns": sweeps * n * L * L / (ms * 1e6), "L": L, "replicas": n, "exchange_every": every,
             "rounds": rounds, "scaling": "strong", "exchange_acceptance": pt.acceptance_rate(),
-            "collective": "none (1 rank)" if world == 1 else "NCCL all-gather of %d doubles per exchange" % n}
+            "collective": "none (1 rank)" if world == 1 else
+                          ("peer stores of %d doubles per exchange over NVLink (CUDA IPC), device-side arrival counters, no collective call" % n
+                           if getattr(pt, "_peers", False) else "NCCL all-gather of %d doubles per exchange" % n)}
 
 
 if __name__ == "__main__":
