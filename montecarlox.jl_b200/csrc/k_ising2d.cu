@@ -769,15 +769,17 @@ static bool aux_streams(mcx_ctx *ctx)
 
 bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (!lat->fast2d || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
-    const bool bc = lat->model == MCX_BLUME_CAPEL;
-    if (bc && (lat->rule == MCX_HEATBATH || env_int("MCX_BC2D", 1) == 0)) return false;      // k_bc2d's own conditions
+    if (lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
+    // which vectorised half-sweep serves this lattice (each launcher re-checks its own conditions)
+    const bool d3 = lat->ndim == 3 && lat->model == MCX_ISING && lat->view.Lx % 32 == 0 && env_int("MCX_ISING3D", 1) != 0;
+    const bool bc = lat->fast2d && lat->model == MCX_BLUME_CAPEL;
+    if (!d3 && !lat->fast2d) return false;
+    if (bc && (lat->rule == MCX_HEATBATH || env_int("MCX_BC2D", 1) == 0)) return false;
     if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
-    // worth it only while a launch is a few items per resident CTA (its tail is then a third of its span)
     const int groups_env = env_int("MCX_GROUPS", -1);
     if (groups_env == 0 || groups_env == 1) return false;
-    const int R = auto_rows_per_strip(lat);
-    const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
+    const int R = d3 ? 16 : auto_rows_per_strip(lat);
+    const int64_t G = (int64_t)((lat->view.Ly + R - 1) / R) * (d3 ? lat->view.Lz : 1) * (lat->view.half >> 4);
     if (G < 96) return false;                                          // rows-of-8 territory
     const int64_t items = (G + kThreads - 1) / kThreads * lat->nchains;
     const int64_t ctas = (int64_t)lat->ctx->sm_count * 6;
@@ -798,7 +800,8 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
                 const int c0 = (int)((int64_t)lat->nchains * g / groups), c1 = (int)((int64_t)lat->nchains * (g + 1) / groups);
                 g_launch_range.chain0 = c0; g_launch_range.nchains = c1 - c0; g_launch_range.stream = ctx->aux[g]; g_launch_range.use_stream = true;
                 const uint64_t t = 2 * (lat->sweep + (uint64_t)s) + (uint64_t)colour;
-                if (bc) launch_sweep_bc2d(lat, colour, t);
+                if (d3) launch_sweep_ising3d(lat, colour, t);
+                else if (bc) launch_sweep_bc2d(lat, colour, t);
                 else if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
             }
     g_launch_range = LaunchRange();

@@ -115,6 +115,9 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps);
 // k_bc2d.cu: vectorised 2-D Blume-Capel half-sweep (Metropolis / Glauber, Lx % 32 == 0)
 bool launch_sweep_bc2d(mcx_lattice *lat, int colour, uint64_t t);       // false: not applicable, nothing launched
 
+// k_ising3d.cu: vectorised 3-D Ising half-sweep (Lx % 32 == 0)
+bool launch_sweep_ising3d(mcx_lattice *lat, int colour, uint64_t t);    // false: not applicable, nothing launched
+
 // k_slab.cu
 int32_t slab_half_sweep(mcx_lattice *lat);
 void slab_free(mcx_lattice *lat);

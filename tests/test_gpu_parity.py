@@ -157,6 +157,33 @@ def test_ising3d_bit_exact(m, oracle, rule, dims):
     _check(sys_, s_or, a_or, alg, 10)
 
 
+@pytest.mark.parametrize("dims", [[32, 8, 4], [64, 16, 6], [32, 32, 8], [128, 4, 4], [64, 12, 10]])
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_ising3d_vectorised_kernel(m, oracle, dims, rule):
+    """k_ising3d (z-neighbour rows, run-time row parity) against the oracle and the rows-of-8 kernel"""
+    for beta, seed, tracking in ((0.2216, 2024, True), (0.35, 5, False), (0.1, 99, True)):
+        nsweeps = 6
+        outs = []
+        for env in ({}, {"MCX_ISING3D": "0"}):
+            os.environ.pop("MCX_ISING3D", None)
+            os.environ.update(env)
+            sys_ = m.Ising(dims, nchains=2)
+            sys_.set_tracking(tracking)
+            alg = _make_alg(m, rule, beta, seed, 1)
+            sys_.init_("random", rng=alg.rng)
+            l0 = sys_.ctx.launch_count()
+            m.sweep_(sys_, alg, nsweeps)
+            outs.append((sys_.spins.copy(), list(sys_.pair_sum()), list(sys_.magnetization()), list(sys_.accepted())))
+        os.environ.pop("MCX_ISING3D", None)
+        assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]
+        for c in range(2):
+            s_or, a_or = _oracle_run(oracle, oracle.ISING, dims, rule, beta, 1, 0, 0, seed, 1 + c, nsweeps)
+            assert np.array_equal(outs[0][0][c], s_or.spins)
+            assert outs[0][1][c] == s_or.pair_count() and outs[0][2][c] == s_or.magnetization(full=True)
+            if rule != 2:
+                assert outs[0][3][c] == a_or.accepted
+
+
 @pytest.mark.parametrize("dims", [[64, 64], [256, 64], [32, 128], [512, 256]])
 @pytest.mark.parametrize("rule", [0, 1])
 def test_blume_capel_vectorised_kernel(m, oracle, dims, rule):
