@@ -369,17 +369,13 @@ def bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, L=1024, n=256
     pt.attach(reps)
     reps.init_("random", rng=m.PhiloxRNG(42, first))
 
-    def pt_round():
-        m.sweep_(reps, pt, every)
-        m.update_(pt)
-
-    for _ in range(3 if every > 1 else 20):
-        pt_round()
+    # rounds x (`every` sweeps of all replicas, then update!(pt)): the loop of pt_Ising2D.jl:52-57, queued by
+    # ParallelTempering.run_ (one library call when the energies reach all ranks without the host)
+    pt.run_(reps, 3 if every > 1 else 20, every)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(rounds):
-        pt_round()
+    pt.run_(reps, rounds, every)
     e1.record(stream)
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))

@@ -195,6 +195,9 @@ int32_t mcx_pt_peer_status(mcx_pt *pt, int32_t *timed_out);
 /* update!(rx, xs): all pairs of the current stage decided on the device with
  * u = EXCHANGE stream of the lower slot (replica_exchange.jl:168), labels swapped, stage toggled */
 int32_t mcx_pt_exchange(mcx_pt *pt);
+/* the user loop of pt_Ising2D.jl:52-57 (sweeps, update!(pt) every `interval` sweeps) queued in one call:
+ * nrounds x (sweeps_per_round sweeps, publish, exchange); one rank or attached peers, else MCX_ERR_UNSUPPORTED */
+int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round);
 int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices /*[n] 1-based*/, int64_t *steps /*[n-1]*/,
                      int64_t *accepted /*[n-1]*/, int64_t *stage, int64_t *round);
 int32_t mcx_pt_reset(mcx_pt *pt);

@@ -62,6 +62,7 @@ SIGNATURES = {
     "mcx_reset_counters": (_i32, [_vp]),
     "mcx_recompute": (_i32, [_vp]),
     "mcx_set_tracking": (_i32, [_vp, _i32]),
+    "mcx_pt_run": (_i32, [_vp, _i64, _i64]),
     "mcx_pt_export": (_i32, [_vp, _vp]),
     "mcx_pt_attach_peers": (_i32, [_vp, _i32, _i32, _vp]),
     "mcx_pt_peer_status": (_i32, [_vp, _P(_i32)]),

@@ -272,11 +272,6 @@ k_bc2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict
     }
 }
 
-int bc_env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 template <int COLOUR, bool TRACK>
 void launch_bc(mcx_lattice *lat, uint64_t t)
@@ -321,7 +316,7 @@ void launch_bc(mcx_lattice *lat, uint64_t t)
 bool launch_sweep_bc2d(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (!lat->fast2d || lat->model != MCX_BLUME_CAPEL || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
-    if (lat->rule == MCX_HEATBATH || lat->table_len != kBcTable || bc_env_int("MCX_BC2D", 1) == 0) return false;
+    if (lat->rule == MCX_HEATBATH || lat->table_len != kBcTable || knobs().bc2d == 0) return false;
     if ((int64_t)(lat->view.Ly / 2) * (lat->view.half >> 4) < 96) return false;       // tiny lattices: rows-of-8 kernel
     const bool track = lat->track_sums;
     if (colour == 0) { if (track) launch_bc<0, true>(lat, t); else launch_bc<0, false>(lat, t); }

@@ -548,11 +548,6 @@ k_init2d(LatView L, int mode, uint32_t seed_lo, uint32_t seed_hi, uint32_t first
     }
 }
 
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 int pick_rows_per_strip(int Ly, int want);
 
@@ -560,7 +555,7 @@ int pick_rows_per_strip(int Ly, int want);
 // lattices, replicas sharded over many GPUs); then shorter strips keep the persistent grid balanced.
 int auto_rows_per_strip(const mcx_lattice *lat)
 {
-    const int forced = env_int("MCX_ROWS_PER_STRIP", 0);
+    const int forced = knobs().rows_per_strip > 0 ? knobs().rows_per_strip : 0;
     if (forced > 0) return pick_rows_per_strip(lat->view.Ly, forced);
     const int64_t nseg = lat->view.half >> 4;
     const int64_t ctas = (int64_t)lat->ctx->sm_count * 6;
@@ -623,7 +618,7 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     // and with the halo rows taken from the neighbour slabs (k_slab.cu)
     constexpr bool kHasFull = MINB == 6 && !PREFETCH;
     const bool slab = kHasFull && (lat->slab != nullptr || band);
-    const bool full = kHasFull && G % kThreads == 0 && env_int("MCX_FULL", 1) != 0;
+    const bool full = kHasFull && G % kThreads == 0 && knobs().full != 0;
     auto kern = slab ? (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, kHasFull>
                              : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, kHasFull>)
                      : (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, false>
@@ -633,7 +628,7 @@ void launch_v(mcx_lattice *lat, uint64_t t)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>, kThreads, 0);
         if (resident < 1) resident = 1;
     }
-    const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
+    const int ctas_per_sm = knobs().ctas_per_sm >= 0 ? knobs().ctas_per_sm : resident;
     // persistent grid: every SM gets its full complement of CTAs (trimming the grid so that all CTAs
     // run the same number of items was measured 8 % slower: SMs with fewer CTAs do not finish sooner)
     int grid = lat->ctx->sm_count * ctas_per_sm;
@@ -661,7 +656,7 @@ void launch_ring(mcx_lattice *lat, uint64_t t)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 0);
         if (resident < 1) resident = 1;
     }
-    const int ctas_per_sm = env_int("MCX_CTAS_PER_SM", resident);
+    const int ctas_per_sm = knobs().ctas_per_sm >= 0 ? knobs().ctas_per_sm : resident;
     // persistent grid: every SM gets its full complement of CTAs (trimming the grid so that all CTAs
     // run the same number of items was measured 8 % slower: SMs with fewer CTAs do not finish sooner)
     int grid = lat->ctx->sm_count * ctas_per_sm;
@@ -678,7 +673,7 @@ void launch_ring(mcx_lattice *lat, uint64_t t)
 template <int COLOUR, bool HEATBATH, bool TRACK>
 void launch_t(mcx_lattice *lat, uint64_t t)
 {
-    const int variant = lat->slab ? 3 : env_int("MCX_VARIANT", 3);
+    const int variant = lat->slab || knobs().variant < 0 ? 3 : knobs().variant;
     switch (variant) {
     case 0: launch_v<COLOUR, HEATBATH, TRACK, 5, true>(lat, t); break;
     case 6: launch_ring<COLOUR, HEATBATH, TRACK, 6, 3>(lat, t); break;
@@ -771,12 +766,12 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 {
     if (lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
     // which vectorised half-sweep serves this lattice (each launcher re-checks its own conditions)
-    const bool d3 = lat->ndim == 3 && lat->model == MCX_ISING && lat->view.Lx % 32 == 0 && env_int("MCX_ISING3D", 1) != 0;
+    const bool d3 = lat->ndim == 3 && lat->model == MCX_ISING && lat->view.Lx % 32 == 0 && knobs().ising3d != 0;
     const bool bc = lat->fast2d && lat->model == MCX_BLUME_CAPEL;
     if (!d3 && !lat->fast2d) return false;
-    if (bc && (lat->rule == MCX_HEATBATH || env_int("MCX_BC2D", 1) == 0)) return false;
-    if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
-    const int groups_env = env_int("MCX_GROUPS", -1);
+    if (bc && (lat->rule == MCX_HEATBATH || knobs().bc2d == 0)) return false;
+    if (knobs().variant >= 0 || knobs().rows_per_strip >= 0) return false;
+    const int groups_env = knobs().groups;
     if (groups_env == 0 || groups_env == 1) return false;
     const int R = d3 ? 16 : auto_rows_per_strip(lat);
     const int64_t G = (int64_t)((lat->view.Ly + R - 1) / R) * (d3 ? lat->view.Lz : 1) * (lat->view.half >> 4);
@@ -816,8 +811,8 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
 {
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->nchains != 1) return false;
     if (lat->slab && !(lat->slab->attached && lat->slab->remote)) return false;      // in-process slabs advance in lockstep
-    if (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP")) return false;
-    const int bands_env = env_int("MCX_BANDS", -1);
+    if (knobs().variant >= 0 || knobs().rows_per_strip >= 0) return false;
+    const int bands_env = knobs().bands;
     if (bands_env == 0 || bands_env == 1) return false;
     // 8 bands (the hardware queues a process gets by default) of 16-row strips, each at least ~100 CTA items:
     // measured +8 % at L = 8192, +17 % at 16384, +10 % at 32768; 2 bands gain nothing (each waits for the other),
@@ -864,9 +859,9 @@ bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
     // small lattices: a chain yields fewer than one CTA of 16-byte segments x strips, so most lanes of
     // this kernel would idle; the rows-of-8 kernel (8 sites per thread) fills the machine instead
     {
-        const int R = pick_rows_per_strip(lat->view.Ly, env_int("MCX_ROWS_PER_STRIP", 16));   // small-lattice test uses 16
+        const int R = pick_rows_per_strip(lat->view.Ly, knobs().rows_per_strip >= 0 ? knobs().rows_per_strip : 16);   // small-lattice test uses 16
         const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
-        if (G < 96 && !lat->slab && getenv("MCX_VARIANT") == nullptr && getenv("MCX_ROWS_PER_STRIP") == nullptr) return false;
+        if (G < 96 && !lat->slab && knobs().variant < 0 && knobs().rows_per_strip < 0) return false;
     }
     if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
     return true;

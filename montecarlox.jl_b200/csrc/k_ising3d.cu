@@ -244,11 +244,6 @@ k_ising3d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
     }
 }
 
-int env3_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 template <int COLOUR, bool HEATBATH, bool TRACK>
 void launch_3d(mcx_lattice *lat, uint64_t t)
@@ -293,7 +288,7 @@ void launch_3d(mcx_lattice *lat, uint64_t t)
 bool launch_sweep_ising3d(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (lat->ndim != 3 || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->view.Lx % 32 != 0) return false;
-    if (lat->view.Ly % 2 != 0 || lat->table_len != k3Table || env3_int("MCX_ISING3D", 1) == 0) return false;
+    if (lat->view.Ly % 2 != 0 || lat->table_len != k3Table || knobs().ising3d == 0) return false;
     if ((int64_t)(lat->view.Ly / 2) * lat->view.Lz * (lat->view.half >> 4) < 96) return false;     // tiny: rows-of-8 kernel
     const bool track = lat->track_sums, hb = lat->rule == MCX_HEATBATH;
     if (colour == 0) {

@@ -25,11 +25,6 @@ namespace {
 constexpr int kResMinWork = 256;                        // thread-rows a CTA must have per half-sweep to be worth it
 constexpr int64_t kResMaxSweepsPerLaunch = 1 << 14;     // keeps the per-thread int32 accumulators far from overflow
 
-int res_env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
 
 __device__ __forceinline__ uint4 lds128(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
@@ -221,7 +216,7 @@ bool plan_and_launch(mcx_lattice *lat, int64_t nsweeps, bool dry_run)
     // candidates: cluster sizes whose row share is even, fits shared memory and gives a CTA enough work;
     // take the smallest, then widen while the batch cannot fill the SMs
     ResidentPlan plan{0, 0, 0, 0, 0};
-    const int forced = res_env_int("MCX_RESIDENT_CLUSTER", 0);
+    const int forced = knobs().resident_cluster > 0 ? knobs().resident_cluster : 0;
     for (int c = 1; c <= 8; c *= 2) {
         if (L.Ly % (2 * c) != 0) break;
         const int rows = L.Ly / c;
@@ -241,7 +236,7 @@ bool plan_and_launch(mcx_lattice *lat, int64_t nsweeps, bool dry_run)
     plan.R = 2;
     for (int r = 16; r >= 2; r -= 2)
         if (plan.rows_cta % r == 0 && ((plan.rows_cta / r) * nseg) % NT == 0) { plan.R = r; break; }
-    if (const int fr = res_env_int("MCX_RESIDENT_ROWS", 0)) if (fr % 2 == 0 && plan.rows_cta % fr == 0) plan.R = fr;
+    if (const int fr = knobs().resident_rows > 0 ? knobs().resident_rows : 0) if (fr % 2 == 0 && plan.rows_cta % fr == 0) plan.R = fr;
 
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
@@ -263,7 +258,7 @@ bool plan_and_launch(mcx_lattice *lat, int64_t nsweeps, bool dry_run)
     plan.nclusters = lat->nchains < max_clusters ? lat->nchains : max_clusters;
     // 8-CTA clusters (lattices near 1 MiB) leave SMs idle (14 such clusters fit a B200) and run the batch in
     // waves: measured slower than the streaming kernel unless the batch is one partial wave of >= 2 lattices
-    if (!forced && res_env_int("MCX_RESIDENT", -1) != 1 && plan.csize == 8 &&
+    if (!forced && knobs().resident != 1 && plan.csize == 8 &&
         (lat->nchains < 2 || lat->nchains > max_clusters))
         return false;
     if (dry_run) return true;
@@ -292,10 +287,10 @@ bool launch_sweeps_resident(mcx_lattice *lat, int64_t nsweeps)
 {
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
     if (nsweeps < 1 || nsweeps > kResMaxSweepsPerLaunch) return false;
-    const int mode = res_env_int("MCX_RESIDENT", -1);
+    const int mode = knobs().resident;
     if (mode == 0) return false;
     // the tuning hooks of the streaming kernel select that kernel
-    if (mode != 1 && (getenv("MCX_VARIANT") || getenv("MCX_ROWS_PER_STRIP") || getenv("MCX_FULL"))) return false;
+    if (mode != 1 && (knobs().variant >= 0 || knobs().rows_per_strip >= 0 || knobs().full >= 0)) return false;
     if (mode != 1) {
         const int64_t kResidentMaxSites = (int64_t)32 << 20;
         if (nsweeps < 2 || (int64_t)lat->nchains * lat->N > kResidentMaxSites) return false;
@@ -304,7 +299,7 @@ bool launch_sweeps_resident(mcx_lattice *lat, int64_t nsweeps)
     // CTA width: enough threads for the thread-rows one CTA can have in flight (16-byte segments x row pairs
     // of the smallest cluster share), so that tiny lattices run many narrow CTAs per SM instead of one wide one
     int64_t work = (int64_t)(lat->view.Ly / 2) * (lat->view.half >> 4);
-    const int nt = res_env_int("MCX_RESIDENT_THREADS", work <= 128 ? 128 : work <= 256 ? 256 : 512);
+    const int nt = knobs().resident_threads > 0 ? knobs().resident_threads : (work <= 128 ? 128 : work <= 256 ? 256 : 512);
 #define MCX_RES_DISPATCH(NT)                                                                                     \
     (heatbath ? (track ? plan_and_launch<true, true, NT>(lat, nsweeps, false) : plan_and_launch<true, false, NT>(lat, nsweeps, false)) \
               : (track ? plan_and_launch<false, true, NT>(lat, nsweeps, false) : plan_and_launch<false, false, NT>(lat, nsweeps, false)))

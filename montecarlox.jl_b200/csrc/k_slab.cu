@@ -150,6 +150,7 @@ int32_t mcx_slab_half_sweep(mcx_lattice *lat)
     SREQ(lat && lat->slab && lat->slab->attached, MCX_ERR_STATE, "needs an attached slab");
     SREQ(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
     SCUDA(cudaSetDevice(lat->ctx->device));
+    knobs_refresh();
     const int32_t st = slab_half_sweep(lat);
     if (st != MCX_OK) return mcx_set_error(st, "slab half-sweep could not be launched");
     SCUDA(cudaGetLastError());

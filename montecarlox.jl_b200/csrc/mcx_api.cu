@@ -45,6 +45,33 @@ static int32_t check_launch(mcx_ctx *ctx)
     return MCX_OK;
 }
 
+// ------------------------------------------------------------------------------------ knobs
+namespace mcx {
+static thread_local Knobs g_knobs;
+static thread_local bool g_knobs_ready = false;
+static int knob(const char *name)
+{
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : -1;
+}
+void knobs_refresh()
+{
+    Knobs &k = g_knobs;
+    k.rows_per_strip = knob("MCX_ROWS_PER_STRIP"); k.ctas_per_sm = knob("MCX_CTAS_PER_SM"); k.variant = knob("MCX_VARIANT");
+    k.full = knob("MCX_FULL"); k.groups = knob("MCX_GROUPS"); k.bands = knob("MCX_BANDS"); k.bc2d = knob("MCX_BC2D");
+    k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
+    k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
+    k.force_generic = knob("MCX_FORCE_GENERIC");
+    g_knobs_ready = true;
+}
+const Knobs &knobs()
+{
+    if (!g_knobs_ready) knobs_refresh();
+    return g_knobs;
+}
+}  // namespace mcx
+
+
 extern "C" {
 
 int32_t mcx_abi_version(void) { return MCX_ABI_VERSION; }
@@ -377,6 +404,7 @@ int32_t mcx_set_tracking(mcx_lattice *lat, int32_t on)
 // ------------------------------------------------------------------------------------ sweep
 int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
 {
+    knobs_refresh();
     REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
     REQUIRE(nsweeps >= 0, MCX_ERR_ARGUMENT, "nsweeps must be >= 0");
     REQUIRE(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
@@ -402,8 +430,7 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
         return check_launch(lat->ctx);
     }
     // test hooks: MCX_FORCE_GENERIC=1 -> shape-generic kernel, =2 -> rows-of-8 kernel
-    const char *fg = getenv("MCX_FORCE_GENERIC");
-    const int force = fg ? atoi(fg) : 0;
+    const int force = knobs().force_generic > 0 ? knobs().force_generic : 0;
     bool try_series = force == 0;        // whole-series launchers (resident kernel, chain groups) still worth asking
     for (int64_t s = 0; s < nsweeps;) {
         if (try_series) {
@@ -721,6 +748,27 @@ int32_t mcx_pt_exchange(mcx_pt *pt)
     pt->stage = 1 - pt->stage;
     pt->round += 1;
     return check_launch(pt->lat->ctx);
+}
+
+// The user loop of pt_Ising2D.jl:52-57 -- `for i in 1:n; sweep; i % interval == 0 && update!(pt); end` -- queued
+// in one call: nrounds x (sweeps_per_round sweeps, publish, exchange).  Needs the energies to reach all ranks
+// without the host (one rank, or peer stores attached); otherwise MCX_ERR_UNSUPPORTED and the caller loops.
+int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round)
+{
+    REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    REQUIRE(nrounds >= 0 && sweeps_per_round >= 1, MCX_ERR_ARGUMENT, "need nrounds >= 0 and sweeps_per_round >= 1");
+    mcx_lattice *lat = pt->lat;
+    REQUIRE(pt->peers || lat->nchains == pt->n, MCX_ERR_UNSUPPORTED,
+            "replicas on other ranks: attach peers (mcx_pt_attach_peers) or drive publish / all-gather / exchange from the host");
+    // exchanging every sweep or two: keep the energy sums current per flip; longer intervals: recompute on publish
+    lat->track_sums = sweeps_per_round < 3;
+    for (int64_t r = 0; r < nrounds; ++r) {
+        int32_t st = mcx_sweep(lat, sweeps_per_round);
+        if (st == MCX_OK) st = mcx_pt_publish(pt);
+        if (st == MCX_OK) st = mcx_pt_exchange(pt);
+        if (st != MCX_OK) return st;
+    }
+    return MCX_OK;
 }
 
 int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices, int64_t *steps, int64_t *accepted, int64_t *stage, int64_t *round)

@@ -86,6 +86,15 @@ struct mcx_flat {
 
 namespace mcx {
 
+// Tuning and test hooks (MCX_* environment variables), read once per public sweep call -- not per launch;
+// -1: variable not set.
+struct Knobs {
+    int rows_per_strip, ctas_per_sm, variant, full, groups, bands, bc2d, ising3d;
+    int resident, resident_cluster, resident_rows, resident_threads, force_generic;
+};
+const Knobs &knobs();
+void knobs_refresh();
+
 // chain sub-range, row band and stream of the launch being issued by the series launchers (k_ising2d.cu);
 // default: the whole batch on the context's stream.  Read by the half-sweep launchers of k_ising2d.cu / k_bc2d.cu.
 struct LaunchRange {

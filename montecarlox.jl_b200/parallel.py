@@ -298,6 +298,24 @@ class ReplicaExchange:
         for a in self.replica.algs[self._first:self._first + self._count]:
             a.steps += int(nsweeps) * sys.N
 
+    def run_(self, sys, nrounds, sweeps_per_round=1):
+        """`nrounds` x (`sweeps_per_round` sweeps of every replica, then update_) -- the loop of
+        pt_Ising2D.jl:52-57 -- queued by the library in one call when the energies reach all ranks without
+        the host (one rank, or peer stores); otherwise the same loop from here."""
+        if self._pt is None or sys is not self._sys:
+            self.attach(sys)
+        nrounds, k = int(nrounds), int(sweeps_per_round)
+        if self._peers or not (isinstance(self.backend, GPUBackend) and self.backend.size > 1):
+            check(lib().mcx_pt_run(self._pt, nrounds, k))
+            for a in self.replica.algs[self._first:self._first + self._count]:
+                a.steps += nrounds * k * sys.N
+            self._dirty = True
+            return None
+        for _ in range(nrounds):
+            self.sweep_system_(sys, k)
+            self._update_device()
+        return None
+
     def _x_tensor(self):
         if self._xbuf is None:
             import torch

@@ -40,15 +40,21 @@ def main():
                 pt_round()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
+            import time
             e0.record(stream)
-            for _ in range(args.rounds):
-                pt_round()
+            h0 = time.perf_counter()
+            if os.environ.get("PT_LOOP", "run") == "run":
+                pt.run_(reps, args.rounds, args.every)
+            else:
+                for _ in range(args.rounds):
+                    pt_round()
+            host_us = (time.perf_counter() - h0) * 1e6 / (args.rounds * args.every)    # host time to ENQUEUE a sweep
             e1.record(stream)
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             sweeps = args.rounds * args.every
             print(json.dumps({"replicas_on_rank": count, "L": args.L, "every": args.every,
-                              "rank_sweeps_per_s": sweeps / (ms * 1e-3), "us_per_sweep": ms * 1e3 / sweeps,
+                              "rank_sweeps_per_s": sweeps / (ms * 1e-3), "us_per_sweep": ms * 1e3 / sweeps, "host_enqueue_us_per_sweep": round(host_us, 2),
                               "attempts_per_ns": sweeps * count * args.L * args.L / (ms * 1e6),
                               "rows_per_strip": os.environ.get("MCX_ROWS_PER_STRIP", "auto")}), flush=True)
             pt.close() if hasattr(pt, "close") else None

@@ -330,6 +330,32 @@ def test_parallel_tempering_matches_oracle(m, oracle):
     assert np.allclose(pt.energies(), [s.energy() for s in o_sys])
 
 
+def test_pt_run_equals_user_loop(m):
+    """ParallelTempering.run_ (one library call for rounds x (sweeps, update!)) == the explicit loop"""
+    L, n, seed = 64, 10, 77
+    betas = m.set_betas(n, 0.3, 0.6, "uniform")
+    outs = []
+    for mode in ("loop", "run"):
+        for every in (1, 4):
+            pt = m.ParallelTempering(betas, seed=seed, backend=m.GPUBackend())
+            reps = m.Ising([L, L], nchains=n)
+            pt.attach(reps)
+            reps.init_("random", rng=m.PhiloxRNG(seed, 0))
+            if mode == "loop":
+                for _ in range(12):
+                    m.sweep_(reps, pt, every)
+                    m.update_(pt)
+            else:
+                pt.run_(reps, 12, every)
+            outs.append((mode, every, list(pt.index()), list(pt.steps), list(pt.accepted), reps.spins.copy(),
+                         [a.steps for a in pt.replica.algs]))
+    for every in (1, 4):
+        a = [o for o in outs if o[0] == "loop" and o[1] == every][0]
+        b = [o for o in outs if o[0] == "run" and o[1] == every][0]
+        assert a[2:5] == b[2:5] and np.array_equal(a[5], b[5]) and a[6] == b[6]
+        assert sum(a[4]) > 0
+
+
 def test_large_lattice_properties(m):
     """L = 4096 (beyond what the oracle sweeps in seconds): size-independent properties"""
     L = 4096
