@@ -750,7 +750,7 @@ bool launch_recompute_ising2d(mcx_lattice *lat)
 static bool aux_streams(mcx_ctx *ctx)
 {
     if (ctx->aux_ready) return true;
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
         if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->aux_join[i], cudaEventDisableTiming) != cudaSuccess) {
             cudaGetLastError();
@@ -819,7 +819,7 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
     // 4 bands gain less, shorter strips or smaller bands lose (profiles/r01_bands_groups.md).  MCX_BANDS forces a count.
     const int Ly = lat->view.Ly;
     const bool forced = bands_env > 1;
-    int bands = forced ? (bands_env > 8 ? 8 : bands_env) : 8;
+    int bands = forced ? (bands_env > 16 ? 16 : bands_env) : 8;
     const int R = 16;
     if (Ly % (R * bands) != 0) return false;
     const int64_t items_per_band = ((int64_t)(Ly / bands / R) * (lat->view.half >> 4) + kThreads - 1) / kThreads;

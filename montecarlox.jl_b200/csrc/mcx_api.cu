@@ -121,7 +121,7 @@ int32_t mcx_ctx_destroy(mcx_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->aux_ready) {
-        for (int i = 0; i < 8; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->aux_join[i]); }
+        for (int i = 0; i < 16; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->aux_join[i]); }
         cudaEventDestroy(ctx->aux_fork);
     }
     delete ctx;

@@ -10,8 +10,8 @@ struct mcx_ctx {
     size_t total_mem;
     uint64_t launches;
     // auxiliary streams for overlapping the half-sweeps of chain groups (created on first use)
-    cudaStream_t aux[8];
-    cudaEvent_t aux_fork, aux_join[8];
+    cudaStream_t aux[16];
+    cudaEvent_t aux_fork, aux_join[16];
     bool aux_ready;
 };
 
