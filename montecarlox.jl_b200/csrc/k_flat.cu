@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
         double Ho1 = P.J * (P.J * (double)pair);
         int64_t run_bin = io;
         unsigned long long run_cnt = 0;
+        bool speculate = true;      // multicanonical: decide 32 attempts at once (phase 2); adapted per batch
         const uint32_t halfN = (uint32_t)L.halfN;
         constexpr uint32_t PF = OBS == MCX_OBS_ENERGY ? 0 : 2;     // plane of the Float64 draw's high half
 
@@ -180,7 +181,95 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                         }
                     }
                     __syncwarp();
-                    // ---- phase 2: the chain's serial recurrence (lane 0)
+                    // ---- phase 2: the chain's serial recurrence.
+                    // Multicanonical weights do not change during a sweep, so a rejected attempt leaves the chain
+                    // state untouched: the 32 lanes decide 32 consecutive attempts against the CURRENT state at
+                    // once, the first accepted one (ballot) is applied, and only the attempts after it are
+                    // decided again.  Every decision is taken with the exact state the serial loop would have, so
+                    // the trajectory is unchanged; the cost drops from one dependent evaluation per attempt to
+                    // one per ACCEPTED attempt (+ 1 per 32).  Wang-Landau changes lw at every attempt: serial loop.
+                    const long long nacc_before = nacc;
+                    if (KIND == MCX_FLAT_MUCA && speculate) {
+                        for (int base = 0; base < cnt && !dead; base += 32) {
+                            const int idx = base + lane;
+                            const bool valid = idx < cnt;
+                            const int32_t d = valid ? s_d[w][idx] : 0;
+                            const float hif = valid ? s_hi[w][idx] : 0.0f;
+                            int dpair, dspin, dspin2;
+                            if (OBS == MCX_OBS_ENERGY) {
+                                const int dE = (int8_t)(d & 0xff), s = (int8_t)((d >> 8) & 0xff);
+                                dpair = -dE; dspin = -2 * s; dspin2 = 0;
+                            } else {
+                                dspin = (int8_t)(d & 0xff); dspin2 = (int8_t)((d >> 8) & 0xff); dpair = (int8_t)((d >> 16) & 0xff);
+                            }
+                            bool mine_accepted = false;
+                            int start = 0;                                   // attempts [0, start) of this group are decided
+                            const int gend = min(32, cnt - base);
+                            while (start < gend) {
+                                // decision of my attempt against the current state (lanes before `start` idle)
+                                const bool live = valid && lane >= start;
+                                const int64_t x_new = OBS == MCX_OBS_ENERGY ? -pair - dpair : spin2 + dspin2;
+                                const int64_t in = bin_of(x_new, P.start, P.step, shift);
+                                const bool inside = in >= 0 && in < P.nbins;
+                                bool acc_i = false;
+                                double lw_new = lw_old, Hn1 = Ho1;
+                                if (live && inside) {
+                                    lw_new = in == io ? lw_old : lw[in];
+                                    double log_ratio;
+                                    if (OBS == MCX_OBS_ENERGY) {
+                                        log_ratio = lw_new - lw_old;
+                                    } else {
+                                        Hn1 = Ho1 + P.J * (P.J * (double)dpair);
+                                        log_ratio = (-P.beta_pair * Hn1 + lw_new) - (-P.beta_pair * Ho1 + lw_old);
+                                    }
+                                    if (log_ratio > 0) acc_i = true;
+                                    else acc_i = draw_less_exp(hif, log_ratio, [&]() {
+                                        const uint32_t q = qb + idx;
+                                        const Philox4 rl = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, q >> 3, PF + 1);
+                                        return lane16(rl, (int)(q & 7));
+                                    });
+                                }
+                                const bool oob_i = live && !inside && P.policy == 0;        // BoundsError when reached
+                                const unsigned ev = __ballot_sync(0xffffffffu, acc_i || oob_i);
+                                const int k = ev ? __ffs(ev) - 1 : gend;                    // first attempt that changes anything
+                                // attempts [start, k) are rejected: they visit the current bin
+                                const int nrej = k - start;
+                                if (nrej > 0 && lane == 0) {
+                                    if (SMEM_HIST) atomicAdd(&s_hist[io], (uint32_t)nrej);
+                                    else if (io == run_bin) run_cnt += nrej;
+                                    else {
+                                        if (run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
+                                        run_bin = io; run_cnt = nrej;
+                                    }
+                                }
+                                if (k >= gend) break;
+                                if (__shfl_sync(0xffffffffu, (int)oob_i, k)) {
+                                    if (lane == 0) atomicExch(P.error, 1);
+                                    dead = 1;
+                                    break;
+                                }
+                                // attempt k is accepted: its values become the chain state on every lane
+                                pair += __shfl_sync(0xffffffffu, dpair, k);
+                                spin += __shfl_sync(0xffffffffu, dspin, k);
+                                spin2 += __shfl_sync(0xffffffffu, dspin2, k);
+                                nacc += 1;
+                                io = __shfl_sync(0xffffffffu, in, k);
+                                lw_old = __shfl_sync(0xffffffffu, lw_new, k);
+                                Ho1 = __shfl_sync(0xffffffffu, Hn1, k);
+                                if (lane == k) mine_accepted = true;
+                                if (lane == 0) {                                            // record_visit! at the new bin
+                                    if (SMEM_HIST) atomicAdd(&s_hist[io], 1u);
+                                    else if (io == run_bin) run_cnt += 1;
+                                    else {
+                                        if (run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
+                                        run_bin = io; run_cnt = 1;
+                                    }
+                                }
+                                start = k + 1;
+                            }
+                            if (valid) s_acc[w][idx] = (uint8_t)mine_accepted;
+                        }
+                    } else
                     if (lane == 0) {
                         for (int idx = 0; idx < cnt; ++idx) {
                             const int32_t d = s_d[w][idx];
@@ -241,6 +330,16 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                         }
                     }
                     dead = __shfl_sync(0xffffffffu, dead, 0);
+                    if (KIND == MCX_FLAT_MUCA) {
+                        if (!speculate) {        // the serial loop ran on lane 0: every lane needs the chain state
+                            pair = __shfl_sync(0xffffffffu, pair, 0); spin = __shfl_sync(0xffffffffu, spin, 0);
+                            spin2 = __shfl_sync(0xffffffffu, spin2, 0); nacc = __shfl_sync(0xffffffffu, nacc, 0);
+                            io = __shfl_sync(0xffffffffu, io, 0); lw_old = __shfl_sync(0xffffffffu, lw_old, 0);
+                            Ho1 = __shfl_sync(0xffffffffu, Ho1, 0);
+                        }
+                        // deciding 32 attempts at once pays while fewer than ~45 % of them are accepted
+                        speculate = (nacc - nacc_before) * 20 < (long long)cnt * 9;
+                    }
                     __syncwarp();
                     // ---- phase 3: write the accepted sites back
 #pragma unroll
