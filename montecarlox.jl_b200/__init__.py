@@ -22,5 +22,6 @@ from .rng import PhiloxRNG, exchange_u, philox4x32_10
 from .spin_systems import (BlumeCapel, Context, Ising, IsingLatticeOptim, default_context, energy, init_,
                            magnetization, sweep_)
 from .tables import build_table, table_len
+from .windows import DeviceWindow, WangLandauWindows, join_logdos, partition_windows
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -80,6 +80,11 @@ class GPUBackend:
             return
         self._dist.all_reduce(tensor, group=self.group)
 
+    def all_reduce_max(self, tensor):
+        if not self._dist or self.size == 1:
+            return
+        self._dist.all_reduce(tensor, op=self._dist.ReduceOp.MAX, group=self.group)
+
     def barrier(self):
         if self._dist and self.size > 1:
             self._dist.barrier(group=self.group)

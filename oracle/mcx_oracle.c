@@ -758,8 +758,14 @@ int mcxo_flat_accept(mcxo_alg *a, mcxo_flat *f, int kind, int64_t x_new, int64_t
  * one site after the other (the acceptance depends on the chain's global observable), in
  * checkerboard order: all colour-0 sites in slot order, then all colour-1 sites.  The stream is
  * positioned at (chain, FLAT, 2*sweep + colour, slot) with slot = row*(Lx/2) + (x>>1) as for SWEEP. */
-int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int observable,
-                    double beta_pair, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps)
+/* policy 0: an out-of-range bin is the reference's BoundsError (test/test_multicanonical.jl:39-43; returns -1).
+ * policy 1: energy windows (BASELINE.json configs[4]).  The reference has no windows; this restates the
+ * contract include/mcx_b200.h gives mcx_flat_create: a proposal that leaves the binned range is a rejected
+ * attempt -- steps += 1, no draw, the visit (record_visit! / lw -= logf) goes to the current bin.  A chain
+ * whose CURRENT state is outside the range is an error under both policies. */
+int mcxo_flat_sweep_policy(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int observable,
+                           double beta_pair, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps,
+                           int policy)
 {
     mcxo_rng r; r.seed = seed; r.chain = chain;
     const int64_t Lx = s->dims[0], Ly = s->dims[1], half = Lx / 2;
@@ -777,10 +783,15 @@ int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int obs
                 int64_t E_old = (int64_t)mcxo_energy(s, 0);
                 int64_t E_new = E_old + (int64_t)dE;
                 int64_t in = mcxo_binindex(f->start, f->step, E_new), io = mcxo_binindex(f->start, f->step, E_old);
-                if (in < 1 || in > f->num || io < 1 || io > f->num) return -1;
-                double log_ratio = f->logweight[in - 1] - f->logweight[io - 1];
+                if (io < 1 || io > f->num) return -1;
+                const int outside = in < 1 || in > f->num;
+                if (outside && policy == 0) return -1;
                 a->steps += 1;
-                int accepted = (log_ratio > 0) || (mcxo_rand_f64(&r) < exp(log_ratio));
+                int accepted = 0;
+                if (!outside) {
+                    double log_ratio = f->logweight[in - 1] - f->logweight[io - 1];
+                    accepted = (log_ratio > 0) || (mcxo_rand_f64(&r) < exp(log_ratio));
+                }
                 a->accepted += accepted;
                 int64_t iv = accepted ? in : io;
                 if (kind == 0) f->histogram[iv - 1] += 1; else f->logweight[iv - 1] -= f->logf;
@@ -792,11 +803,16 @@ int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int obs
                 double Ho1 = s->J * s->sum_pair; int64_t Ho2 = s->sum_spins2;
                 double Hn1 = Ho1 + s->J * dpair; int64_t Hn2 = Ho2 + dspin2;
                 int64_t in = mcxo_binindex(f->start, f->step, Hn2), io = mcxo_binindex(f->start, f->step, Ho2);
-                if (in < 1 || in > f->num || io < 1 || io > f->num) return -1;
-                /* logweight(CustomEnsemble, H) = -beta*H[1] + lw2(H[2]) (muca_BlumeCapel.jl:49-51) */
-                double log_ratio = (-beta_pair * Hn1 + f->logweight[in - 1]) - (-beta_pair * Ho1 + f->logweight[io - 1]);
+                if (io < 1 || io > f->num) return -1;
+                const int outside = in < 1 || in > f->num;
+                if (outside && policy == 0) return -1;
                 a->steps += 1;
-                int accepted = (log_ratio > 0) || (mcxo_rand_f64(&r) < exp(log_ratio));
+                int accepted = 0;
+                if (!outside) {
+                    /* logweight(CustomEnsemble, H) = -beta*H[1] + lw2(H[2]) (muca_BlumeCapel.jl:49-51) */
+                    double log_ratio = (-beta_pair * Hn1 + f->logweight[in - 1]) - (-beta_pair * Ho1 + f->logweight[io - 1]);
+                    accepted = (log_ratio > 0) || (mcxo_rand_f64(&r) < exp(log_ratio));
+                }
                 a->accepted += accepted;
                 int64_t iv = accepted ? in : io;
                 if (kind == 0) f->histogram[iv - 1] += 1; else f->logweight[iv - 1] -= f->logf;
@@ -804,6 +820,12 @@ int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int obs
             }
         }
     return 0;
+}
+
+int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int observable,
+                    double beta_pair, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps)
+{
+    return mcxo_flat_sweep_policy(s, a, f, kind, observable, beta_pair, seed, chain, sweep0, nsweeps, 0);
 }
 
 /* ===================================================================== */

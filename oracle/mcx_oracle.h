@@ -136,6 +136,11 @@ void    mcxo_muca_update(double *logweight, const double *histogram, int64_t n);
  * pair term (muca_BlumeCapel.jl). Returns 0, or -1 on an out-of-range bin (BoundsError). */
 int mcxo_flat_sweep(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int observable,
                     double beta_pair, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps);
+/* the same with the out-of-range policy of include/mcx_b200.h mcx_flat_create: 0 = BoundsError (the
+ * reference), 1 = energy window (a proposal leaving the range is a rejected attempt; not in the reference) */
+int mcxo_flat_sweep_policy(mcxo_system *s, mcxo_alg *a, mcxo_flat *f, int kind, int observable,
+                           double beta_pair, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps,
+                           int policy);
 /* single generic accept!(alg, x_new, x_old) on a table, with explicit u (test helper) */
 int mcxo_flat_accept(mcxo_alg *a, mcxo_flat *f, int kind, int64_t x_new, int64_t x_old, double u);
 

@@ -110,6 +110,8 @@ def lib():
     L.mcxo_muca_update.argtypes = [pd, pd, i64]
     L.mcxo_flat_sweep.argtypes = [vp, C.POINTER(_Alg), C.POINTER(_Flat), ci, ci, dbl, u64, u32, u64, i64]
     L.mcxo_flat_sweep.restype = ci
+    L.mcxo_flat_sweep_policy.argtypes = [vp, C.POINTER(_Alg), C.POINTER(_Flat), ci, ci, dbl, u64, u32, u64, i64, ci]
+    L.mcxo_flat_sweep_policy.restype = ci
     L.mcxo_flat_accept.argtypes = [C.POINTER(_Alg), C.POINTER(_Flat), ci, i64, i64, dbl]
     L.mcxo_flat_accept.restype = ci
     L.mcxo_exchange_log_ratio.argtypes = [dbl, dbl, dbl, dbl]
@@ -231,9 +233,9 @@ class System:
     def sweep_random_site(self, alg, xo, nattempts, use_table=False):
         lib().mcxo_sweep_random_site(self.p, C.byref(alg.a), C.byref(xo), nattempts, int(use_table))
 
-    def flat_sweep(self, alg, flat, kind, observable, beta_pair, seed, chain, sweep0, nsweeps):
-        return lib().mcxo_flat_sweep(self.p, C.byref(alg.a), C.byref(flat.f), kind, observable, beta_pair,
-                                     seed, chain, sweep0, nsweeps)
+    def flat_sweep(self, alg, flat, kind, observable, beta_pair, seed, chain, sweep0, nsweeps, policy=0):
+        return lib().mcxo_flat_sweep_policy(self.p, C.byref(alg.a), C.byref(flat.f), kind, observable, beta_pair,
+                                            seed, chain, sweep0, nsweeps, policy)
 
 
 def xoshiro(seed):
