@@ -383,3 +383,18 @@ def test_large_lattice_properties(m):
     # upload/download round trip is the identity
     sys2.spins = sp
     assert np.array_equal(sys2.spins, sp) and sys2.energy() == e_cached
+
+
+def test_device_reproduces_committed_trajectories(m):
+    """The committed golden trajectories (tests/golden/trajectories.json, RNG layout v1) without the oracle
+    in the loop: spins (sha256), integer sums, accepted counts and flat-histogram tables, bit for bit;
+    energies that involve a Float64 field / crystal-field term to 1e-9."""
+    import json
+    import os
+    import _golden_cases as g
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trajectories.json")) as fh:
+        gold = json.load(fh)["cases"]
+    for c in g.cases():
+        want, got = gold[g.name_of(c)], g.device_result(c, m)
+        assert got.pop("energy") == pytest.approx(want.pop("energy"), abs=1e-9), g.name_of(c)
+        assert got == want, g.name_of(c)

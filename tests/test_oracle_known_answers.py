@@ -184,3 +184,19 @@ def test_threshold_tables_match_float_compare(oracle):
                     ms = np.concatenate([rng.integers(0, 2 ** 32, 64), [0, 2 ** 32 - 1, max(t - 1, 0), min(t, 2 ** 32 - 1)]])
                     for m in ms:
                         assert (float(m) / 2 ** 32 < p) == (int(m) < t)
+
+
+def test_oracle_reproduces_committed_trajectories(oracle):
+    """tests/golden/trajectories.json (written by tests/golden/gen_trajectories.py) freezes RNG layout v1:
+    the oracle must still produce every committed trajectory.  The device is held to the same file in
+    tests/test_gpu_parity.py::test_device_reproduces_committed_trajectories."""
+    import json
+    import os
+    import _golden_cases as g
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trajectories.json")) as fh:
+        gold = json.load(fh)
+    assert gold["rng_layout"] == 1
+    cs = g.cases()
+    assert sorted(g.name_of(c) for c in cs) == sorted(gold["cases"])
+    for c in cs:
+        assert g.oracle_result(c) == gold["cases"][g.name_of(c)], g.name_of(c)
