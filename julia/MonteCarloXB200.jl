@@ -338,4 +338,77 @@ sweep!(sys::SlabIsing, alg, nsweeps::Integer=1) = sweep!(sys.part, alg, nsweeps)
 local_pair_sum(sys::SlabIsing) = sums(sys.part)[1]
 local_spin_sum(sys::SlabIsing) = sums(sys.part)[2]
 
+# ----------------------------------------------------------------------------------------------
+# 6. Wang-Landau in energy windows (BASELINE.json configs[4]; beyond the reference, whose lookups outside the
+#    binned range throw BoundsError, test/test_multicanonical.jl:39-43).  One DeviceIsing batch per window
+#    (one chain per walker, own DeviceCtx = own stream), `mcx_flat_create(..., out_of_range_policy = 1)`:
+#    a proposal leaving the window is a rejected attempt that visits the current bin.  Windows are dealt to
+#    the ranks in contiguous blocks; nothing is exchanged while sampling.  The Python mirror
+#    (montecarlox.jl_b200/windows.py) adds the drive of the walkers into their windows and is what the tests run.
+# ----------------------------------------------------------------------------------------------
+mutable struct DeviceWangLandau
+    h::Ptr{Cvoid}              # mcx_flat: one log-weight table per chain, like one WangLandauEnsemble per algorithm
+    sys::DeviceIsing
+    bins::StepRange{Int,Int}
+    logf::Float64
+end
+
+"WangLandau(rng, bins; logf) (algorithms/wang_landau.jl:10-18) for every chain of `sys`, restricted to `bins`"
+function DeviceWangLandau(sys::DeviceIsing, bins::StepRange{Int,Int}; logf::Float64=1.0, window::Bool=true)
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((:mcx_flat_create, libmcx), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Int64, Int64, Int64, Float64, Int32, Ref{Ptr{Cvoid}}),
+                sys.h, 1, 0, first(bins), step(bins), length(bins), 0.0, window ? 1 : 0, out))
+    return DeviceWangLandau(out[], sys, bins, logf)
+end
+
+"n*N attempts per walker: spin_flip!(sys, alg::ImportanceSampling) (ising.jl:25-33) + accept! (wang_landau.jl:29-37)"
+function sweep!(wl::DeviceWangLandau, nsweeps::Integer=1)
+    check(ccall((:mcx_flat_set_logf, libmcx), Int32, (Ptr{Cvoid}, Float64), wl.h, wl.logf))
+    check(ccall((:mcx_flat_sweep, libmcx), Int32, (Ptr{Cvoid}, Int64), wl.h, nsweeps))
+    return nothing
+end
+
+"log-weight tables [nbins, nchains] as host Float64 (examples read `ens.logweight.values`, muca_Ising2D.jl:89-90)"
+function logweights(wl::DeviceWangLandau)
+    lw = Matrix{Float64}(undef, length(wl.bins), wl.sys.nchains)
+    GC.@preserve lw check(ccall((:mcx_flat_get_logweight, libmcx), Int32, (Ptr{Cvoid}, Ptr{Float64}), wl.h, lw))
+    return lw
+end
+
+MonteCarloX.update!(wl::DeviceWangLandau; power::Real=0.5) = (wl.logf *= power; nothing)   # ensembles/wang_landau.jl:23
+
+"equal-width windows over bin indices 1:nbins, neighbours sharing `overlap` of a window -> Vector of UnitRange"
+function partition_windows(nbins::Int, nwindows::Int; overlap::Float64=0.5)
+    nwindows == 1 && return [1:nbins]
+    width = min(max(ceil(Int, nbins / (1 + (nwindows - 1) * (1 - overlap))), 2), nbins)
+    stride = (nbins - width) / (nwindows - 1)
+    firsts = [round(Int, k * stride) for k in 0:nwindows-1]
+    firsts[end] = nbins - width
+    return [f+1:f+width for f in firsts]
+end
+
+"join window pieces of log g (0.0 = never visited) at their overlaps: shift by the mean difference, cross-fade"
+function join_logdos(pieces::Vector{Vector{Float64}}, windows::Vector{UnitRange{Int}}, nbins::Int)
+    out = fill(NaN, nbins)
+    prev_end = 0
+    for (k, (p, w)) in enumerate(zip(pieces, windows))
+        vis = p .!= 0.0
+        if k == 1
+            out[w[vis]] = p[vis]; prev_end = last(w); continue
+        end
+        both = isfinite.(out[w]) .& vis
+        any(both) || throw(ArgumentError("windows $(k-1) and $k share no visited bin"))
+        shift = sum(out[w][both] .- p[both]) / count(both)
+        span = max(min(prev_end, last(w)) - first(w) + 1, 1)
+        for (i, b) in enumerate(w)
+            vis[i] || continue
+            t = clamp((i - 0.5) / span, 0.0, 1.0)
+            out[b] = both[i] ? (1 - t) * out[b] + t * (p[i] + shift) : p[i] + shift
+        end
+        prev_end = max(prev_end, last(w))
+    end
+    return out
+end
+
 end # module

@@ -40,6 +40,7 @@ struct FlatParams {
     uint32_t seed_lo, seed_hi, first_chain;
     uint64_t sweep0;
     int nsweeps, policy, step_shift;
+    int wl_spec;                // Wang-Landau decisions at once: -1 adaptive (serial / 8 / 32), 0 serial only, 8, 32
 };
 
 // rand < exp(log_ratio) for rand = m * 2^-32, m = hi << 16 | lo, decided exactly but cheaply:
@@ -131,6 +132,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
         int64_t run_bin = io;
         unsigned long long run_cnt = 0;
         bool speculate = true;      // multicanonical: decide 32 attempts at once (phase 2); adapted per batch
+        // Wang-Landau: decide `wl_width` consecutive attempts at once (0: the serial loop on lane 0); adapted per batch
+        int wl_width = KIND == MCX_FLAT_WANG_LANDAU ? (P.wl_spec < 0 ? 8 : P.wl_spec) : 0;
         const uint32_t halfN = (uint32_t)L.halfN;
         constexpr uint32_t PF = OBS == MCX_OBS_ENERGY ? 0 : 2;     // plane of the Float64 draw's high half
 
@@ -269,6 +272,96 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                             }
                             if (valid) s_acc[w][idx] = (uint8_t)mine_accepted;
                         }
+                    } else if (KIND == MCX_FLAT_WANG_LANDAU && wl_width > 0) {
+                        // Wang-Landau changes lw at every attempt, but a REJECTED attempt changes it predictably: it
+                        // visits the current bin, lw[io] -= logf (wang_landau.jl:33-35), and leaves everything else
+                        // alone.  So the lanes decide G consecutive attempts at once, lane j assuming that the j
+                        // attempts before it were rejected: it replays their j subtractions (one rounding each, as
+                        // the serial loop does) to get the current bin's weight it would see.  The first accepted
+                        // attempt (ballot) is applied and the attempts after it are decided again.  Every decision
+                        // uses exactly the values the serial loop would have; the table of a chain is private, and only
+                        // bin io changes between two accepted attempts, so the other lanes' loads lw[in] are current.
+                        const int G = wl_width;
+                        for (int base = 0; base < cnt && !dead; base += G) {
+                            const int idx = base + lane;
+                            const bool valid = lane < G && idx < cnt;
+                            const int32_t d = valid ? s_d[w][idx] : 0;
+                            const float hif = valid ? s_hi[w][idx] : 0.0f;
+                            int dpair, dspin, dspin2;
+                            if (OBS == MCX_OBS_ENERGY) {
+                                const int dE = (int8_t)(d & 0xff), s = (int8_t)((d >> 8) & 0xff);
+                                dpair = -dE; dspin = -2 * s; dspin2 = 0;
+                            } else {
+                                dspin = (int8_t)(d & 0xff); dspin2 = (int8_t)((d >> 8) & 0xff); dpair = (int8_t)((d >> 16) & 0xff);
+                            }
+                            bool mine_accepted = false;
+                            int start = 0;                                   // attempts [0, start) of this group are decided
+                            const int gend = min(G, cnt - base);
+                            while (start < gend) {
+                                const bool live = valid && lane >= start;
+                                double lw_cur = lw_old;                      // lw[io] after the rejections before my attempt
+                                for (int i = start; i < lane && live; ++i) lw_cur -= P.logf;
+                                const int64_t x_new = OBS == MCX_OBS_ENERGY ? -pair - dpair : spin2 + dspin2;
+                                const int64_t in = bin_of(x_new, P.start, P.step, shift);
+                                const bool inside = in >= 0 && in < P.nbins;
+                                bool acc_i = false;
+                                double lw_new = lw_cur, Hn1 = Ho1;
+                                if (live && inside) {
+                                    lw_new = in == io ? lw_cur : lw[in];
+                                    double log_ratio;
+                                    if (OBS == MCX_OBS_ENERGY) {
+                                        log_ratio = lw_new - lw_cur;
+                                    } else {
+                                        Hn1 = Ho1 + P.J * (P.J * (double)dpair);
+                                        log_ratio = (-P.beta_pair * Hn1 + lw_new) - (-P.beta_pair * Ho1 + lw_cur);
+                                    }
+                                    if (log_ratio > 0) acc_i = true;
+                                    else acc_i = draw_less_exp(hif, log_ratio, [&]() {
+                                        const uint32_t q = qb + idx;
+                                        const Philox4 rl = stream_block(P.seed_lo, P.seed_hi, chain_id, TAG_FLAT, t, q >> 3, PF + 1);
+                                        return lane16(rl, (int)(q & 7));
+                                    });
+                                }
+                                const bool oob_i = live && !inside && P.policy == 0;        // BoundsError when reached
+                                const unsigned ev = __ballot_sync(0xffffffffu, acc_i || oob_i);
+                                const int k = ev ? __ffs(ev) - 1 : gend;                    // first attempt that is not a rejection
+                                // attempts [start, k) are rejected: lw[io] after their visits is what lane k started
+                                // from, or one more subtraction after the last lane if nothing else happened
+                                const int nrej = k - start;
+                                const double lw_last = __shfl_sync(0xffffffffu, lw_cur, min(k, gend - 1));
+                                const double lw_after = k < gend ? lw_last : lw_last - P.logf;
+                                if (k >= gend) {
+                                    lw_old = lw_after;
+                                    if (lane == 0) lw[io] = lw_old;
+                                    break;
+                                }
+                                if (__shfl_sync(0xffffffffu, (int)oob_i, k)) {
+                                    lw_old = lw_after;
+                                    if (lane == 0) {
+                                        if (nrej > 0) lw[io] = lw_old;
+                                        atomicExch(P.error, 1);
+                                    }
+                                    dead = 1;
+                                    break;
+                                }
+                                // attempt k is accepted: the chain moves to bin in_k and visits it
+                                const int64_t in_k = __shfl_sync(0xffffffffu, in, k);
+                                const double lw_new_k = __shfl_sync(0xffffffffu, lw_new, k);
+                                pair += __shfl_sync(0xffffffffu, dpair, k);
+                                spin += __shfl_sync(0xffffffffu, dspin, k);
+                                spin2 += __shfl_sync(0xffffffffu, dspin2, k);
+                                nacc += 1;
+                                Ho1 = __shfl_sync(0xffffffffu, Hn1, k);
+                                if (lane == 0 && nrej > 0) lw[io] = lw_after;
+                                io = in_k;
+                                lw_old = lw_new_k - P.logf;                 // lw_old = lw_new; lw_old -= logf
+                                if (lane == 0) lw[io] = lw_old;
+                                if (lane == k) mine_accepted = true;
+                                __syncwarp();                               // lane 0's stores before the next round's loads
+                                start = k + 1;
+                            }
+                            if (valid) s_acc[w][idx] = (uint8_t)mine_accepted;
+                        }
                     } else
                     if (lane == 0) {
                         for (int idx = 0; idx < cnt; ++idx) {
@@ -330,6 +423,21 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                         }
                     }
                     dead = __shfl_sync(0xffffffffu, dead, 0);
+                    if (KIND == MCX_FLAT_WANG_LANDAU) {
+                        if (wl_width == 0) {     // the serial loop ran on lane 0: every lane needs the chain state
+                            pair = __shfl_sync(0xffffffffu, pair, 0); spin = __shfl_sync(0xffffffffu, spin, 0);
+                            spin2 = __shfl_sync(0xffffffffu, spin2, 0); nacc = __shfl_sync(0xffffffffu, nacc, 0);
+                            io = __shfl_sync(0xffffffffu, io, 0); lw_old = __shfl_sync(0xffffffffu, lw_old, 0);
+                            Ho1 = __shfl_sync(0xffffffffu, Ho1, 0);
+                        }
+                        if (P.wl_spec < 0) {
+                            // a round of group decisions costs about 2.3 (8 lanes) or 3.3 (32 lanes) serial attempts
+                            // (profiles/r01_wl_group_decisions.md): acceptance of this batch > 40 % -> serial loop,
+                            // > 15 % -> 8 at once, else 32
+                            const long long a = nacc - nacc_before;
+                            wl_width = a * 5 > (long long)cnt * 2 ? 0 : a * 20 > (long long)cnt * 3 ? 8 : 32;
+                        }
+                    }
                     if (KIND == MCX_FLAT_MUCA) {
                         if (!speculate) {        // the serial loop ran on lane 0: every lane needs the chain state
                             pair = __shfl_sync(0xffffffffu, pair, 0); spin = __shfl_sync(0xffffffffu, spin, 0);
@@ -405,6 +513,7 @@ void launch_flat_sweep(mcx_flat *f, uint64_t sweep0, int nsweeps)
     P.beta_pair = f->beta_pair; P.logf = f->logf; P.J = lat->J;
     P.seed_lo = (uint32_t)lat->seed; P.seed_hi = (uint32_t)(lat->seed >> 32); P.first_chain = lat->first_chain;
     P.sweep0 = sweep0; P.nsweeps = nsweeps; P.policy = f->policy;
+    P.wl_spec = knobs().wl_spec == 0 || knobs().wl_spec == 8 || knobs().wl_spec == 32 ? knobs().wl_spec : -1;
     P.step_shift = -1;
     for (int sh = 0; sh < 62; ++sh)
         if (f->step == ((int64_t)1 << sh)) P.step_shift = sh;
@@ -553,6 +662,7 @@ int32_t mcx_flat_sweep(mcx_flat *f, int64_t nsweeps)
     FREQ(nsweeps >= 0, MCX_ERR_ARGUMENT, "nsweeps must be >= 0");
     mcx_lattice *lat = f->lat;
     FCUDA(cudaSetDevice(lat->ctx->device));
+    knobs_refresh();
     if (lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
     // shared-memory counters are 32-bit: bound the attempts one block can record per launch
     const double per_sweep = 4.0 * (double)lat->N;

@@ -91,6 +91,7 @@ namespace mcx {
 struct Knobs {
     int rows_per_strip, ctas_per_sm, variant, full, groups, bands, bc2d, ising3d;
     int resident, resident_cluster, resident_rows, resident_threads, force_generic;
+    int wl_spec;      // MCX_WL_SPEC: Wang-Landau attempts decided at once (0 = serial loop, 8, 32; unset = adaptive)
 };
 const Knobs &knobs();
 void knobs_refresh();

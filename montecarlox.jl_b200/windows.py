@@ -230,8 +230,12 @@ class WangLandauWindows:
     def _ground_state(self, antiferro):
         if not antiferro:
             return np.ones(self.N, dtype=np.int8)
-        idx = np.indices(self.dims[::-1]).sum(axis=0)            # site i = x + Lx*(y + Ly*z) (ising.jl:444-456)
-        return (1 - 2 * (idx & 1)).astype(np.int8).reshape(-1)
+        par = np.zeros(self.dims[::-1], dtype=np.int8)           # site i = x + Lx*(y + Ly*z) (ising.jl:444-456)
+        for ax, n in enumerate(self.dims[::-1]):
+            shape = [1] * len(self.dims)
+            shape[ax] = n
+            par = par ^ (np.arange(n, dtype=np.int8) & 1).reshape(shape)
+        return (1 - 2 * par).astype(np.int8).reshape(-1)
 
     # ---- seeding
     def prepare_(self):

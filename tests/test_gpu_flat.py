@@ -157,3 +157,65 @@ def test_muca_iterations_converge_to_exact_dos(m):
     ref = {e: exact[e] - exact[0] for e in exact}
     rmse = np.sqrt(np.mean([(est[e] - ref[e]) ** 2 for e in exact]))
     assert rmse < 0.35, rmse
+
+
+def _wl_device_vs_oracle(m, oracle, model, dims, nch, first_chain, seed, init, lo, step, nbins, policy, logfs, nsweeps,
+                         observable=0, beta_pair=0.0):
+    """Wang-Landau chains through the C ABI (one table per chain) against the oracle, several logf stages."""
+    import ctypes as C
+    lib, check = m.lib(), m._lib.check
+    N = int(np.prod(dims))
+    sys_ = (m.Ising if model == 0 else m.BlumeCapel)(dims, nchains=nch)
+    rng = m.PhiloxRNG(seed, first_chain)
+    if init == "random":
+        sys_.init_("random", rng=rng)
+    else:
+        check(lib.mcx_lattice_set_first_chain_id(sys_.h_lat, first_chain))
+    sys_.set_rng(seed, 0)
+    h = C.c_void_p()
+    check(lib.mcx_flat_create(sys_.h_lat, m._lib.FLAT_WANG_LANDAU, observable, lo, step, nbins, beta_pair, policy, C.byref(h)))
+    refs = []
+    for c in range(nch):
+        s = oracle.System(model, dims)
+        if init == "random":
+            s.init_random(seed, first_chain + c)
+        else:
+            s.spins = np.ones(N, dtype=np.int8)
+        refs.append((s, oracle.Flat(lo, step, nbins), oracle.Alg(0, 0.0)))
+    sweep0 = 0
+    for logf in logfs:
+        check(lib.mcx_flat_set_logf(h, logf))
+        check(lib.mcx_flat_sweep(h, nsweeps))
+        lw = np.empty((nch, nbins), dtype=np.float64)
+        check(lib.mcx_flat_get_logweight(h, lw.ctypes.data))
+        spins = np.asarray(sys_.spins).reshape(nch, N)
+        acc = np.atleast_1d(sys_.accepted())
+        for c, (s, f, a) in enumerate(refs):
+            f.f.logf = logf
+            assert s.flat_sweep(a, f, 1, observable, beta_pair, seed, first_chain + c, sweep0, nsweeps, policy=policy) == 0
+            assert np.array_equal(lw[c], f.logweight), (logf, c)
+            assert np.array_equal(spins[c], s.spins), (logf, c)
+            assert acc[c] == a.accepted
+        sweep0 += nsweeps
+    check(lib.mcx_flat_destroy(h))
+    return [a.accepted / a.steps for _, _, a in refs]
+
+
+@pytest.mark.parametrize("spec", [None, "0", "8", "32"])
+def test_wang_landau_group_decisions_bit_exact(m, oracle, spec, monkeypatch):
+    """k_flat_warp decides several consecutive Wang-Landau attempts at once (lane j replays the j rejections before
+    it); MCX_WL_SPEC pins the width (0 = the serial loop on lane 0, unset = adaptive).  Every width must reproduce
+    the oracle bit for bit: power-of-two and inexact logf, full range and energy window, 2-D and 3-D, low and high
+    acceptance, and the (pair, spin^2) observable of muca_BlumeCapel.jl."""
+    if spec is None:
+        monkeypatch.delenv("MCX_WL_SPEC", raising=False)
+    else:
+        monkeypatch.setenv("MCX_WL_SPEC", spec)
+    _wl_device_vs_oracle(m, oracle, 0, [8, 8], 3, 5, 77, "random", -128, 4, 65, 0, [1.0, 0.5, 0.25], 40)
+    _wl_device_vs_oracle(m, oracle, 0, [8, 8], 2, 0, 78, "random", -64, 4, 33, 1, [float(np.log(2.0)), 0.1], 60)
+    _wl_device_vs_oracle(m, oracle, 0, [4, 4, 6], 2, 9, 79, "random", -288, 4, 145, 0, [0.3], 30)
+    r = _wl_device_vs_oracle(m, oracle, 0, [16, 16], 2, 1, 80, "up", -512, 4, 257, 0, [1.0, 1e-3], 30)
+    assert min(r) > 0.02
+    N = 64
+    _wl_device_vs_oracle(m, oracle, 1, [8, 8], 2, 3, 81, "up", 0, 1, N + 1, 0, [0.7, 0.35], 30,
+                         observable=m._lib.OBS_SPIN2_WITH_PAIR_BOLTZMANN, beta_pair=1 / 0.9)
