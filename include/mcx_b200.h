@@ -97,6 +97,16 @@ int32_t mcx_lattice_set_first_chain_id(mcx_lattice *lat, uint32_t first_chain_id
  * host_spins is [nchains][N]. */
 int32_t mcx_lattice_upload(mcx_lattice *lat, const int8_t *host_spins);
 int32_t mcx_lattice_download(mcx_lattice *lat, int8_t *host_spins);      /* read sys.spins */
+/* The same assignment split in two, for callers that stream configurations through the device (the reference
+ * has no counterpart: `sys.spins .= host` is a host-memory copy).  _begin copies host_spins into the handle's
+ * staging buffer on an internal copy stream and returns at once; the lattice itself is not touched, so sweeps
+ * already queued keep running while the bytes cross PCIe.  _commit orders the context's stream after that copy,
+ * converts the staging buffer into the lattice (+ _recompute_cached!) and is otherwise mcx_lattice_upload.
+ * host_spins must stay valid and unchanged until _commit has been called and the stream has passed it; pinned
+ * memory is what makes the copy overlap.  One upload may be pending per handle; mcx_lattice_download while one
+ * is pending is MCX_ERR_STATE. */
+int32_t mcx_lattice_upload_begin(mcx_lattice *lat, const int8_t *host_spins);
+int32_t mcx_lattice_upload_commit(mcx_lattice *lat);
 /* init!(sys, :up/:down/:zero/:random; rng) ising.jl:74, blume_capel.jl:106 (INIT stream) */
 int32_t mcx_lattice_init(mcx_lattice *lat, int32_t mode, uint64_t seed);
 

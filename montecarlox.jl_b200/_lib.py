@@ -49,6 +49,8 @@ SIGNATURES = {
     "mcx_lattice_set_first_chain_id": (_i32, [_vp, _u32]),
     "mcx_lattice_upload": (_i32, [_vp, _vp]),
     "mcx_lattice_download": (_i32, [_vp, _vp]),
+    "mcx_lattice_upload_begin": (_i32, [_vp, _vp]),
+    "mcx_lattice_upload_commit": (_i32, [_vp]),
     "mcx_lattice_init": (_i32, [_vp, _i32, _u64]),
     "mcx_set_rule": (_i32, [_vp, _i32, _vp, _i32, _i32]),
     "mcx_set_labels": (_i32, [_vp, _vp]),

@@ -184,6 +184,12 @@ static void lattice_free(mcx_lattice *lat)
     cudaFree(lat->d_tlo);
     cudaFree(lat->d_labels);
     cudaFree(lat->d_staging);
+    if (lat->copy_stream) {
+        cudaStreamSynchronize(lat->copy_stream);
+        cudaStreamDestroy(lat->copy_stream);
+        cudaEventDestroy(lat->ev_copied);
+        cudaEventDestroy(lat->ev_packed);
+    }
     free(lat->h_table);
     delete lat;
 }
@@ -273,20 +279,64 @@ static int32_t ensure_staging(mcx_lattice *lat)
 int32_t mcx_lattice_upload(mcx_lattice *lat, const int8_t *host_spins)
 {
     REQUIRE(lat && host_spins, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(!lat->upload_pending, MCX_ERR_STATE, "an upload is pending on this handle (the staging buffer is in use): commit it first");
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     int32_t st = ensure_staging(lat);
     if (st != MCX_OK) return st;
     CUDA_TRY(cudaMemcpyAsync(lat->d_staging, host_spins, (size_t)lat->N * (size_t)lat->nchains,
                              cudaMemcpyHostToDevice, lat->ctx->stream));
     launch_pack(lat);
+    if (lat->copy_stream) {      // a later upload_begin may overwrite d_staging only after this conversion
+        CUDA_TRY(cudaEventRecord(lat->ev_packed, lat->ctx->stream));
+        lat->packed_recorded = true;
+    }
     launch_recompute(lat);
     lat->sums_dirty = false;
+    return check_launch(lat->ctx);
+}
+
+int32_t mcx_lattice_upload_begin(mcx_lattice *lat, const int8_t *host_spins)
+{
+    REQUIRE(lat && host_spins, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(!lat->upload_pending, MCX_ERR_STATE, "an upload is already pending on this handle: commit it first");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    int32_t st = ensure_staging(lat);
+    if (st != MCX_OK) return st;
+    if (!lat->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&lat->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&lat->ev_copied, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&lat->ev_packed, cudaEventDisableTiming));
+        // whatever the context's stream has queued so far may still read or write d_staging
+        CUDA_TRY(cudaEventRecord(lat->ev_packed, lat->ctx->stream));
+        lat->packed_recorded = true;
+    }
+    if (lat->packed_recorded) CUDA_TRY(cudaStreamWaitEvent(lat->copy_stream, lat->ev_packed, 0));
+    CUDA_TRY(cudaMemcpyAsync(lat->d_staging, host_spins, (size_t)lat->N * (size_t)lat->nchains,
+                             cudaMemcpyHostToDevice, lat->copy_stream));
+    CUDA_TRY(cudaEventRecord(lat->ev_copied, lat->copy_stream));
+    lat->upload_pending = true;
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_upload_commit(mcx_lattice *lat)
+{
+    REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
+    REQUIRE(lat->upload_pending, MCX_ERR_STATE, "no upload pending on this handle: call mcx_lattice_upload_begin first");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    CUDA_TRY(cudaStreamWaitEvent(lat->ctx->stream, lat->ev_copied, 0));
+    launch_pack(lat);
+    CUDA_TRY(cudaEventRecord(lat->ev_packed, lat->ctx->stream));
+    lat->packed_recorded = true;
+    launch_recompute(lat);
+    lat->sums_dirty = false;
+    lat->upload_pending = false;
     return check_launch(lat->ctx);
 }
 
 int32_t mcx_lattice_download(mcx_lattice *lat, int8_t *host_spins)
 {
     REQUIRE(lat && host_spins, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(!lat->upload_pending, MCX_ERR_STATE, "an upload is pending on this handle (the staging buffer is in use): commit it first");
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     int32_t st = ensure_staging(lat);
     if (st != MCX_OK) return st;

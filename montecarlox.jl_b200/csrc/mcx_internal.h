@@ -41,6 +41,10 @@ struct mcx_lattice {
     int64_t steps;              // attempts per chain since the last reset (same for every chain)
     double J, h, D;
     int8_t *d_staging;          // [nchains][N] reference-order spins for upload/download
+    // split upload (mcx_lattice_upload_begin / _commit): H2D into d_staging on a copy stream of the handle
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_copied, ev_packed;   // copy finished; last conversion out of d_staging finished
+    bool upload_pending, packed_recorded;
     bool fast2d;                // Lx % 32 == 0 && ndim == 2: row-aligned 128-bit kernels apply
     bool track_sums;            // fast kernels accumulate pair/spin sums per flip (else recompute lazily)
     bool sums_dirty;            // pair/spin sums are stale (untracked sweeps ran)

@@ -130,6 +130,14 @@ class AbstractSpinSystem:
         """Upload from a raw host pointer (e.g. pinned memory) without touching numpy."""
         check(lib().mcx_lattice_upload(self.h_lat, C.c_void_p(host_ptr)))
 
+    def upload_begin(self, host_ptr):
+        """Start copying a host buffer (raw pointer, pinned memory for the copy to overlap) towards the device
+        without touching the lattice: sweeps already queued keep running.  `upload_commit` makes it the lattice."""
+        check(lib().mcx_lattice_upload_begin(self.h_lat, C.c_void_p(host_ptr)))
+
+    def upload_commit(self):
+        check(lib().mcx_lattice_upload_commit(self.h_lat))
+
     # ---- observables (ising.jl:17-18, blume_capel.jl:18-19)
     def _sums(self):
         n = self.nchains

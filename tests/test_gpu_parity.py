@@ -398,3 +398,62 @@ def test_device_reproduces_committed_trajectories(m):
         want, got = gold[g.name_of(c)], g.device_result(c, m)
         assert got.pop("energy") == pytest.approx(want.pop("energy"), abs=1e-9), g.name_of(c)
         assert got == want, g.name_of(c)
+
+
+def test_split_upload_equals_upload(m):
+    """mcx_lattice_upload_begin / _commit: the copy runs beside sweeps that are already queued and does not touch the
+    lattice until the commit; afterwards the handle behaves as after mcx_lattice_upload."""
+    import torch
+    L, seed = 256, 9
+    rs = np.random.default_rng(1)
+    spins1 = (2 * rs.integers(0, 2, L * L) - 1).astype(np.int8)
+
+    def fresh():
+        s = m.Ising([L, L])
+        a = m.Metropolis(m.PhiloxRNG(seed, 0), beta=0.44)
+        s.init_("random", rng=a.rng)
+        return s, a
+
+    ref, aref = fresh()
+    m.sweep_(ref, aref, 2)
+    before = ref.spins.copy()
+    ref.spins = spins1                       # plain upload
+    ref.set_rng(seed, 10)
+    m.sweep_(ref, aref, 3)
+
+    for pinned in (False, True):
+        s, a = fresh()
+        if pinned:
+            buf = torch.empty(L * L, dtype=torch.int8).pin_memory()
+            buf.copy_(torch.from_numpy(spins1))
+            ptr = buf.data_ptr()
+        else:
+            buf = spins1.copy()
+            ptr = buf.ctypes.data
+        s._bind_alg(a)
+        m._lib.check(m.lib().mcx_sweep(s.h_lat, 2))      # queued; the copy below must not disturb it
+        s.upload_begin(ptr)
+        with pytest.raises(AssertionError):
+            s.upload_begin(ptr)                           # one pending upload per handle
+        with pytest.raises(AssertionError):
+            s.spins                                       # download needs the staging buffer
+        with pytest.raises(AssertionError):
+            s.spins = spins1
+        assert s.energy() == int(-_pair_sum_2d(before, L))   # still the swept old lattice
+        s.upload_commit()
+        with pytest.raises(AssertionError):
+            s.upload_commit()
+        assert np.array_equal(s.spins, spins1)
+        assert s.energy() == s.energy(full=True) == int(-_pair_sum_2d(spins1, L))
+        s.set_rng(seed, 10)
+        m.sweep_(s, a, 3)
+        assert np.array_equal(s.spins, ref.spins) and s.energy() == ref.energy()
+        # a second round trip on the same handle (events are reused)
+        s.upload_begin(ptr)
+        s.upload_commit()
+        assert np.array_equal(s.spins, spins1)
+
+
+def _pair_sum_2d(spins, L):
+    a = np.asarray(spins, dtype=np.int64).reshape(L, L)
+    return int((a * np.roll(a, 1, 0)).sum() + (a * np.roll(a, 1, 1)).sum())
