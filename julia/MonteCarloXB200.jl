@@ -172,6 +172,13 @@ function Base.getproperty(sys::DeviceIsing, name::Symbol)
     return getfield(sys, name)
 end
 
+# Split assignment of sys.spins for callers that stream configurations through the device: the H2D copy runs on the
+# handle's copy stream beside sweeps that are already queued; `host` must stay alive and unchanged until the commit.
+upload_begin!(sys::DeviceIsing, host::Vector{Int8}) =
+    check(ccall((:mcx_lattice_upload_begin, libmcx), Int32, (Ptr{Cvoid}, Ptr{Int8}), getfield(sys, :h), host))
+upload_commit!(sys::DeviceIsing) =
+    check(ccall((:mcx_lattice_upload_commit, libmcx), Int32, (Ptr{Cvoid},), getfield(sys, :h)))
+
 function sums(sys::DeviceIsing)
     n = sys.nchains
     pair, spin, spin2, acc, steps = (Vector{Int64}(undef, n) for _ in 1:5)
