@@ -61,7 +61,7 @@ void knobs_refresh()
     k.full = knob("MCX_FULL"); k.groups = knob("MCX_GROUPS"); k.bands = knob("MCX_BANDS"); k.bc2d = knob("MCX_BC2D");
     k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
     k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
-    k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC");
+    k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
     g_knobs_ready = true;
 }
 const Knobs &knobs()
@@ -184,6 +184,7 @@ static void lattice_free(mcx_lattice *lat)
     cudaFree(lat->d_tlo);
     cudaFree(lat->d_labels);
     cudaFree(lat->d_staging);
+    cudaFree(lat->d_queue);
     if (lat->copy_stream) {
         cudaStreamSynchronize(lat->copy_stream);
         cudaStreamDestroy(lat->copy_stream);
@@ -484,12 +485,26 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     bool try_series = force == 0;        // whole-series launchers (resident kernel, chain groups) still worth asking
     for (int64_t s = 0; s < nsweeps;) {
         if (try_series) {
+            // MCX_QUEUE=1: the whole series in one launch, work items of all half-sweeps from one ticket counter
+            if (knobs().queue > 0 && launch_sweeps_ising2d_queue(lat, nsweeps - s)) {
+                if (!lat->track_sums) lat->sums_dirty = true;
+                lat->sweep += (uint64_t)(nsweeps - s);
+                s = nsweeps;
+                continue;
+            }
             // series of sweeps over small lattices: one launch with the lattice resident in shared memory
             const int64_t chunk = nsweeps - s < 16384 ? nsweeps - s : 16384;
             if (launch_sweeps_resident(lat, chunk)) {
                 if (!lat->track_sums) lat->sums_dirty = true;
                 lat->sweep += (uint64_t)chunk;
                 s += chunk;
+                continue;
+            }
+            // small batches of lattices too big for shared memory: the ticket-queue series (its own policy, k_queue.cu)
+            if (knobs().queue < 0 && launch_sweeps_ising2d_queue(lat, nsweeps - s)) {
+                if (!lat->track_sums) lat->sums_dirty = true;
+                lat->sweep += (uint64_t)(nsweeps - s);
+                s = nsweeps;
                 continue;
             }
             // chain groups (batches) or row bands (one big lattice) on auxiliary streams overlap each other's launch tails
@@ -570,8 +585,13 @@ int32_t mcx_observables(mcx_lattice *lat, int64_t *pair_sum, int64_t *spin_sum, 
     std::vector<long long> h((size_t)lat->nchains * SUM_FIELDS);
     CUDA_TRY(cudaMemcpyAsync(h.data(), lat->d_sums, h.size() * sizeof(long long), cudaMemcpyDeviceToHost,
                              lat->ctx->stream));
+    unsigned long long queue_err = 0;     // k_queue.cu: raised when a dependency wait gave up
+    if (lat->d_queue)
+        CUDA_TRY(cudaMemcpyAsync(&queue_err, (const unsigned long long *)lat->d_queue + 1, sizeof(queue_err),
+                                 cudaMemcpyDeviceToHost, lat->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
     CUDA_TRY(cudaGetLastError());
+    REQUIRE(queue_err == 0, MCX_ERR_CUDA, "sweep series (ticket queue): a dependency wait timed out; the lattice is not valid");
     for (int c = 0; c < lat->nchains; ++c) {
         if (pair_sum) pair_sum[c] = h[(size_t)c * SUM_FIELDS + SUM_PAIR];
         if (spin_sum) spin_sum[c] = h[(size_t)c * SUM_FIELDS + SUM_SPIN];

@@ -45,6 +45,8 @@ struct mcx_lattice {
     cudaStream_t copy_stream;
     cudaEvent_t ev_copied, ev_packed;   // copy finished; last conversion out of d_staging finished
     bool upload_pending, packed_recorded;
+    void *d_queue;              // k_queue.cu: ticket counter, error flag and per-item progress words
+    size_t queue_bytes;
     bool fast2d;                // Lx % 32 == 0 && ndim == 2: row-aligned 128-bit kernels apply
     bool track_sums;            // fast kernels accumulate pair/spin sums per flip (else recompute lazily)
     bool sums_dirty;            // pair/spin sums are stale (untracked sweeps ran)
@@ -95,6 +97,8 @@ namespace mcx {
 struct Knobs {
     int rows_per_strip, ctas_per_sm, variant, full, groups, bands, bc2d, ising3d;
     int resident, resident_cluster, resident_rows, resident_threads, force_generic;
+    int queue_rows;   // MCX_QUEUE_ROWS: strip height of the ticket-queue kernel (tuning hook)
+    int queue;        // MCX_QUEUE: 1 = series of sweeps through the ticket-queue kernel (k_queue.cu)
     int wl_spec;      // MCX_WL_SPEC: Wang-Landau attempts decided at once (0 = serial loop, 8, 32; unset = adaptive)
 };
 const Knobs &knobs();
@@ -142,6 +146,9 @@ bool launch_recompute_ising2d(mcx_lattice *lat);
 bool launch_pack_ising2d(mcx_lattice *lat);
 bool launch_unpack_ising2d(mcx_lattice *lat);
 bool launch_init_ising2d(mcx_lattice *lat, int mode, uint64_t seed);                        // false: shape not supported
+
+// k_queue.cu: nsweeps whole sweeps in one launch, work items of all half-sweeps taken from one ticket counter
+bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps);   // false: not applicable, nothing launched
 
 // k_rows8.cu
 bool launch_sweep_rows8(mcx_lattice *lat, int colour, uint64_t t);     // false: shape not supported
