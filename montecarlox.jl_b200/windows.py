@@ -17,6 +17,12 @@ adds is therefore defined here, on top of the reference's per-attempt rule:
 * windows are independent units: they are dealt to the ranks in contiguous blocks with NO data-path
   collective while sampling; `logdos()` all-gathers the window pieces (a few KB to MB, once) and every
   rank joins them at the overlaps on the host;
+* optionally (`exchange_`) walkers of neighbouring windows swap configurations -- the reference's replica
+  exchange (`exchange_log_ratio` / `_accept_exchange`, replica_exchange.jl:110-115, even / odd pair stages
+  :158-178) with the two windows' Wang-Landau tables as the two ensembles, attempted only when both energies
+  lie in both windows; across ranks only the walkers' energies, two table differences per walker pair and the
+  accepted configurations move (point-to-point), and `u` is the counter-based EXCHANGE stream, so every rank
+  takes the same decisions;
 * random streams are keyed by the GLOBAL walker number (window * walkers + walker), so the joined result
   does not depend on how many ranks the windows were dealt to.
 
@@ -35,7 +41,8 @@ import numpy as np
 from . import _lib
 from ._lib import McxError, check, lib
 from .binned_object import BinnedObject
-from .parallel import GPUBackend, partition_slots
+from .parallel import GPUBackend, _accept_exchange, partition_slots
+from .rng import exchange_u
 from .tables import build_table
 
 
@@ -218,6 +225,11 @@ class WangLandauWindows:
         self._lw_stage = [None] * self.count    # tables at the start of the current logf stage
         self.steps = 0
         self.prepared = False
+        # neighbour-window exchange: stage parity and round as in ReplicaExchange (replica_exchange.jl:13-19);
+        # attempts / acceptances per window pair (w, w + 1), counted on the rank that owns window w
+        self.exchange_stage, self.exchange_round = 0, 0
+        self.exchange_steps = np.zeros(max(self.nwindows - 1, 0), dtype=np.int64)
+        self.exchange_accepted = np.zeros(max(self.nwindows - 1, 0), dtype=np.int64)
         # drive parameters
         self.beta_max, self.drive_sweeps, self.drive_check, self.drive_trials = 2.0, 24, 1, 48
 
@@ -327,16 +339,142 @@ class WangLandauWindows:
         self.logf *= power
         return None
 
-    def run_(self, logf_final, sweeps_per_stage, flatness=None, max_checks=20):
+    def run_(self, logf_final, sweeps_per_stage, flatness=None, max_checks=20, exchange_every=None):
         """Stages of `sweeps_per_stage` sweeps until logf <= logf_final.  With `flatness` set a stage is
-        extended (up to max_checks times) until every window of every rank reaches it."""
+        extended (up to max_checks times) until every window of every rank reaches it.  With `exchange_every`
+        set the sweeps of a stage come in blocks of that many, each followed by one exchange stage."""
         while self.logf > logf_final:
             for _ in range(max_checks):
-                self.sweep_(sweeps_per_stage)
+                if exchange_every:
+                    done = 0
+                    while done < sweeps_per_stage:
+                        n = min(int(exchange_every), sweeps_per_stage - done)
+                        self.sweep_(n)
+                        self.exchange_()
+                        done += n
+                else:
+                    self.sweep_(sweeps_per_stage)
                 if flatness is None or self._all_min(min(self.flatness())) >= flatness:
                     break
             self.update_()
         return self
+
+    # ---- replica exchange between neighbouring windows
+    def _owner(self, w):
+        return w // self.count if self.count else 0
+
+    def _table_terms(self, j, E_mine, E_other):
+        """per walker c of local window j: lw(E_other[c]) - lw(E_mine[c]) on the walker's own table, or NaN when
+        E_other[c] is outside the window (then the pair is not attempted)"""
+        lo, _ = self.window_energies(self.first + j)
+        step = self.bins.step
+        out = np.full(self.walkers, np.nan)
+        for c in range(self.walkers):
+            d = int(E_other[c]) - lo
+            if d >= 0 and d % step == 0 and d // step < self.width:
+                out[c] = self._lw[j][c, d // step] - self._lw[j][c, (int(E_mine[c]) - lo) // step]
+        return out
+
+    def _p2p(self, peer, send, recv):
+        """exchange two equally shaped numpy arrays with rank `peer` (tensors on the device under NCCL)"""
+        import torch
+        dist = self.backend._dist
+        on_gpu = dist.get_backend(self.backend.group) == "nccl"
+        dev = "cuda:%d" % self.device if on_gpu else "cpu"
+        t_out = torch.from_numpy(np.ascontiguousarray(send)).to(dev)
+        t_in = torch.empty_like(t_out)
+        ops = [dist.P2POp(dist.isend, t_out, peer, group=self.backend.group),
+               dist.P2POp(dist.irecv, t_in, peer, group=self.backend.group)]
+        if self.backend.rank > peer:
+            ops.reverse()
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        recv[...] = t_in.cpu().numpy()
+
+    def exchange_(self):
+        """One exchange stage: window pairs (w, w + 1) with w = stage (mod 2), walker c with walker c.
+        log_ratio = [lw_w(E') - lw_w(E)] + [lw_w+1(E) - lw_w+1(E')] (exchange_log_ratio, replica_exchange.jl:110-113);
+        accepted = log_ratio > 0 || u < exp(log_ratio) (:115); on accept the two CONFIGURATIONS change places (the
+        tables belong to the windows).  Call between sweep_ calls; the tables are not touched."""
+        if not self.prepared:
+            raise AssertionError("call prepare_() first")
+        k, me = self.walkers, self.backend.rank
+        energies = {j: np.asarray(self.local[j].energies(), dtype=np.int64) for j in range(self.count)}
+        spins_cache = {}
+
+        def spins_of(j):
+            if j not in spins_cache:
+                spins_cache[j] = self.local[j].spins().copy()
+            return spins_cache[j]
+
+        dirty = set()
+        for w in range(self.exchange_stage % 2, self.nwindows - 1, 2):
+            lo_rank, hi_rank = self._owner(w), self._owner(w + 1)
+            if me not in (lo_rank, hi_rank):
+                continue
+            i_am_lo, i_am_hi = me == lo_rank, me == hi_rank
+            j_lo, j_hi = w - self.first, w + 1 - self.first
+            # energies of both sides
+            E_lo = energies[j_lo] if i_am_lo else np.empty(k, dtype=np.int64)
+            E_hi = energies[j_hi] if i_am_hi else np.empty(k, dtype=np.int64)
+            if lo_rank != hi_rank:
+                if i_am_lo:
+                    self._p2p(hi_rank, E_lo, E_hi)
+                else:
+                    self._p2p(lo_rank, E_hi, E_lo)
+            # each side evaluates the difference on its own tables
+            d_lo = self._table_terms(j_lo, E_lo, E_hi) if i_am_lo else np.empty(k)
+            d_hi = self._table_terms(j_hi, E_hi, E_lo) if i_am_hi else np.empty(k)
+            if lo_rank != hi_rank:
+                if i_am_lo:
+                    self._p2p(hi_rank, d_lo, d_hi)
+                else:
+                    self._p2p(lo_rank, d_hi, d_lo)
+            swap = np.zeros(k, dtype=bool)
+            for c in range(k):
+                if np.isnan(d_lo[c]) or np.isnan(d_hi[c]):
+                    continue                                            # an energy outside the other window: no attempt
+                u = exchange_u(self.seed, w * k + c, self.exchange_round)
+                swap[c] = _accept_exchange(float(d_lo[c] + d_hi[c]), u)
+                if i_am_lo:
+                    self.exchange_steps[w] += 1
+                    self.exchange_accepted[w] += int(swap[c])
+            if not swap.any():
+                continue
+            if lo_rank == hi_rank:
+                a, b = spins_of(j_lo), spins_of(j_hi)
+                tmp = a[swap].copy()
+                a[swap] = b[swap]
+                b[swap] = tmp
+                energies[j_lo], energies[j_hi] = np.where(swap, E_hi, E_lo), np.where(swap, E_lo, E_hi)
+                dirty.update((j_lo, j_hi))
+            else:
+                j_mine, peer = (j_lo, hi_rank) if i_am_lo else (j_hi, lo_rank)
+                mine = spins_of(j_mine)
+                incoming = np.empty_like(mine[swap])
+                self._p2p(peer, mine[swap], incoming)
+                mine[swap] = incoming
+                energies[j_mine] = np.where(swap, E_hi, E_lo) if i_am_lo else np.where(swap, E_lo, E_hi)
+                dirty.add(j_mine)
+        for j in dirty:
+            self.local[j].set_spins(spins_cache[j])
+        self.exchange_stage = 1 - self.exchange_stage
+        self.exchange_round += 1
+        return None
+
+    def exchange_rates(self):
+        """acceptance rate per window pair (acceptance_rates(rx), replica_exchange.jl:64-74), on every rank"""
+        if self.nwindows < 2:
+            return np.zeros(0)
+        st, ac = self.exchange_steps.astype(np.float64), self.exchange_accepted.astype(np.float64)
+        if self.backend.size > 1:
+            import torch
+            t = self._tensor(2 * (self.nwindows - 1))
+            t[:] = torch.from_numpy(np.concatenate([st, ac])).to(t.device)
+            self.backend.all_reduce_sum(t)
+            v = t.cpu().numpy()
+            st, ac = v[:self.nwindows - 1], v[self.nwindows - 1:]
+        return np.where(st > 0, ac / np.maximum(st, 1), 0.0)
 
     def _all_min(self, value):
         if self.backend.size == 1:

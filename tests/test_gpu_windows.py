@@ -38,6 +38,12 @@ def test_windows_device_equals_oracle(m, oracle, dims, nwindows, walkers, overla
         for j in range(dev.count):
             assert np.array_equal(dev._lw[j], ref._lw[j]), (stage, j)
         assert dev.flatness() == ref.flatness()
+        dev.exchange_()                                              # neighbour-window exchange: same decisions, same swaps
+        ref.exchange_()
+        assert np.array_equal(dev.exchange_accepted, ref.exchange_accepted)
+        assert np.array_equal(dev.exchange_steps, ref.exchange_steps)
+        for a, b in zip(dev.spins(), ref.spins()):
+            assert np.array_equal(a, b)
         dev.update_()
         ref.update_()
     for a, b in zip(dev.spins(), ref.spins()):

@@ -139,6 +139,40 @@ def test_three_dimensional_windows_and_argument_errors(oracle):
         m.WangLandauWindows([8, 8], nwindows=3, walkers=0, window_factory=OracleWindow)
 
 
+def test_neighbour_window_exchange(oracle):
+    """exchange_: the reference's exchange rule (replica_exchange.jl:110-115) between walkers of neighbouring windows.
+    A stage permutes configurations (nothing is created or lost), keeps every walker inside its window, only pairs
+    whose energies both lie in the overlap are attempted, and the density of states still converges (RMSE < 0.3)."""
+    import hashlib
+    import mcx_b200 as m
+    from _window_engine import OracleWindow
+    wl = m.WangLandauWindows([8, 8], nwindows=4, walkers=2, overlap=0.5, seed=7, window_factory=OracleWindow)
+    wl.prepare_()
+    swaps = 0
+    for _ in range(40):
+        wl.sweep_(20)
+        before = [s.copy() for s in wl.spins()]
+        E_before = [e.copy() for e in wl.energies()]
+        acc0 = wl.exchange_accepted.sum()
+        wl.exchange_()
+        after, E_after = wl.spins(), wl.energies()
+        digest = lambda groups: sorted(hashlib.sha256(r.tobytes()).hexdigest() for g_ in groups for r in g_)
+        assert digest(before) == digest(after)
+        assert sorted(np.concatenate(E_before)) == sorted(np.concatenate(E_after))
+        changed = sum(int((a != b).any(axis=1).sum()) for a, b in zip(before, after))
+        assert changed <= 2 * (wl.exchange_accepted.sum() - acc0)       # identical configurations may swap unseen
+        swaps += wl.exchange_accepted.sum() - acc0
+        for w, E in enumerate(E_after):
+            lo, hi = wl.window_energies(w)
+            assert ((lo <= E) & (E <= hi)).all()
+    assert swaps > 0 and wl.exchange_round == 40 and wl.exchange_stage == 0
+    assert (wl.exchange_accepted <= wl.exchange_steps).all() and wl.exchange_steps.sum() <= 40 * 2 * 2
+    rates = wl.exchange_rates()
+    assert rates.shape == (3,) and (rates >= 0).all() and (rates <= 1).all()
+    wl.run_(2e-5, 2000, exchange_every=50)
+    assert rmse_vs_exact(wl.logdos(), exact_logdos(8)) < 0.3
+
+
 # ------------------------------------------------------------------ two ranks (gloo)
 def _free_port():
     s = socket.socket()
@@ -157,15 +191,16 @@ def _worker(rank, world, port, out):
     from _window_engine import OracleWindow
     wl = m.WangLandauWindows([8, 8], nwindows=4, walkers=2, seed=7, backend=m.GPUBackend(), window_factory=OracleWindow)
     assert (wl.first, wl.count) == (2 * rank, 2)
-    wl.prepare_().run_(0.05, 300, flatness=0.5, max_checks=3)
-    np.save(os.path.join(out, "rank%d.npy" % rank), wl.logdos().values)
+    wl.prepare_().run_(0.05, 300, flatness=0.5, max_checks=3, exchange_every=25)
+    np.save(os.path.join(out, "rank%d.npy" % rank), np.concatenate([wl.logdos().values, wl.exchange_rates()]))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_two_ranks_join_to_the_single_rank_result(tmp_path, oracle):
-    """Windows dealt to two ranks (no collective while sampling, one all-gather of the pieces): both ranks hold
-    the same joined table, and it is bit-identical to the one-rank run (streams keyed by global walker)."""
+    """Windows dealt to two ranks (no collective while sampling, point-to-point neighbour-window exchanges, one
+    all-gather of the pieces): both ranks hold the same joined table and exchange statistics, bit-identical to the
+    one-rank run (streams keyed by global walker, exchange decisions by the counter-based EXCHANGE stream)."""
     import torch.multiprocessing as mp
     import mcx_b200 as m
     from _window_engine import OracleWindow
@@ -174,7 +209,8 @@ def test_two_ranks_join_to_the_single_rank_result(tmp_path, oracle):
     r0, r1 = (np.load(os.path.join(str(tmp_path), "rank%d.npy" % r)) for r in range(world))
     assert np.array_equal(r0, r1, equal_nan=True)
     wl = m.WangLandauWindows([8, 8], nwindows=4, walkers=2, seed=7, window_factory=OracleWindow)
-    wl.prepare_().run_(0.05, 300, flatness=0.5, max_checks=3)
-    assert np.array_equal(wl.logdos().values, r0, equal_nan=True)
+    wl.prepare_().run_(0.05, 300, flatness=0.5, max_checks=3, exchange_every=25)
+    assert np.array_equal(np.concatenate([wl.logdos().values, wl.exchange_rates()]), r0, equal_nan=True)
+    assert wl.exchange_accepted.sum() > 0                             # pairs (0,1), (2,3) inside a rank, (1,2) across ranks
     with pytest.raises(ValueError):                                # 4 windows do not divide over 3 ranks
         m.partition_slots(4, 3, 0)
