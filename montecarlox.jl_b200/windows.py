@@ -117,7 +117,8 @@ class DeviceWindow:
         self.sys = Ising(self.dims, nchains=self.k, ctx=self.ctx)
         check(lib().mcx_lattice_set_first_chain_id(self.sys.h_lat, int(first_chain)))
         self.sys._first_chain = int(first_chain)
-        self.sys.set_rng(int(seed), 0)
+        self.sys_seed = int(seed)
+        self.sys.set_rng(self.sys_seed, 0)
         self.h_flat = None
         self.nbins = 0
 
@@ -131,6 +132,13 @@ class DeviceWindow:
     def energies(self):
         """E = -sum_pair_interactions per walker (ising.jl:175-177 with J = 1, h = 0), int64[k]"""
         return -self.sys._sums()[0]
+
+    # ---- position of the random streams: one sweep counter per lattice, shared by both kinds of sweep
+    def get_sweep(self):
+        return int(self.sys.sweep_index)
+
+    def set_sweep(self, n):
+        self.sys.set_rng(self.sys_seed, int(n))
 
     # ---- canonical checkerboard sweeps (the drive into the window)
     def canonical_(self, rule, beta, nsweeps):
@@ -191,7 +199,7 @@ class WangLandauWindows:
     """
 
     def __init__(self, dims, nwindows, walkers=1, overlap=0.5, seed=42, logf=1.0, bins=None, backend=None,
-                 device=None, window_factory=None):
+                 device=None, window_factory=None, windows=None):
         self.dims = [int(d) for d in dims]
         if len(self.dims) not in (2, 3) or any(d % 2 or d < 4 for d in self.dims):
             raise ValueError("windowed Wang-Landau needs a 2-D or 3-D lattice with even dimensions >= 4")
@@ -205,7 +213,9 @@ class WangLandauWindows:
         self.nwindows, self.walkers = int(nwindows), int(walkers)
         if self.walkers < 1:
             raise ValueError("walkers must be >= 1")
-        self.windows = partition_windows(len(bins), self.nwindows, overlap)
+        self.windows = [tuple(w) for w in windows] if windows is not None else partition_windows(len(bins), self.nwindows, overlap)
+        if len(self.windows) != self.nwindows or len({n for _, n in self.windows}) != 1:
+            raise ValueError("need nwindows windows of equal width")
         self.width = self.windows[0][1]
         self.seed, self.logf = int(seed), float(logf)
         if not (self.logf > 0):
@@ -521,6 +531,44 @@ class WangLandauWindows:
         out = BinnedObject(self.bins, np.nan)
         out.values[...] = g
         return out
+
+    # ---- checkpoint / restart (cf. checkpoint!/restore_checkpoint, src/infrastructure/checkpointing.jl:48-101, and
+    #      docs/src/examples/spin_systems/checkpoint_Ising2D.jl:40-106: the restarted run continues the same trajectory)
+    def state(self):
+        """Everything this rank needs to continue the run: plain numpy / Python values (picklable)."""
+        if not self.prepared:
+            raise AssertionError("nothing to checkpoint before prepare_()")
+        return {"dims": self.dims, "bins": (self.bins.start, self.bins.stop, self.bins.step), "nwindows": self.nwindows,
+                "walkers": self.walkers, "windows": list(self.windows), "seed": self.seed, "logf": self.logf,
+                "rank": self.backend.rank, "size": self.backend.size, "steps": self.steps,
+                "exchange": (self.exchange_stage, self.exchange_round, self.exchange_steps.copy(), self.exchange_accepted.copy()),
+                "spins": [eng.spins().copy() for eng in self.local], "sweep": [eng.get_sweep() for eng in self.local],
+                "lw": [a.copy() for a in self._lw], "lw_stage": [a.copy() for a in self._lw_stage]}
+
+    @classmethod
+    def restore(cls, st, backend=None, device=None, window_factory=None):
+        """Rebuild the driver of this rank from `state()`; the same rank layout is required."""
+        b = st["bins"]
+        self = cls(st["dims"], st["nwindows"], walkers=st["walkers"], seed=st["seed"], logf=st["logf"],
+                   bins=range(b[0], b[1], b[2]), backend=backend, device=device, window_factory=window_factory,
+                   windows=st["windows"])
+        if (self.backend.rank, self.backend.size) != (st["rank"], st["size"]):
+            raise ValueError("checkpoint of rank %d / %d restored on rank %d / %d"
+                             % (st["rank"], st["size"], self.backend.rank, self.backend.size))
+        self.steps = st["steps"]
+        self.exchange_stage, self.exchange_round = st["exchange"][0], st["exchange"][1]
+        self.exchange_steps[...] = st["exchange"][2]
+        self.exchange_accepted[...] = st["exchange"][3]
+        for j, eng in enumerate(self.local):
+            lo, _ = self.window_energies(self.first + j)
+            eng.set_spins(st["spins"][j])
+            eng.set_sweep(st["sweep"][j])
+            eng.open_window(lo, self.bins.step, self.width)
+            eng.set_logweight(st["lw"][j])
+            self._lw[j] = st["lw"][j].copy()
+            self._lw_stage[j] = st["lw_stage"][j].copy()
+        self.prepared = True
+        return self
 
     def spins(self):
         """[count][walkers, N] configurations of the local windows"""

@@ -31,6 +31,12 @@ class OracleWindow:
     def energies(self):
         return np.array([int(s.energy(full=True)) for s in self.sys], dtype=np.int64)
 
+    def get_sweep(self):
+        return self.sweep
+
+    def set_sweep(self, n):
+        self.sweep = int(n)
+
     def canonical_(self, rule, beta, nsweeps):
         for c, s in enumerate(self.sys):
             s.sweep_checkerboard(oracle.Alg(rule, float(beta)), self.seed, self.first_chain + c, self.sweep, int(nsweeps))

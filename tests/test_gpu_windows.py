@@ -79,3 +79,28 @@ def test_windows_run_concurrently_on_their_own_streams(m):
     assert all(w.ctx.launch_count() > b for w, b in zip(wl.local, before))
     assert all(v.sum() == 10 * 256 * 2 for v in wl.visits())
     wl.close()
+
+
+def test_windows_checkpoint_restart_on_device(m):
+    """state() / restore() on the device: the restarted run continues the uninterrupted run's trajectory"""
+    import pickle
+    kw = dict(nwindows=4, walkers=2, overlap=0.5, seed=3)
+    full = m.WangLandauWindows([16, 16], **kw).prepare_()
+    part = m.WangLandauWindows([16, 16], **kw).prepare_()
+    for wl in (full, part):
+        wl.run_(0.2, 60, exchange_every=20)
+    blob = pickle.dumps(part.state())
+    part.close()
+    resumed = m.WangLandauWindows.restore(pickle.loads(blob))
+    for wl in (full, resumed):
+        wl.sweep_(25)
+        wl.exchange_()
+        wl.run_(0.04, 60, exchange_every=20)
+    for a, b in zip(full._lw, resumed._lw):
+        assert np.array_equal(a, b)
+    for a, b in zip(full.spins(), resumed.spins()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(full.exchange_accepted, resumed.exchange_accepted)
+    assert np.array_equal(full.logdos().values, resumed.logdos().values, equal_nan=True)
+    full.close()
+    resumed.close()

@@ -173,6 +173,43 @@ def test_neighbour_window_exchange(oracle):
     assert rmse_vs_exact(wl.logdos(), exact_logdos(8)) < 0.3
 
 
+def test_checkpoint_restart_continues_the_trajectory(oracle, tmp_path):
+    """state() / restore(): like the reference's checkpoint example (checkpoint_Ising2D.jl:40-106), a restarted run
+    continues the same trajectory -- tables, configurations, exchange counters and the joined log g are identical to
+    the uninterrupted run."""
+    import pickle
+    import mcx_b200 as m
+    from _window_engine import OracleWindow
+    kw = dict(nwindows=4, walkers=2, overlap=0.5, seed=3, window_factory=OracleWindow)
+    full = m.WangLandauWindows([8, 8], **kw)
+    full.prepare_()
+    part = m.WangLandauWindows([8, 8], **kw)
+    with pytest.raises(AssertionError):
+        part.state()
+    part.prepare_()
+    for wl in (full, part):
+        wl.run_(0.2, 200, exchange_every=20)
+    path = tmp_path / "wl.ckpt"
+    with open(path, "wb") as fh:
+        pickle.dump(part.state(), fh)
+    part.close()
+    with open(path, "rb") as fh:
+        resumed = m.WangLandauWindows.restore(pickle.load(fh), window_factory=OracleWindow)
+    assert resumed.logf == full.logf and resumed.steps == full.steps
+    for wl in (full, resumed):
+        wl.sweep_(30)
+        wl.exchange_()
+        wl.run_(0.02, 200, exchange_every=20)
+    for a, b in zip(full._lw, resumed._lw):
+        assert np.array_equal(a, b)
+    for a, b in zip(full.spins(), resumed.spins()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(full.exchange_steps, resumed.exchange_steps)
+    assert np.array_equal(full.exchange_accepted, resumed.exchange_accepted)
+    assert np.array_equal(full.logdos().values, resumed.logdos().values, equal_nan=True)
+    assert full.flatness() == resumed.flatness()
+
+
 # ------------------------------------------------------------------ two ranks (gloo)
 def _free_port():
     s = socket.socket()
