@@ -185,6 +185,12 @@ class DeviceWindow:
         if ctx is not None:
             ctx.close()
 
+    def __del__(self):
+        try:                      # tables before the lattice, the lattice before its context
+            self.close()
+        except Exception:
+            pass
+
 
 # --------------------------------------------------------------------------- the driver
 class WangLandauWindows:
