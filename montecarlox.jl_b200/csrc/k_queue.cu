@@ -20,6 +20,11 @@ namespace mcx {
 namespace {
 
 constexpr int kThreads = 128;
+// resident CTAs per SM the kernel is compiled for.  5 (96 registers) is what was measured in round 1; 6 compiles to 80
+// registers without spills (ptxas) and is the first thing to A/B: scripts/build_variant.sh q6 "-DMCX_QUEUE_MINB=6"
+#ifndef MCX_QUEUE_MINB
+#define MCX_QUEUE_MINB 5
+#endif
 
 enum { Q_TICKET = 0, Q_ERR = 1, Q_WORDS = 2 };
 
@@ -141,7 +146,7 @@ __device__ __forceinline__ void queue_item(const LatView &L, const int chain, co
 }
 
 template <bool HEATBATH, bool TRACK>
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, MCX_QUEUE_MINB)
 k_ising2d_queue(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
                 const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
                 uint64_t t0, uint64_t nhalf, uint32_t first_chain, int R, int nstrips, int ipc /* items per chain and half-sweep */,
