@@ -51,3 +51,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("the oracle", "").replace("and to the oracle", "") or f == "k_ising2d.cu", f
+
+
+def test_scripts_and_bench_parse():
+    """the measurement scripts only run on a GPU box; at least make sure they are valid Python here"""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "scripts", "*.py")) + [os.path.join(root, "bench.py"),
+                                                                 os.path.join(root, "__graft_entry__.py")]
+    assert len(files) >= 8
+    for f in files:
+        with open(f) as fh:
+            ast.parse(fh.read(), filename=f)
