@@ -346,6 +346,63 @@ local_pair_sum(sys::SlabIsing) = sums(sys.part)[1]
 local_spin_sum(sys::SlabIsing) = sums(sys.part)[2]
 
 # ----------------------------------------------------------------------------------------------
+# 5b. Multicanonical chains on the device and the whole parallel-tempering loop in one call.
+#     The reference's host objects stay the source of truth: `ens.logweight.values` / `ens.histogram.values`
+#     are ordinary Float64 arrays that the examples read and modify (muca_Ising2D.jl:36-39,89-90); the device
+#     mirror is refreshed from / into them around every sweep! call.
+# ----------------------------------------------------------------------------------------------
+mutable struct DeviceMulticanonical
+    h::Ptr{Cvoid}              # mcx_flat, kind MUCA: ONE log-weight table and ONE histogram shared by all chains of `sys`
+    sys::DeviceIsing
+    alg                        # ImportanceSampling{<:MulticanonicalEnsemble} (algorithms/multicanonical.jl:9-25)
+end
+
+function DeviceMulticanonical(sys::DeviceIsing, alg)
+    ens = MonteCarloX.ensemble(alg)::MonteCarloX.MulticanonicalEnsemble
+    b = ens.logweight.bins[1]                                   # DiscreteBinning(start, step, num), binned_object.jl:13-17
+    out = Ref{Ptr{Cvoid}}()
+    check(ccall((:mcx_flat_create, libmcx), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Int64, Int64, Int64, Float64, Int32, Ref{Ptr{Cvoid}}),
+                sys.h, 0, 0, b.start, b.step, b.num, 0.0, 0, out))           # policy 0: out of range = BoundsError
+    rng = alg.rng::PhiloxRNG
+    check(ccall((:mcx_lattice_set_first_chain_id, libmcx), Int32, (Ptr{Cvoid}, UInt32), sys.h, rng.chain))
+    return DeviceMulticanonical(out[], sys, alg)
+end
+
+"n*N attempts per chain: spin_flip!(sys, alg::ImportanceSampling) (ising.jl:25-33) with record_visit! (multicanonical.jl:25-30)"
+function sweep!(mc::DeviceMulticanonical, nsweeps::Integer=1)
+    ens = MonteCarloX.ensemble(mc.alg)
+    lw, hist = ens.logweight.values, ens.histogram.values
+    acc0 = sum(sums(mc.sys)[4])
+    GC.@preserve lw check(ccall((:mcx_flat_set_logweight, libmcx), Int32, (Ptr{Cvoid}, Ptr{Float64}), mc.h, lw))
+    all(iszero, hist) && check(ccall((:mcx_flat_reset_histogram, libmcx), Int32, (Ptr{Cvoid},), mc.h))   # after reset!(alg)
+    check(ccall((:mcx_flat_sweep, libmcx), Int32, (Ptr{Cvoid}, Int64), mc.h, nsweeps))
+    GC.@preserve hist check(ccall((:mcx_flat_get_histogram, libmcx), Int32, (Ptr{Cvoid}, Ptr{Float64}), mc.h, hist))
+    mc.alg.steps += nsweeps * prod(mc.sys.dims) * mc.sys.nchains               # importance_sampling.jl:81
+    mc.alg.accepted += sum(sums(mc.sys)[4]) - acc0
+    return nothing
+end
+# update!(ensemble(alg)) and reset!(alg) are the reference's own methods on the host arrays
+# (ensembles/multicanonical.jl:32-44, algorithms/multicanonical.jl:27-33); nothing to override.
+
+"merge_histograms! over ranks (parallel_multicanonical.jl:38-52): one all-reduce on the device histogram; every rank then
+ applies the same update!, which replaces the Bcast of distribute_logweight! (:59-73)"
+function merge_histograms!(mc::DeviceMulticanonical, allreduce_sum!::Function)
+    p = Ref{Ptr{Cvoid}}(); n = Ref{Int64}()
+    check(ccall((:mcx_flat_device_histogram, libmcx), Int32, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}, Ref{Int64}), mc.h, p, n))
+    allreduce_sum!(Ptr{UInt64}(p[]), n[])                        # NCCL.jl / CUDA-aware MPI.jl on the device pointer
+    hist = MonteCarloX.ensemble(mc.alg).histogram.values
+    GC.@preserve hist check(ccall((:mcx_flat_get_histogram, libmcx), Int32, (Ptr{Cvoid}, Ptr{Float64}), mc.h, hist))
+    return nothing
+end
+
+"the user loop `for i in 1:n; sweeps; i % interval == 0 && update!(pt); end` (pt_Ising2D.jl:52-57) queued in one call"
+function run!(rx::DeviceReplicaExchange, nrounds::Integer, sweeps_per_round::Integer)
+    check(ccall((:mcx_pt_run, libmcx), Int32, (Ptr{Cvoid}, Int64, Int64), rx.h, nrounds, sweeps_per_round))
+    return nothing
+end
+
+# ----------------------------------------------------------------------------------------------
 # 6. Wang-Landau in energy windows (BASELINE.json configs[4]; beyond the reference, whose lookups outside the
 #    binned range throw BoundsError, test/test_multicanonical.jl:39-43).  One DeviceIsing batch per window
 #    (one chain per walker, own DeviceCtx = own stream), `mcx_flat_create(..., out_of_range_policy = 1)`:
