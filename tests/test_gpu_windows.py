@@ -104,3 +104,52 @@ def test_windows_checkpoint_restart_on_device(m):
     assert np.array_equal(full.logdos().values, resumed.logdos().values, equal_nan=True)
     full.close()
     resumed.close()
+
+
+_WINDOWS_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+ngpu = torch.cuda.device_count()
+torch.cuda.set_device(rank %% ngpu)
+dist.init_process_group("gloo", rank=rank, world_size=world)
+import mcx_b200 as m
+
+def run(backend):
+    wl = m.WangLandauWindows([16, 16], nwindows=4, walkers=2, overlap=0.5, seed=11, backend=backend, device=rank %% ngpu)
+    wl.prepare_().run_(0.1, 120, flatness=0.3, max_checks=2, exchange_every=20)
+    out = np.concatenate([wl.logdos().values, wl.exchange_rates()])
+    accepted = int(wl.exchange_accepted.sum())
+    wl.close()
+    return out, accepted
+
+got, _ = run(m.GPUBackend())                 # windows 0-1 on rank 0, 2-3 on rank 1; pair (1, 2) crosses the ranks
+dist.barrier()
+ok = True
+if rank == 0:
+    class One(m.GPUBackend):                 # all four windows on one rank, nothing exchanged between processes
+        rank = property(lambda self: 0); size = property(lambda self: 1)
+    ref, accepted = run(One())
+    ok = bool(np.array_equal(got, ref, equal_nan=True) and accepted > 0)
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"ok": ok}))
+dist.destroy_process_group()
+'''
+
+
+def test_windows_over_two_processes_equal_one_process(m, tmp_path):
+    """windows dealt to two processes (gloo for the plumbing, the device for everything else): cross-rank neighbour
+    exchange and the final all-gather give the one-process result bit for bit"""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "wl_worker.py"
+    script.write_text(_WINDOWS_WORKER % {"root": root})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29671", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    assert res["ok"], res
