@@ -79,6 +79,13 @@ int32_t mcx_ctx_info(mcx_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t
                      uint64_t *total_mem_bytes);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int32_t mcx_ctx_launch_count(mcx_ctx *ctx, uint64_t *count);
+/* Device-side waits (ticket-queue dependencies, slab neighbours, replica-exchange peers) give up after 10-25 s
+ * instead of hanging the GPU and store a code into a zero-copy error word of the context.  Every later call on
+ * the context (mcx_sweep, mcx_ctx_sync, mcx_observables, mcx_pt_run, mcx_pt_state, ...) then fails at once with
+ * MCX_ERR_CUDA -- no synchronisation is needed to see it; the reference has no counterpart (its MPI waits block).
+ * mcx_ctx_async_error reads the code (0: none) without failing; mcx_ctx_clear_error synchronises and resets it. */
+int32_t mcx_ctx_async_error(mcx_ctx *ctx, int32_t *code);
+int32_t mcx_ctx_clear_error(mcx_ctx *ctx);
 
 /* ---- lattice: SpinSystems Ising / BlumeCapel constructors ---------------------------------
  * mcx_lattice_create  <- Ising(dims) ising.jl:413, IsingLatticeOptim(Lx,Ly) ising.jl:441,
@@ -205,9 +212,16 @@ int32_t mcx_pt_peer_status(mcx_pt *pt, int32_t *timed_out);
 /* update!(rx, xs): all pairs of the current stage decided on the device with
  * u = EXCHANGE stream of the lower slot (replica_exchange.jl:168), labels swapped, stage toggled */
 int32_t mcx_pt_exchange(mcx_pt *pt);
-/* the user loop of pt_Ising2D.jl:52-57 (sweeps, update!(pt) every `interval` sweeps) queued in one call:
- * nrounds x (sweeps_per_round sweeps, publish, exchange); one rank or attached peers, else MCX_ERR_UNSUPPORTED */
+/* the user loop of pt_Ising2D.jl:52-57 (sweeps, update!(pt) every `interval` sweeps) in one call:
+ * nrounds x (sweeps_per_round sweeps, publish, exchange); one rank or attached peers, else MCX_ERR_UNSUPPORTED.
+ * For 2-D Ising int8 lattices with Lx % 32 == 0 all rounds run in ONE persistent kernel launch: the warp that
+ * finishes a round's last work item stores the energies into every rank's buffer (NVLink), waits for the other
+ * ranks' energies, decides the exchanges and releases the next round -- same decisions, same trajectories as
+ * mcx_sweep + mcx_pt_publish + mcx_pt_exchange per round (MCX_PT_PERSIST=0 forces that path). */
 int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round);
+/* how the last mcx_pt_run was executed: *path = 1 one persistent launch (*strip_rows = rows per work item), 0 = rounds
+ * queued from the host.  Diagnostics for bench.py and the tests. */
+int32_t mcx_pt_run_info(mcx_pt *pt, int32_t *path, int32_t *strip_rows);
 int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices /*[n] 1-based*/, int64_t *steps /*[n-1]*/,
                      int64_t *accepted /*[n-1]*/, int64_t *stage, int64_t *round);
 int32_t mcx_pt_reset(mcx_pt *pt);

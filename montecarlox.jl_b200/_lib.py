@@ -43,6 +43,8 @@ SIGNATURES = {
     "mcx_ctx_sync": (_i32, [_vp]),
     "mcx_ctx_info": (_i32, [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_u64)]),
     "mcx_ctx_launch_count": (_i32, [_vp, _P(_u64)]),
+    "mcx_ctx_async_error": (_i32, [_vp, _P(_i32)]),
+    "mcx_ctx_clear_error": (_i32, [_vp]),
     "mcx_lattice_create": (_i32, [_vp, _i32, _i32, _P(_i32), _i32, _i32, _P(_vp)]),
     "mcx_lattice_destroy": (_i32, [_vp]),
     "mcx_lattice_set_couplings": (_i32, [_vp, _dbl, _dbl, _dbl]),
@@ -65,6 +67,7 @@ SIGNATURES = {
     "mcx_recompute": (_i32, [_vp]),
     "mcx_set_tracking": (_i32, [_vp, _i32]),
     "mcx_pt_run": (_i32, [_vp, _i64, _i64]),
+    "mcx_pt_run_info": (_i32, [_vp, _P(_i32), _P(_i32)]),
     "mcx_pt_export": (_i32, [_vp, _vp]),
     "mcx_pt_attach_peers": (_i32, [_vp, _i32, _i32, _vp]),
     "mcx_pt_peer_status": (_i32, [_vp, _P(_i32)]),

@@ -34,7 +34,7 @@ constexpr int kThreads = 128;
 
 // Cross-GPU ordering of a slab's half-sweep t (k_slab.cu): its boundary strips may start once both
 // neighbours have finished the boundary strips of their half-sweep t - 1 ...
-__device__ __forceinline__ void slab_wait(unsigned long long *ctl, uint64_t t, int sides)
+__device__ __forceinline__ void slab_wait(unsigned long long *ctl, uint64_t t, int sides, int *err)
 {
     const volatile unsigned long long *f = ctl;
     const unsigned long long need = t - f[SLAB_T0];
@@ -43,7 +43,11 @@ __device__ __forceinline__ void slab_wait(unsigned long long *ctl, uint64_t t, i
     while (((sides & 1) && f[SLAB_FLAG_UP] < need) || ((sides & 2) && f[SLAB_FLAG_DN] < need)) {
         __nanosleep(100);
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 20000000000ull) { ctl[SLAB_ERR] = 1; break; }     // 20 s: give up rather than hang the GPU
+        if (t1 - t0 > 20000000000ull) {                                 // 20 s: give up rather than hang the GPU
+            ctl[SLAB_ERR] = 1;
+            if (err) { *(volatile int *)err = ASYNC_ERR_SLAB; __threadfence_system(); }   // seen by the host's next call
+            break;
+        }
     }
     __threadfence_system();
 }
@@ -134,7 +138,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             strip = strip == 0 ? nstrips - 1 : strip - 1;
             boundary_item = L.slab_ctl != nullptr && (int64_t)item * kThreads < 2 * (int64_t)nseg;
             if (boundary_item) {
-                if (threadIdx.x == 0) slab_wait(L.slab_ctl, t, L.slab_sides);
+                if (threadIdx.x == 0) slab_wait(L.slab_ctl, t, L.slab_sides, L.err);
                 __syncthreads();
             }
         }
@@ -199,18 +203,34 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
                 if (edgeA) sideA = po[colA];
                 if (edgeB) sideB = po[half + colB];
             }
+#ifdef MCX_OPT_PHILOX_FIRST
+            // probe: generate the first row's Philox blocks before the loaded rows are first touched
+            const Philox4 ra = philox4x32_10(blk, t_lo, c2, chain_id, seed_lo, seed_hi);
+            const Philox4 rb = philox4x32_10(blk + 1, t_lo, c2, chain_id, seed_lo, seed_hi);
+            const uint32_t z = opaque_zero(ra.x ^ rb.x);
+            D.x |= z; D.y |= z; D.z |= z; D.w |= z;
+            Ta.x |= z; Ta.y |= z; Ta.z |= z; Ta.w |= z;
+            sideA |= z; sideB |= z;
+#else
+            const uint32_t z = 0;
+#endif
             uint32_t sA, sB;
             if (COLOUR == 0) {
-                sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
+                sA = __shfl_up_sync(0xffffffffu, C.w | z, 1) >> 24;
                 sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
             } else {
-                sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
+                sA = __shfl_down_sync(0xffffffffu, C.x | z, 1) & 0xffu;
                 sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
             }
             if (edgeA) sA = sideA;
             if (edgeB) sB = sideB;
+#ifdef MCX_OPT_PHILOX_FIRST
+            const uint4 Na = update_row_with<COLOUR, HEATBATH, TRACK>(ra, rb, Ta, U, C, D, sA, blk, t_lo, c2lo, chain_id, seed_lo,
+                                                                      seed_hi, s_pair, s_thi, s_tlo, acc, active);
+#else
             const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
                                                                  seed_hi, s_pair, s_thi, s_tlo, acc, active);
+#endif
 #ifndef MCX_OPT_INTERLEAVE_ROWS
             // finish (and store) row a before starting row b: fewer live registers, measured +4 %
             if (active) *reinterpret_cast<uint4 *>(pt) = Na;

@@ -23,7 +23,8 @@ __global__ void k_pt_publish(const long long *__restrict__ sums, double *__restr
 }
 
 // thread 0 of a block: wait until every rank has published round `value`; 20 s give up and raise *err
-__device__ __forceinline__ void pt_wait_all(const unsigned long long *arrived, int nranks, unsigned long long value, int *err)
+__device__ __forceinline__ void pt_wait_all(const unsigned long long *arrived, int nranks, unsigned long long value, int *err,
+                                            int *ctx_err)
 {
     const volatile unsigned long long *a = arrived;
     unsigned long long t0, t1;
@@ -32,7 +33,11 @@ __device__ __forceinline__ void pt_wait_all(const unsigned long long *arrived, i
         while (a[r] < value) {
             __nanosleep(100);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) { *err = 1; return; }
+            if (t1 - t0 > 20000000000ull) {
+                *err = 1;
+                if (ctx_err) { *(volatile int *)ctx_err = ASYNC_ERR_PT_PEERS; __threadfence_system(); }   // the host's next call fails
+                return;
+            }
         }
     __threadfence_system();
 }
@@ -42,10 +47,10 @@ __global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__
                               int32_t *__restrict__ slot_of, long long *__restrict__ steps,
                               long long *__restrict__ accepted, int32_t *__restrict__ labels, int nlocal,
                               int first_slot, uint32_t seed_lo, uint32_t seed_hi, const unsigned long long *arrived,
-                              int nranks, int *err)
+                              int nranks, int *err, int *ctx_err)
 {
     if (arrived) {      // energies arrive by peer stores: wait for every rank's publish of this round
-        if (threadIdx.x == 0) pt_wait_all(arrived, nranks, round + 1, err);
+        if (threadIdx.x == 0) pt_wait_all(arrived, nranks, round + 1, err, ctx_err);
         __syncthreads();
     }
     // 0-based pair k joins ladder indices k and k+1; stage 0 takes k = 0,2,4,.. (reference first=1)
@@ -119,7 +124,7 @@ void launch_pt_exchange(mcx_pt *pt)
     k_pt_exchange<<<blocks, 128, 0, lat->ctx->stream>>>(
         pt->n, pt->stage, pt->round, pt->d_betas, pt->d_x + (pt->peers ? (pt->round & 1) * pt->n : 0), pt->d_index, pt->d_slot_of,
         pt->d_steps, pt->d_accepted, lat->d_labels, lat->nchains, pt->first_slot, (uint32_t)lat->seed,
-        (uint32_t)(lat->seed >> 32), pt->peers ? pt->d_arrived : nullptr, pt->nranks, pt->d_err);
+        (uint32_t)(lat->seed >> 32), pt->peers ? pt->d_arrived : nullptr, pt->nranks, pt->d_err, lat->ctx->d_err);
     lat->ctx->launches++;
 }
 

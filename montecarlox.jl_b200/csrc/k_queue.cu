@@ -20,13 +20,14 @@ namespace mcx {
 namespace {
 
 constexpr int kThreads = 128;
-// resident CTAs per SM the kernel is compiled for.  5 (96 registers) is what was measured in round 1; 6 compiles to 80
-// registers without spills (ptxas) and is the first thing to A/B: scripts/build_variant.sh q6 "-DMCX_QUEUE_MINB=6"
+// resident CTAs per SM the kernel is compiled for.  5 (96 registers); 6 compiles to 80 registers without spills but was
+// measured 6-11 % slower at every batch size (37 M more warp instructions per 20 sweeps of 32 x 1024^2:
+// profiles/r02_queue_kernel.md)
 #ifndef MCX_QUEUE_MINB
 #define MCX_QUEUE_MINB 5
 #endif
 
-enum { Q_TICKET = 0, Q_ERR = 1, Q_WORDS = 2 };
+enum { Q_TICKET = 0, Q_WORDS = 2 };
 
 __device__ __forceinline__ uint4 ld_cg128(const uint8_t *p)
 {
@@ -192,7 +193,10 @@ k_ising2d_queue(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *_
                     while (ld_acquire(prog + dep) < (uint32_t)h) {
                         __nanosleep(64);
                         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-                        if (t_now - t_begin > 10000000000ull) { atomicExch(ctl + Q_ERR, 1ull); break; }   // 10 s: give up, never hang
+                        if (t_now - t_begin > 10000000000ull) {          // 10 s: give up, never hang; the host's next call fails
+                            if (L.err) { *(volatile int *)L.err = ASYNC_ERR_QUEUE_DEP; __threadfence_system(); }
+                            break;
+                        }
                     }
                 }
             }
@@ -218,7 +222,7 @@ k_ising2d_queue(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *_
 
 }  // namespace
 
-// nsweeps whole sweeps of lat->sweep .. in one launch; false: not applicable, nothing launched.
+// nsweeps whole sweeps of lat->sweep .. in one launch (advances lat->sweep); false: not applicable, nothing launched.
 // MCX_QUEUE=1: whenever the shape allows; =0: never; unset: small batches only -- a half-sweep of between half
 // and one and a half work items per resident CTA (e.g. the 32 replicas of 1024 x 1024 a parallel-tempering rank
 // holds at 8 GPUs: 1207 attempts/ns against 1018 with one launch per half-sweep and chain group,
@@ -264,18 +268,21 @@ bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps)
     }
     unsigned long long *ctl = (unsigned long long *)lat->d_queue;
     uint32_t *progress = (uint32_t *)(ctl + Q_WORDS);
+    LatView Lk = L;
+    Lk.err = ctx->d_err;                                       // a dependency wait that gives up raises the context's error word
     int64_t grid = grid_max;
     if (grid > per_half * 2) grid = per_half * 2;
     // 2^32 half-sweeps of progress per launch at most; chunk long series
     for (int64_t done = 0; done < nsweeps;) {
         const int64_t chunk = nsweeps - done < 500000000 ? nsweeps - done : 500000000;
         cudaMemsetAsync(lat->d_queue, 0, need, ctx->stream);
-        kern<<<(unsigned)grid, kThreads, 0, ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums, (uint32_t)lat->seed,
+        kern<<<(unsigned)grid, kThreads, 0, ctx->stream>>>(Lk, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums, (uint32_t)lat->seed,
                                                            (uint32_t)(lat->seed >> 32), 2 * (lat->sweep + (uint64_t)done),
                                                            2 * (uint64_t)chunk, lat->first_chain, R, nstrips, ipc, ctl, progress);
         ctx->launches++;
         done += chunk;
     }
+    lat->sweep += (uint64_t)nsweeps;
     return true;
 }
 

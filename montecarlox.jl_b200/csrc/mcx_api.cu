@@ -62,6 +62,7 @@ void knobs_refresh()
     k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
     k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
     k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
+    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST");
     g_knobs_ready = true;
 }
 const Knobs &knobs()
@@ -69,7 +70,31 @@ const Knobs &knobs()
     if (!g_knobs_ready) knobs_refresh();
     return g_knobs;
 }
+const char *async_error_text(int code)
+{
+    switch (code) {
+    case ASYNC_ERR_QUEUE_DEP: return "sweep series (ticket queue): a dependency wait timed out";
+    case ASYNC_ERR_SLAB: return "slab half-sweep: the wait for a neighbour GPU timed out";
+    case ASYNC_ERR_PT_PEERS: return "replica exchange: the wait for another rank's energies timed out";
+    case ASYNC_ERR_PT_ROUND: return "parallel-tempering rounds: the wait for the previous round's exchange timed out";
+    default: return "a device-side wait timed out";
+    }
+}
 }  // namespace mcx
+
+// A kernel that gave up a device-side wait has stored its code into the context's zero-copy error word: every later
+// call on the context fails at once (no synchronisation needed to see it) until mcx_ctx_clear_error.
+static int32_t async_error(mcx_ctx *ctx)
+{
+    const int code = ctx->h_err ? *(volatile int *)ctx->h_err : 0;
+    if (code == 0) return MCX_OK;
+    return fail(MCX_ERR_CUDA, "%s; lattices of this context are not valid (mcx_ctx_clear_error to go on)", async_error_text(code));
+}
+#define ASYNC_CHECK(ctx)                         \
+    do {                                         \
+        const int32_t a__ = async_error(ctx);    \
+        if (a__ != MCX_OK) return a__;           \
+    } while (0)
 
 
 extern "C" {
@@ -100,12 +125,22 @@ int32_t mcx_ctx_create(int32_t device, void *stream, mcx_ctx **out)
     c->cc_minor = prop.minor;
     c->total_mem = prop.totalGlobalMem;
     c->launches = 0;
+    c->h_err = c->d_err = nullptr;
+    if (cudaHostAlloc((void **)&c->h_err, sizeof(int) * 4, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&c->d_err, c->h_err, 0) != cudaSuccess) {
+        const cudaError_t he = cudaGetLastError();
+        if (c->h_err) cudaFreeHost(c->h_err);
+        delete c;
+        return fail(MCX_ERR_CUDA, "zero-copy error word: %s", cudaGetErrorString(he));
+    }
+    memset(c->h_err, 0, sizeof(int) * 4);
     if (stream) {
         c->stream = (cudaStream_t)stream;
         c->own_stream = false;
     } else {
         cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (se != cudaSuccess) {
+            cudaFreeHost(c->h_err);
             delete c;
             return fail(MCX_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
         }
@@ -124,6 +159,7 @@ int32_t mcx_ctx_destroy(mcx_ctx *ctx)
         for (int i = 0; i < 16; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->aux_join[i]); }
         cudaEventDestroy(ctx->aux_fork);
     }
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
     delete ctx;
     return MCX_OK;
 }
@@ -152,6 +188,23 @@ int32_t mcx_ctx_sync(mcx_ctx *ctx)
     REQUIRE(ctx, MCX_ERR_ARGUMENT, "ctx is NULL");
     CUDA_TRY(cudaSetDevice(ctx->device));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ASYNC_CHECK(ctx);
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_async_error(mcx_ctx *ctx, int32_t *code)
+{
+    REQUIRE(ctx && code, MCX_ERR_ARGUMENT, "NULL argument");
+    *code = ctx->h_err ? *(volatile int *)ctx->h_err : 0;
+    return MCX_OK;
+}
+
+int32_t mcx_ctx_clear_error(mcx_ctx *ctx)
+{
+    REQUIRE(ctx, MCX_ERR_ARGUMENT, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_err) *(volatile int *)ctx->h_err = 0;
     return MCX_OK;
 }
 
@@ -185,6 +238,7 @@ static void lattice_free(mcx_lattice *lat)
     cudaFree(lat->d_labels);
     cudaFree(lat->d_staging);
     cudaFree(lat->d_queue);
+    cudaFree(lat->d_series);
     if (lat->copy_stream) {
         cudaStreamSynchronize(lat->copy_stream);
         cudaStreamDestroy(lat->copy_stream);
@@ -236,6 +290,7 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
         return fail(MCX_ERR_CUDA, "device allocation failed: %s", cudaGetErrorString(e));
     }
     v.up_planes = v.dn_planes = v.planes; v.row_offset = 0; v.slab_sides = 3; v.slab_ctl = nullptr;
+    v.err = ctx->d_err;
     cudaMemsetAsync(lat->d_labels, 0, sizeof(int32_t) * (size_t)nchains, ctx->stream);
     cudaMemsetAsync(lat->d_sums, 0, sizeof(long long) * SUM_FIELDS * (size_t)nchains, ctx->stream);
     // constructors start all-up (ising.jl:118, blume_capel.jl:156)
@@ -459,6 +514,7 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");
     REQUIRE(nsweeps >= 0, MCX_ERR_ARGUMENT, "nsweeps must be >= 0");
     REQUIRE(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
+    ASYNC_CHECK(lat->ctx);
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     if (lat->track_sums && lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
     if (lat->slab) {
@@ -486,9 +542,8 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
     for (int64_t s = 0; s < nsweeps;) {
         if (try_series) {
             // MCX_QUEUE=1: the whole series in one launch, work items of all half-sweeps from one ticket counter
-            if (knobs().queue > 0 && launch_sweeps_ising2d_queue(lat, nsweeps - s)) {
+            if (knobs().queue > 0 && launch_sweeps_ising2d_queue(lat, nsweeps - s)) {      // advances lat->sweep itself
                 if (!lat->track_sums) lat->sums_dirty = true;
-                lat->sweep += (uint64_t)(nsweeps - s);
                 s = nsweeps;
                 continue;
             }
@@ -503,7 +558,6 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
             // small batches of lattices too big for shared memory: the ticket-queue series (its own policy, k_queue.cu)
             if (knobs().queue < 0 && launch_sweeps_ising2d_queue(lat, nsweeps - s)) {
                 if (!lat->track_sums) lat->sums_dirty = true;
-                lat->sweep += (uint64_t)(nsweeps - s);
                 s = nsweeps;
                 continue;
             }
@@ -541,9 +595,19 @@ int32_t mcx_sweep_series(mcx_lattice *lat, int64_t nmeasure, int64_t interval, i
     REQUIRE(nmeasure >= 0 && interval >= 1, MCX_ERR_ARGUMENT, "need nmeasure >= 0 and interval >= 1");
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     const size_t stride = (size_t)lat->nchains * SUM_FIELDS;
-    long long *d_series = nullptr;
     if (nmeasure == 0) return MCX_OK;
-    CUDA_TRY(cudaMalloc((void **)&d_series, sizeof(long long) * stride * (size_t)nmeasure));
+    ASYNC_CHECK(lat->ctx);
+    // the snapshot buffer belongs to the handle and only ever grows: no allocation (an implicit device
+    // synchronisation) inside a series once a handle has run one of this length
+    const size_t series_bytes = sizeof(long long) * stride * (size_t)nmeasure;
+    if (lat->series_bytes < series_bytes) {
+        CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+        cudaFree(lat->d_series);
+        lat->d_series = nullptr; lat->series_bytes = 0;
+        CUDA_TRY(cudaMalloc((void **)&lat->d_series, series_bytes));
+        lat->series_bytes = series_bytes;
+    }
+    long long *d_series = lat->d_series;
     const bool was_tracking = lat->track_sums;
     lat->track_sums = true;                       // the snapshots need current sums after every interval
     int32_t st = MCX_OK;
@@ -561,7 +625,7 @@ int32_t mcx_sweep_series(mcx_lattice *lat, int64_t nmeasure, int64_t interval, i
         if (e == cudaSuccess) e = cudaStreamSynchronize(lat->ctx->stream);
         if (e != cudaSuccess) st = fail(MCX_ERR_CUDA, "series copy failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_series);
+    if (st == MCX_OK) st = async_error(lat->ctx);
     if (lat->model == MCX_ISING && st == MCX_OK)
         for (int64_t i = 0; i < nmeasure * lat->nchains; ++i) out[i * SUM_FIELDS + SUM_SPIN2] = lat->N;
     return st;
@@ -585,13 +649,9 @@ int32_t mcx_observables(mcx_lattice *lat, int64_t *pair_sum, int64_t *spin_sum, 
     std::vector<long long> h((size_t)lat->nchains * SUM_FIELDS);
     CUDA_TRY(cudaMemcpyAsync(h.data(), lat->d_sums, h.size() * sizeof(long long), cudaMemcpyDeviceToHost,
                              lat->ctx->stream));
-    unsigned long long queue_err = 0;     // k_queue.cu: raised when a dependency wait gave up
-    if (lat->d_queue)
-        CUDA_TRY(cudaMemcpyAsync(&queue_err, (const unsigned long long *)lat->d_queue + 1, sizeof(queue_err),
-                                 cudaMemcpyDeviceToHost, lat->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
     CUDA_TRY(cudaGetLastError());
-    REQUIRE(queue_err == 0, MCX_ERR_CUDA, "sweep series (ticket queue): a dependency wait timed out; the lattice is not valid");
+    ASYNC_CHECK(lat->ctx);                // a device-side wait of an earlier sweep gave up
     for (int c = 0; c < lat->nchains; ++c) {
         if (pair_sum) pair_sum[c] = h[(size_t)c * SUM_FIELDS + SUM_PAIR];
         if (spin_sum) spin_sum[c] = h[(size_t)c * SUM_FIELDS + SUM_SPIN];
@@ -693,7 +753,7 @@ int32_t mcx_pt_destroy(mcx_pt *pt)
         if (p) cudaIpcCloseMemHandle(p);
     cudaFree(pt->d_betas); cudaFree(pt->d_x); cudaFree(pt->d_index); cudaFree(pt->d_slot_of);
     cudaFree(pt->d_steps); cudaFree(pt->d_accepted); cudaFree(pt->d_arrived); cudaFree(pt->d_err);
-    cudaFree(pt->d_peer_x); cudaFree(pt->d_peer_arrived);
+    cudaFree(pt->d_peer_x); cudaFree(pt->d_peer_arrived); cudaFree(pt->d_dev);
     delete pt;
     return MCX_OK;
 }
@@ -804,6 +864,7 @@ int32_t mcx_pt_peer_status(mcx_pt *pt, int32_t *timed_out)
 int32_t mcx_pt_publish(mcx_pt *pt)
 {
     REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    ASYNC_CHECK(pt->lat->ctx);
     CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
     refresh_sums(pt->lat);
     launch_pt_publish(pt);
@@ -813,6 +874,7 @@ int32_t mcx_pt_publish(mcx_pt *pt)
 int32_t mcx_pt_exchange(mcx_pt *pt)
 {
     REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    ASYNC_CHECK(pt->lat->ctx);
     CUDA_TRY(cudaSetDevice(pt->lat->ctx->device));
     launch_pt_exchange(pt);
     pt->stage = 1 - pt->stage;
@@ -825,11 +887,23 @@ int32_t mcx_pt_exchange(mcx_pt *pt)
 // without the host (one rank, or peer stores attached); otherwise MCX_ERR_UNSUPPORTED and the caller loops.
 int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round)
 {
+    knobs_refresh();
     REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
     REQUIRE(nrounds >= 0 && sweeps_per_round >= 1, MCX_ERR_ARGUMENT, "need nrounds >= 0 and sweeps_per_round >= 1");
     mcx_lattice *lat = pt->lat;
     REQUIRE(pt->peers || lat->nchains == pt->n, MCX_ERR_UNSUPPORTED,
             "replicas on other ranks: attach peers (mcx_pt_attach_peers) or drive publish / all-gather / exchange from the host");
+    REQUIRE(lat->rule >= 0, MCX_ERR_STATE, "no update rule set: call mcx_set_rule first");
+    ASYNC_CHECK(lat->ctx);
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    if (nrounds == 0) return MCX_OK;
+    // all rounds in ONE persistent launch (k_persist.cu): sweeps, energies to every rank, exchange, labels -- the
+    // host queues nothing between rounds
+    if (launch_pt_rounds_persistent(pt, nrounds, sweeps_per_round)) {
+        pt->last_path = 1;
+        return check_launch(lat->ctx);
+    }
+    pt->last_path = 0;
     // exchanging every sweep or two: keep the energy sums current per flip; longer intervals: recompute on publish
     lat->track_sums = sweeps_per_round < 3;
     for (int64_t r = 0; r < nrounds; ++r) {
@@ -841,12 +915,23 @@ int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round)
     return MCX_OK;
 }
 
+/* how the last mcx_pt_run was executed: path 1 = one persistent launch for all rounds (strip_rows = its strip
+ * height), 0 = rounds queued from the host */
+int32_t mcx_pt_run_info(mcx_pt *pt, int32_t *path, int32_t *strip_rows)
+{
+    REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
+    if (path) *path = pt->last_path;
+    if (strip_rows) *strip_rows = pt->persist_R;
+    return MCX_OK;
+}
+
 int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices, int64_t *steps, int64_t *accepted, int64_t *stage, int64_t *round)
 {
     REQUIRE(pt, MCX_ERR_ARGUMENT, "pt is NULL");
     mcx_lattice *lat = pt->lat;
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    ASYNC_CHECK(lat->ctx);                // exchanges decided on energies that never arrived are not a state
     if (indices) {
         std::vector<int32_t> id(pt->n);
         CUDA_TRY(cudaMemcpy(id.data(), pt->d_index, sizeof(int32_t) * pt->n, cudaMemcpyDeviceToHost));

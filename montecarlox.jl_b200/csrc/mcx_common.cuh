@@ -82,6 +82,7 @@ struct LatView {
     // neighbour's block; [5]: arrival counter of the boundary CTAs (launches ordered against the up side or
     // both); [6]: raised when a wait gave up; [7]: arrival counter of launches ordered against the down side only.
     unsigned long long *slab_ctl;
+    int *err;               // mcx_ctx::d_err: sticky error word of the device-side waits
 };
 enum { SLAB_FLAG_UP = 0, SLAB_FLAG_DN = 1, SLAB_T0 = 2, SLAB_UP_SLOT = 3, SLAB_DN_SLOT = 4, SLAB_ARRIVED = 5, SLAB_ERR = 6, SLAB_ARRIVED_DN = 7, SLAB_CTL_WORDS = 8 };
 

@@ -13,6 +13,10 @@ struct mcx_ctx {
     cudaStream_t aux[16];
     cudaEvent_t aux_fork, aux_join[16];
     bool aux_ready;
+    // sticky error word of the device-side spin waits (ticket-queue dependencies, slab neighbours, replica-exchange
+    // peers): zero-copy host memory, written by the kernel that gives up a wait, read by the host on every later
+    // call of this context without a synchronisation (mcx::async_error)
+    int *h_err, *d_err;
 };
 
 // slab decomposition state of a lattice handle (k_slab.cu)
@@ -45,8 +49,10 @@ struct mcx_lattice {
     cudaStream_t copy_stream;
     cudaEvent_t ev_copied, ev_packed;   // copy finished; last conversion out of d_staging finished
     bool upload_pending, packed_recorded;
-    void *d_queue;              // k_queue.cu: ticket counter, error flag and per-item progress words
+    void *d_queue;              // k_queue.cu / k_persist.cu: control words (ticket counter, ...) and per-item progress words
     size_t queue_bytes;
+    long long *d_series;        // mcx_sweep_series: snapshots of the sums, grown on demand
+    size_t series_bytes;
     bool fast2d;                // Lx % 32 == 0 && ndim == 2: row-aligned 128-bit kernels apply
     bool track_sums;            // fast kernels accumulate pair/spin sums per flip (else recompute lazily)
     bool sums_dirty;            // pair/spin sums are stale (untracked sweeps ran)
@@ -56,6 +62,9 @@ struct mcx_lattice {
 struct mcx_pt {
     mcx_lattice *lat;
     int n, first_slot;
+    void *d_dev;                // k_persist.cu: device copy of the ladder view the persistent rounds read
+    int persist_R;              // tallest strip the in-kernel rounds last ran with (reported by mcx_pt_run_info)
+    int last_path;              // 0: host-queued rounds, 1: one persistent launch (k_persist.cu)
     double *d_betas;            // [n] ladder
     double *d_x;                // [n] per-slot energies
     int32_t *d_index;           // [n] 0-based ladder index held by slot
@@ -99,6 +108,8 @@ struct Knobs {
     int resident, resident_cluster, resident_rows, resident_threads, force_generic;
     int queue_rows;   // MCX_QUEUE_ROWS: strip height of the ticket-queue kernel (tuning hook)
     int queue;        // MCX_QUEUE: 1 = series of sweeps through the ticket-queue kernel (k_queue.cu)
+    int queue_grid;   // MCX_QUEUE_GRID: CTAs of the persistent rounds kernel (tuning hook; default: every resident slot)
+    int pt_persist;   // MCX_PT_PERSIST: 1 = mcx_pt_run as one persistent launch whenever the shape allows, 0 = never
     int wl_spec;      // MCX_WL_SPEC: Wang-Landau attempts decided at once (0 = serial loop, 8, 32; unset = adaptive)
 };
 const Knobs &knobs();
@@ -149,6 +160,12 @@ bool launch_init_ising2d(mcx_lattice *lat, int mode, uint64_t seed);            
 
 // k_queue.cu: nsweeps whole sweeps in one launch, work items of all half-sweeps taken from one ticket counter
 bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps);   // false: not applicable, nothing launched
+// k_persist.cu: nrounds x (sweeps_per_round sweeps, energies to all ranks, exchange) in ONE launch; false: not applicable
+bool launch_pt_rounds_persistent(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round);
+
+// codes a kernel stores into mcx_ctx::d_err when a device-side wait gives up
+enum { ASYNC_ERR_QUEUE_DEP = 1, ASYNC_ERR_SLAB = 2, ASYNC_ERR_PT_PEERS = 3, ASYNC_ERR_PT_ROUND = 4 };
+const char *async_error_text(int code);
 
 // k_rows8.cu
 bool launch_sweep_rows8(mcx_lattice *lat, int colour, uint64_t t);     // false: shape not supported
