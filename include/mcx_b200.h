@@ -158,6 +158,8 @@ int32_t mcx_observables(mcx_lattice *lat, int64_t *pair_sum, int64_t *spin_sum, 
                         int64_t *accepted, int64_t *steps);
 int32_t mcx_energies(mcx_lattice *lat, double *energy);                  /* energy(sys) per chain */
 int32_t mcx_reset_counters(mcx_lattice *lat);                            /* reset!(alg) importance_sampling.jl:106 */
+/* restore alg.accepted (per chain) and alg.steps from a checkpoint (checkpointing.jl:95-101) */
+int32_t mcx_set_counters(mcx_lattice *lat, const int64_t *accepted, int64_t steps);
 int32_t mcx_recompute(mcx_lattice *lat);                                 /* energy(sys; full=true) */
 /* on (default): sweeps keep pair/spin sums current per flip, like modify! (ising.jl:200-205).
  * off: sweeps only count accepted moves; the sums are recomputed from the spins on the next

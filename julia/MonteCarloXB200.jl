@@ -276,6 +276,13 @@ mutable struct DeviceReplicaExchange
     n::Int
 end
 
+"position of the lattice's next sweep in the SWEEP stream (kept when an algorithm is bound to a lattice that has already run)"
+function next_sweep(sys::DeviceIsing)
+    seed = Ref{UInt64}(); nxt = Ref{UInt64}()
+    check(ccall((:mcx_get_rng, libmcx), Int32, (Ptr{Cvoid}, Ref{UInt64}, Ref{UInt64}), sys.h, seed, nxt))
+    return nxt[]
+end
+
 "ParallelTempering(betas; seed, rng = s -> PhiloxRNG(seed; chain = s - seed - 1)) bound to a batched lattice"
 function attach(backend::GPUBackend, sys::DeviceIsing, algs::Vector)
     n = length(algs)
@@ -286,10 +293,12 @@ function attach(backend::GPUBackend, sys::DeviceIsing, algs::Vector)
                                sys.h, rule_code(algs[1]), T, n, length(T) ÷ n))
     betas = Float64[MonteCarloX.ensemble(a).beta for a in algs]
     out = Ref{Ptr{Cvoid}}()
-    check(ccall((:mcx_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64), sys.h, algs[1].rng.seed, 0))
+    check(ccall((:mcx_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64), sys.h, algs[1].rng.seed, next_sweep(sys)))
     GC.@preserve betas check(ccall((:mcx_pt_create, libmcx), Int32,
                                    (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Ref{Ptr{Cvoid}}), sys.h, n, first, betas, out))
-    return DeviceReplicaExchange(out[], sys, backend, n)
+    rx = DeviceReplicaExchange(out[], sys, backend, n)
+    finalizer(r -> (r.h == C_NULL || ccall((:mcx_pt_destroy, libmcx), Int32, (Ptr{Cvoid},), r.h); r.h = C_NULL), rx)
+    return rx
 end
 
 "update!(rx): replica_exchange.jl:158-178 on the device; only the energies cross NVLink"
@@ -366,7 +375,13 @@ function DeviceMulticanonical(sys::DeviceIsing, alg)
                 sys.h, 0, 0, b.start, b.step, b.num, 0.0, 0, out))           # policy 0: out of range = BoundsError
     rng = alg.rng::PhiloxRNG
     check(ccall((:mcx_lattice_set_first_chain_id, libmcx), Int32, (Ptr{Cvoid}, UInt32), sys.h, rng.chain))
-    return DeviceMulticanonical(out[], sys, alg)
+    # the FLAT stream is keyed by the algorithm's seed, exactly like the canonical bind (runs with different
+    # PhiloxRNG(seed) must differ); the lattice keeps its sweep position
+    check(ccall((:mcx_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64), sys.h, rng.seed, next_sweep(sys)))
+    mc = DeviceMulticanonical(out[], sys, alg)
+    # the flat handle points into the lattice: destroy it first (mc.sys keeps the lattice alive until then)
+    finalizer(x -> (x.h == C_NULL || ccall((:mcx_flat_destroy, libmcx), Int32, (Ptr{Cvoid},), x.h); x.h = C_NULL), mc)
+    return mc
 end
 
 "n*N attempts per chain: spin_flip!(sys, alg::ImportanceSampling) (ising.jl:25-33) with record_visit! (multicanonical.jl:25-30)"
@@ -398,8 +413,24 @@ end
 
 "the user loop `for i in 1:n; sweeps; i % interval == 0 && update!(pt); end` (pt_Ising2D.jl:52-57) queued in one call"
 function run!(rx::DeviceReplicaExchange, nrounds::Integer, sweeps_per_round::Integer)
+    # 2-D Ising replicas: all rounds in ONE persistent kernel launch (energies, exchange decisions and labels inside the
+    # kernel; k_persist.cu); otherwise the rounds are queued by the library.  A device-side wait that gave up (a rank that
+    # never arrived) makes this and every later call fail with MCX_ERR_CUDA until mcx_ctx_clear_error.
     check(ccall((:mcx_pt_run, libmcx), Int32, (Ptr{Cvoid}, Int64, Int64), rx.h, nrounds, sweeps_per_round))
     return nothing
+end
+
+"code of a device-side wait that timed out on this context (0: none); clear_error! synchronises and resets it"
+function async_error(ctx_handle::Ptr{Cvoid})
+    code = Ref{Int32}()
+    check(ccall((:mcx_ctx_async_error, libmcx), Int32, (Ptr{Cvoid}, Ref{Int32}), ctx_handle, code))
+    return code[]
+end
+clear_error!(ctx_handle::Ptr{Cvoid}) = check(ccall((:mcx_ctx_clear_error, libmcx), Int32, (Ptr{Cvoid},), ctx_handle))
+
+"restore alg.accepted (per chain) and alg.steps of a checkpointed lattice (checkpointing.jl:95-101)"
+function set_counters!(sys::DeviceIsing, accepted::Vector{Int64}, steps::Integer)
+    GC.@preserve accepted check(ccall((:mcx_set_counters, libmcx), Int32, (Ptr{Cvoid}, Ptr{Int64}, Int64), sys.h, accepted, steps))
 end
 
 # ----------------------------------------------------------------------------------------------
@@ -417,13 +448,18 @@ mutable struct DeviceWangLandau
     logf::Float64
 end
 
-"WangLandau(rng, bins; logf) (algorithms/wang_landau.jl:10-18) for every chain of `sys`, restricted to `bins`"
-function DeviceWangLandau(sys::DeviceIsing, bins::StepRange{Int,Int}; logf::Float64=1.0, window::Bool=true)
+"WangLandau(rng, bins; logf) (algorithms/wang_landau.jl:10-18) for every chain of `sys`, restricted to `bins`; walker c
+ draws from PhiloxRNG(rng.seed; chain = rng.chain + c)"
+function DeviceWangLandau(sys::DeviceIsing, rng::PhiloxRNG, bins::StepRange{Int,Int}; logf::Float64=1.0, window::Bool=true)
     out = Ref{Ptr{Cvoid}}()
     check(ccall((:mcx_flat_create, libmcx), Int32,
                 (Ptr{Cvoid}, Int32, Int32, Int64, Int64, Int64, Float64, Int32, Ref{Ptr{Cvoid}}),
                 sys.h, 1, 0, first(bins), step(bins), length(bins), 0.0, window ? 1 : 0, out))
-    return DeviceWangLandau(out[], sys, bins, logf)
+    check(ccall((:mcx_lattice_set_first_chain_id, libmcx), Int32, (Ptr{Cvoid}, UInt32), sys.h, rng.chain))
+    check(ccall((:mcx_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64), sys.h, rng.seed, next_sweep(sys)))
+    wl = DeviceWangLandau(out[], sys, bins, logf)
+    finalizer(x -> (x.h == C_NULL || ccall((:mcx_flat_destroy, libmcx), Int32, (Ptr{Cvoid},), x.h); x.h = C_NULL), wl)
+    return wl
 end
 
 "n*N attempts per walker: spin_flip!(sys, alg::ImportanceSampling) (ising.jl:25-33) + accept! (wang_landau.jl:29-37)"

@@ -64,6 +64,7 @@ SIGNATURES = {
     "mcx_observables": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mcx_energies": (_i32, [_vp, _vp]),
     "mcx_reset_counters": (_i32, [_vp]),
+    "mcx_set_counters": (_i32, [_vp, _vp, _i64]),
     "mcx_recompute": (_i32, [_vp]),
     "mcx_set_tracking": (_i32, [_vp, _i32]),
     "mcx_pt_run": (_i32, [_vp, _i64, _i64]),

@@ -29,8 +29,7 @@ class CheckpointSession:
 def checkpoint_(ckpt, **kwargs):
     """checkpoint!(ckpt; kwargs...) (:48-56)"""
     state = dict(ckpt._state)
-    state.update(kwargs)
-    ckpt._state.update(kwargs)
+    state.update(kwargs)          # merged into the written snapshot only; the session's own state is left alone (:49-50)
     tmp = ckpt.file + ".tmp"
     with open(tmp, "wb") as io:
         pickle.dump(state, io, protocol=pickle.HIGHEST_PROTOCOL)

@@ -192,6 +192,11 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                     // the trajectory is unchanged; the cost drops from one dependent evaluation per attempt to
                     // one per ACCEPTED attempt (+ 1 per 32).  Wang-Landau changes lw at every attempt: serial loop.
                     const long long nacc_before = nacc;
+                    // a decision loop that stops early (BoundsError, policy 0) must not leave the previous batch's
+                    // flags behind for phase 3: attempts that are never decided are not accepted
+#pragma unroll
+                    for (int j = 0; j < kBatch / 32; ++j) s_acc[w][32 * j + lane] = 0;
+                    __syncwarp();
                     if (KIND == MCX_FLAT_MUCA && speculate) {
                         for (int base = 0; base < cnt && !dead; base += 32) {
                             const int idx = base + lane;

@@ -691,6 +691,23 @@ int32_t mcx_reset_counters(mcx_lattice *lat)
     return MCX_OK;
 }
 
+// restore checkpointed counters: alg.accepted per chain and alg.steps (importance_sampling.jl:26-27 through
+// checkpointing.jl:95-101)
+int32_t mcx_set_counters(mcx_lattice *lat, const int64_t *accepted, int64_t steps)
+{
+    REQUIRE(lat && accepted, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(steps >= 0, MCX_ERR_ARGUMENT, "steps must be >= 0");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    std::vector<long long> h((size_t)lat->nchains * SUM_FIELDS);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), lat->d_sums, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    for (int c = 0; c < lat->nchains; ++c) h[(size_t)c * SUM_FIELDS + SUM_ACC] = accepted[c];
+    CUDA_TRY(cudaMemcpyAsync(lat->d_sums, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    lat->steps = steps;
+    return MCX_OK;
+}
+
 int32_t mcx_recompute(mcx_lattice *lat)
 {
     REQUIRE(lat, MCX_ERR_ARGUMENT, "lat is NULL");

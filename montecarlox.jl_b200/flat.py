@@ -73,6 +73,7 @@ class DeviceFlat:
                                     int(policy), C.byref(h)))
         self.h = h
         check(lib().mcx_lattice_set_first_chain_id(sys.h_lat, alg.rng.chain))
+        sys._first_chain = alg.rng.chain       # what a checkpoint of the lattice must restore
         sys.set_rng(alg.rng.seed)
 
     def close(self):

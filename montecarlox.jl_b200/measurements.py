@@ -103,7 +103,7 @@ def sweep_series_(sys, alg, nmeasure, interval=1):
     before = int(sys._sums()[3].sum())
     out = np.empty((int(nmeasure), sys.nchains, 4), dtype=np.int64)
     check(lib().mcx_sweep_series(sys.h_lat, int(nmeasure), int(interval), out.ctypes.data))
-    alg.steps += int(nmeasure) * int(interval) * sys.N
+    alg.steps += int(nmeasure) * int(interval) * sys.N * sys.nchains     # summed over the chains, like alg.accepted
     pair, spin, spin2, acc = (out[:, :, k] for k in range(4))
     if hasattr(alg, "accepted") and nmeasure:
         alg.accepted += int(acc[-1].sum()) - before

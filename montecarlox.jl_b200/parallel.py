@@ -283,6 +283,7 @@ class ReplicaExchange:
         self._betas = betas
         self._xbuf = None
         self._peers = False
+        self._acc_seen = np.atleast_1d(sys._sums()[3]).astype(np.int64).copy()   # per-chain accepted already credited
         if isinstance(self.backend, GPUBackend) and self.backend.size > 1 and os.environ.get("MCX_PT_P2P", "1") != "0":
             # energies travel by peer stores over NVLink (CUDA IPC), no collective call per exchange
             buf = C.create_string_buffer(128)
@@ -339,9 +340,21 @@ class ReplicaExchange:
         self._dirty = True
         return None
 
+    def sync_counters(self):
+        """credit the accepted moves of this rank's lattices to their replicas' algorithms (alg.accepted,
+        importance_sampling.jl:80-85): the device counts them per chain; read lazily, never inside a sweep loop"""
+        if self._pt is None:
+            return
+        now = np.atleast_1d(self._sys._sums()[3]).astype(np.int64)
+        seen = np.where(now < self._acc_seen, 0, self._acc_seen)      # counters were reset in between
+        for c, a in enumerate(self.replica.algs[self._first:self._first + self._count]):
+            a.accepted += int(now[c] - seen[c])
+        self._acc_seen = now.copy()
+
     def _pull(self):
         if self._pt is None or not getattr(self, "_dirty", False):
             return
+        self.sync_counters()
         st, rd = C.c_int64(), C.c_int64()
         check(lib().mcx_pt_state(self._pt, self.indices.ctypes.data, self.steps.ctypes.data,
                                  self.accepted.ctypes.data, C.byref(st), C.byref(rd)))
@@ -383,8 +396,34 @@ class ReplicaExchange:
             except Exception:
                 pass
 
-    def __del__(self):
-        self.close()        # self._sys (strong ref) keeps the lattice alive until here
+    # -- serialisation (checkpoint!/restore_checkpoint, checkpointing.jl:48-101): the ladder (indices, per-edge
+    # counters, stage, exchange round), the algorithms, and the lattice it is attached to
+    def __getstate__(self):
+        self._dirty = self._pt is not None
+        self._pull()
+        return {"backend_kind": type(self.backend).__name__, "algs": self.replica.algs, "stage": int(self.stage),
+                "indices": self.indices.copy(), "steps": self.steps.copy(), "accepted": self.accepted.copy(),
+                "round": int(self.round), "sys": self._sys if self._pt is not None else None,
+                "betas": [float(b) for b in self._betas] if self._pt is not None else None}
+
+    def __setstate__(self, st):
+        algs = st["algs"]
+        backend = GPUBackend() if st["backend_kind"] == "GPUBackend" else ThreadsBackend(len(algs))
+        ReplicaExchange.__init__(self, backend, algs)
+        self.stage, self.round = st["stage"], st["round"]
+        self.indices[:] = st["indices"]
+        self.steps[:] = st["steps"]
+        self.accepted[:] = st["accepted"]
+        if st["sys"] is not None:
+            # attach() reads the ladder off the algorithms in slot order: hand it the ladder, then restore the permutation
+            ens_type = type(algs[0].ensemble)
+            for r, a in enumerate(algs):
+                a.ensemble = ens_type(beta=st["betas"][r])
+            self.attach(st["sys"])
+            check(lib().mcx_pt_set_state(self._pt, self.indices.ctypes.data, self.steps.ctypes.data,
+                                         self.accepted.ctypes.data, int(self.stage), int(self.round)))
+            self._dirty = True
+            self._pull()            # the ensembles follow the restored labels again (replica_exchange.jl:133)
 
 
 class _CudaArray:

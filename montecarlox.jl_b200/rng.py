@@ -41,8 +41,18 @@ class PhiloxRNG:
         self.tag, self.t, self.q, self.draw = tag, int(t), int(q), 0
         return self
 
+    def _next_draw(self):
+        """planes 2n, 2n+1 of draw n; the plane field is 8 bits, so after 128 draws at one position the stream moves
+        on to the same lane of the next block (q += 8) instead of aliasing the tag field"""
+        if self.draw >= 128:
+            self.q += 8
+            self.draw = 0
+        n = self.draw
+        self.draw += 1
+        return n
+
     def _lane16(self, plane):
-        out = stream_block(self.seed, self.chain, self.tag, self.t, self.q >> 3, plane)
+        out = stream_block(self.seed, self.chain, self.tag, self.t, (self.q >> 3) & _MASK, plane & 0xFF)
         lane = self.q & 7
         return (out[lane >> 1] >> (16 * (lane & 1))) & 0xFFFF
 
@@ -50,15 +60,14 @@ class PhiloxRNG:
         """rand(rng)::Float64 -- 32 bits, exact in Float64."""
         if self.tag == TAG_EXCHANGE:
             return exchange_u(self.seed, self.chain, self.t)
-        hi = self._lane16(2 * self.draw)
-        lo = self._lane16(2 * self.draw + 1)
-        self.draw += 1
+        n = self._next_draw()
+        hi = self._lane16(2 * n)
+        lo = self._lane16(2 * n + 1)
         return ((hi << 16) | lo) / 4294967296.0
 
     def rand_bool(self):
         """rand(rng, Bool)."""
-        hi = self._lane16(2 * self.draw)
-        self.draw += 1
+        hi = self._lane16(2 * self._next_draw())
         return bool(hi >> 15)
 
 

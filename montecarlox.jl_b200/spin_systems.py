@@ -96,7 +96,8 @@ class AbstractSpinSystem:
         return {"cls_dims": self.dims, "J": self.J, "h": self.h, "D": self.D, "nchains": self.nchains,
                 "device": self.ctx.device, "spins": self.spins.copy(), "seed": seed.value, "next_sweep": nxt.value,
                 "labels": self.get_labels(), "rule": getattr(self, "_rule_tables", None),
-                "first_chain": getattr(self, "_first_chain", 0)}
+                "first_chain": getattr(self, "_first_chain", 0),
+                "accepted": np.atleast_1d(acc).astype(np.int64), "steps": int(np.atleast_1d(steps)[0])}
 
     def __setstate__(self, st):
         AbstractSpinSystem.__init__(self, st["cls_dims"], st["J"], st["h"], st["D"], st["nchains"],
@@ -108,6 +109,9 @@ class AbstractSpinSystem:
         check(lib().mcx_lattice_set_first_chain_id(self.h_lat, st["first_chain"]))
         self._first_chain = st["first_chain"]
         check(lib().mcx_set_rng(self.h_lat, st["seed"], st["next_sweep"]))
+        if "accepted" in st:        # the lattice-side counters of the bound algorithm (importance_sampling.jl:26-27)
+            acc = np.ascontiguousarray(st["accepted"], dtype=np.int64)
+            check(lib().mcx_set_counters(self.h_lat, acc.ctypes.data, int(st["steps"])))
 
     # ---- sys.spins
     def _shape(self, a):
@@ -305,7 +309,9 @@ def sweep_(sys, alg, nsweeps=1):
     if getattr(alg, "_track_counters", True):
         before = sys._sums()[3].copy()
     check(lib().mcx_sweep(sys.h_lat, int(nsweeps)))
-    alg.steps += int(nsweeps) * sys.N
+    # one algorithm object drives every chain of a batch: its counters are sums over the chains, so that
+    # acceptance_rate(alg) = accepted / steps stays a rate (importance_sampling.jl:95-101)
+    alg.steps += int(nsweeps) * sys.N * sys.nchains
     if before is not None and hasattr(alg, "accepted"):
         alg.accepted += int((sys._sums()[3] - before).sum())
     return None

@@ -167,3 +167,24 @@ def test_checkpoint_session_roundtrip(tmp_path):
     m.finalize_(ck)
     import os
     assert not os.path.exists(f)
+
+
+def test_checkpoint_kwargs_do_not_leak_into_the_session(tmp_path):
+    """checkpoint!(ckpt; kwargs...) merges the keywords into the written snapshot only (checkpointing.jl:48-56)"""
+    f = str(tmp_path / "c.mcx")
+    ck = m.init_checkpoint(f, {"x": 1.5})
+    m.checkpoint_(ck, sweep=7)
+    assert m.restore_checkpoint(f).sweep == 7
+    with pytest.raises(AttributeError):
+        ck.sweep
+
+
+def test_philox_rng_many_draws_do_not_alias_other_streams():
+    """more than 128 draws at one position: the 8-bit plane field must not spill into the tag field"""
+    rng = m.PhiloxRNG(5, 1).position(0, 3, 17)
+    first = [rng.rand() for _ in range(300)]
+    assert len(set(first)) == 300
+    other = m.PhiloxRNG(5, 1).position(1, 3, 17)      # tag 1 = EXCHANGE stream
+    assert rng.tag == 0 and all(0.0 <= u < 1.0 for u in first)
+    again = m.PhiloxRNG(5, 1).position(0, 3, 17)
+    assert [again.rand() for _ in range(300)] == first
