@@ -10,7 +10,11 @@ collective).
 
     python bench.py --gpus 1 --steps 5 --warmup 3            # ours
     python bench.py --impl reference --steps 3 --warmup 1    # the reference's CPU algorithm (oracle port)
+    python bench.py --config c1|c3|c4|c5                     # the other BASELINE.json configs as the line's metric
+    python bench.py --storage bit                            # configs[1] on one-bit-per-spin planes
 
+The default line (configs[1]) also carries short legs of the other configs under "configs": {"c1", "c4", "c5", "bit"}
+(each with its own cpu_baseline on the host cores) and "pt" / "pt_every_sweep" (configs[2]); --no-extras drops them.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -44,17 +48,23 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-slab", action="store_true", help="skip the auxiliary slab-decomposition measurement (N > 1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="which BASELINE.json config the line's metric is measured on (c2 = configs[1], the headline)")
+    ap.add_argument("--storage", default="int8", choices=["int8", "bit"], help="device storage of the c2 lattice")
+    ap.add_argument("--no-extras", action="store_true", help="c2 only: skip the short legs of the other configs")
     return ap.parse_args()
 
 
 def workload_config(args, world):
     return {
         "workload": "2D Ising L=%d single-chain checkerboard %s at beta_c (BASELINE.json configs[1])" % (args.L, args.rule),
-        "L": args.L, "beta": BETA_C, "rule": args.rule, "storage": "int8 (1 byte/spin, 2 colour planes)",
+        "L": args.L, "beta": BETA_C, "rule": args.rule,
+        "storage": "int8 (1 byte/spin, 2 colour planes)" if args.storage == "int8" else "bit (1 bit/spin, 2 colour planes)",
         "chains_per_gpu": 1, "sweeps_per_step": args.sweeps_per_step,
         "rng": "Philox4x32-10, 32-bit draws (16-bit high half + lazy low half)",
-        "l2_policy": "input (%d MiB) larger than L2 (126 MB); no flush needed" % (args.L * args.L >> 20),
-        "parallelism": "replicas only: %d independent chain(s), one per GPU" % world,
+        "l2_policy": ("input (%d MiB) larger than L2 (126 MB); no flush needed" % (args.L * args.L >> 20)) if args.storage == "int8"
+                     else "input (%d MiB) fits the 126 MB L2 by design: one-bit storage is quoted in attempts/ns and L2 GB/s, not as an HBM fraction" % (args.L * args.L >> 23),
+        "parallelism": "replicas only: one independent chain per GPU",
         "track_sums": bool(args.track),
     }
 
@@ -410,6 +420,313 @@ def bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, L=1024, n=256
             "collective": "none (1 rank)" if world == 1 else
                           ("peer stores of %d doubles per exchange over NVLink (CUDA IPC), device-side arrival counters, no collective call" % n
                            if getattr(pt, "_peers", False) else "NCCL all-gather of %d doubles per exchange" % n)}
+
+
+# ------------------------------------------------------------------ the other BASELINE.json configs
+# Each leg returns {"metric", "value", "unit", "config", "roofline", "e2e", "cpu_baseline"?, "parity"?, ...}: the default
+# line embeds short runs of them under "configs"; `--config cX` prints one as the line itself.
+def _sha(*arrays):
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def _threads():
+    return max(1, min(os.cpu_count() or 1, 64))
+
+
+def _run_threads(fn, n):
+    """fn(i) on n Python threads (the oracle's C loops release the GIL); returns wall seconds"""
+    th = [threading.Thread(target=fn, args=(i,)) for i in range(n)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def _moments(series, N):
+    """<E>/N, <|m|>, U4 = 1 - <m^4> / (3 <m^2>^2) from int64 [n, chains, 4] snapshots {pair, spin, spin2, accepted}"""
+    import numpy as np
+    e = -series[:, :, 0].astype(np.float64) / N
+    mm = series[:, :, 1].astype(np.float64) / N
+    m2, m4 = (mm ** 2).mean(), (mm ** 4).mean()
+    return {"energy_per_site": float(e.mean()), "abs_m": float(np.abs(mm).mean()), "U4": float(1.0 - m4 / (3.0 * m2 * m2))}
+
+
+def cpu_leg_c1(nthreads, sweeps):
+    """the reference's random-site Metropolis loop, L = 64 at beta_c, seed 42,
+    one chain per thread (oracle port of SpinSystems/src/ising.jl:35-41 + importance_sampling.jl:80-85)"""
+    from oracle import oracle
+    oracle.build()
+    L, therm, interval = 64, 1000, 10
+    t0 = time.perf_counter()
+    st = oracle.stats_random_site(L, BETA_C, nthreads, therm, sweeps, interval, nthreads, 42)
+    dt = time.perf_counter() - t0
+    attempts = nthreads * (therm + sweeps) * L * L
+    m2, m4 = st[:, 2].mean(), st[:, 3].mean()
+    return {"value": attempts / (dt * 1e9), "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "%d chain(s) x (%d + %d) random-site sweeps of L=64 at beta_c, seed 42, xoshiro256++ (%.1f s; oracle "
+                      "mcxo_stats_random_site)" % (nthreads, therm, sweeps, dt),
+            "energy_per_site": float(st[:, 0].mean()), "abs_m": float(st[:, 1].mean()), "U4": float(1.0 - m4 / (3.0 * m2 * m2))}
+
+
+def bench_c1(m, ctx, stream, args, sweeps=100000, cpu=True):
+    """configs[0]: 2-D Ising L = 64 Metropolis at beta_c, 10^5 sweeps, <E>/N, <|m|>, U4 (importance_Ising2D.jl:105-122).
+    On the device the lattice lives in shared memory for the whole series (k_ising2d_resident); the measurements are
+    snapshots of the tracked sums every `interval` sweeps (mcx_sweep_series)."""
+    import numpy as np
+    import torch
+    from mcx_b200._lib import check, lib
+    L, interval, therm = 64, 10, 1000
+    N = L * L
+    nmeasure = sweeps // interval
+    sys_ = m.Ising([L, L], ctx=ctx)
+    rng = m.PhiloxRNG(42, 0)
+    alg = m.Metropolis(rng, beta=BETA_C)
+    sys_._bind_alg(alg)
+    sys_.init_("random", rng=rng)
+    check(lib().mcx_sweep(sys_.h_lat, therm))
+    series = np.empty((nmeasure, 1, 4), dtype=np.int64)
+    check(lib().mcx_sweep_series(sys_.h_lat, min(nmeasure, 100), interval, series.ctypes.data))   # warm-up (grows the snapshot buffer)
+    check(lib().mcx_sweep_series(sys_.h_lat, nmeasure, interval, series.ctypes.data))
+    torch.cuda.synchronize()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    check(lib().mcx_sweep_series(sys_.h_lat, nmeasure, interval, series.ctypes.data))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    stats = _moments(series, N)
+    # e2e: host spins in (pinned), the series out
+    host = torch.from_numpy(sys_.spins.copy()).pin_memory()
+    t0 = time.perf_counter()
+    sys_.upload_from(host.data_ptr())
+    check(lib().mcx_sweep_series(sys_.h_lat, nmeasure, interval, series.ctypes.data))
+    e2e_s = time.perf_counter() - t0
+    attempts = nmeasure * interval * N
+    peak, _ = measured_peak()
+    achieved = 3.0 * attempts / (ms * 1e-3) / 1e9
+    out = {"metric": METRIC, "value": attempts / (ms * 1e6), "unit": UNIT, "ms": ms, "gpu_launches": int(launches),
+           "config": {"workload": "2D Ising L=64 Metropolis at beta_c, %d sweeps, seed 42 (BASELINE.json configs[0])" % sweeps,
+                      "L": L, "sweeps": sweeps, "measure_every": interval, "thermalisation_sweeps": therm},
+           "us_per_sweep": ms * 1e3 / (nmeasure * interval),
+           "roofline": {"bound": "hbm", "kernel": "k_ising2d_resident (both colour planes in shared memory for %d sweeps per launch)" % interval,
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "note": "3 B/attempt is the streaming figure; this kernel touches HBM for 2 B/site per launch only, so the "
+                                "fraction says how far a 4096-site lattice is from filling the machine, not kernel quality"},
+           "e2e": {"value": attempts / (e2e_s * 1e9), "unit": UNIT, "h2d_bytes_per_step": N, "d2h_bytes_per_step": int(series.nbytes),
+                   "api": "mcx_lattice_upload + mcx_sweep_series (C ABI)"},
+           "result": stats}
+    if cpu:
+        try:
+            out["cpu_baseline"] = cpu_leg_c1(1, sweeps)
+            out["cpu_baseline_all_cores"] = cpu_leg_c1(_threads(), max(sweeps // 4, 1000))
+            ref = out["cpu_baseline"]
+            out["parity"] = {"kind": "statistical (different update order and generator: random-site xoshiro vs checkerboard Philox)",
+                             "d_energy_per_site": stats["energy_per_site"] - ref["energy_per_site"],
+                             "d_abs_m": stats["abs_m"] - ref["abs_m"], "d_U4": stats["U4"] - ref["U4"]}
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)}
+    return out
+
+
+def cpu_leg_c3(nthreads, seconds, L=1024, every=200):
+    """BASELINE.md section 4 'PT': replicas = host threads, L = 1024, one exchange per `every` sweeps
+    (pt_Ising2D.jl:37-57 on ThreadsBackend: random-site sweeps per replica, then update!(rx))"""
+    import numpy as np
+    from oracle import oracle
+    oracle.build()
+    n = nthreads
+    betas = oracle.set_betas(n, 1 / 3.0, 1 / 1.5)
+    sysv = [oracle.System(oracle.ISING, [L, L]) for _ in range(n)]
+    algs = [oracle.Alg(oracle.METROPOLIS, float(b)) for b in betas]
+    xos = [oracle.xoshiro(42 + i) for i in range(n)]
+    for i, s_ in enumerate(sysv):
+        s_.init_random(42, i)
+    N = L * L
+    t = _run_threads(lambda i: sysv[i].sweep_random_site(algs[i], xos[i], N), n)      # calibrate: one sweep each
+    sweeps = int(max(1, min(every, seconds / max(t, 1e-6))))
+    dt = _run_threads(lambda i: sysv[i].sweep_random_site(algs[i], xos[i], sweeps * N), n)
+    t0 = time.perf_counter()
+    idx = np.arange(1, n + 1, dtype=np.int64)
+    steps, acc = np.zeros(max(n - 1, 1), dtype=np.int64), np.zeros(max(n - 1, 1), dtype=np.int64)
+    xs = np.array([s_.energy() for s_ in sysv])
+    if n > 1:
+        oracle.rx_update(0, idx, steps, acc, betas[idx - 1], xs, np.full(n, 0.5))
+    dt += (time.perf_counter() - t0) * sweeps / every          # the exchange's share of `sweeps` sweeps
+    return {"value": sweeps / dt, "unit": "PT sweeps/s (all %d replicas swept once)" % n, "cores": nthreads, "kind": "port",
+            "attempts_per_ns": sweeps * n * N / (dt * 1e9),
+            "sample": "%d replicas of L=%d (one per thread), %d random-site sweeps each + 1/%d of an update!(rx) (%.1f s; oracle "
+                      "mcxo_sweep_random_site + mcxo_rx_update)" % (n, L, sweeps, every, dt)}
+
+
+def cpu_leg_c4(nthreads, sweeps=1, L=512):
+    """config 4 on the host: one Blume-Capel L = 512 multicanonical chain per thread, pair term at T = 0.9, visits on
+    sum s^2 (muca_BlumeCapel.jl:33-108 through ThreadsBackend); oracle mcxo_flat_sweep_policy"""
+    from oracle import oracle
+    oracle.build()
+    N = L * L
+    sysv = [oracle.System(oracle.BLUME_CAPEL, [L, L]) for _ in range(nthreads)]
+    flats = [oracle.Flat(0, 1, N + 1) for _ in range(nthreads)]
+    algs = [oracle.Alg(0, 0.0) for _ in range(nthreads)]
+    dt = _run_threads(lambda i: sysv[i].flat_sweep(algs[i], flats[i], 0, 1, 1 / 0.9, 42, i, 0, sweeps, policy=0), nthreads)
+    return {"value": nthreads * sweeps * N / (dt * 1e9), "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "%d chain(s) x %d multicanonical sweep(s) of Blume-Capel L=%d, one chain per thread (%.1f s)" % (nthreads, sweeps, L, dt)}
+
+
+def bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, iterations=3, therm=2, record=8, L=512, chains=1024, cpu=True):
+    """configs[3]: Blume-Capel L = 512, 1024 chains, multicanonical weight iteration in sum s^2 (muca_BlumeCapel.jl:33-108):
+    per iteration thermalise, reset!, record, merge_histograms! (all-reduce when the chains are sharded over ranks),
+    update!.  Everything stays on the device (C ABI: mcx_flat_*)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mcx_b200._lib import check, lib
+    N = L * L
+    count = chains // world
+    first = rank * count
+    sys_ = m.BlumeCapel([L, L], nchains=count, ctx=ctx)
+    check(lib().mcx_lattice_set_first_chain_id(sys_.h_lat, first))
+    sys_.set_rng(42, 0)
+    h = C.c_void_p()
+    check(lib().mcx_flat_create(sys_.h_lat, m._lib.FLAT_MUCA, m._lib.OBS_SPIN2_WITH_PAIR_BOLTZMANN, 0, 1, N + 1, 1 / 0.9, 0, C.byref(h)))
+    hist_ptr, nb = C.c_void_p(), C.c_int64()
+    check(lib().mcx_flat_device_histogram(h, C.byref(hist_ptr), C.byref(nb)))
+    from mcx_b200.parallel import _as_torch
+    hist = _as_torch(hist_ptr.value, nb.value, torch.int64, ctx.device)
+
+    def iteration():
+        check(lib().mcx_flat_sweep(h, therm))
+        check(lib().mcx_flat_reset_histogram(h))
+        check(lib().mcx_flat_sweep(h, record))
+        if world > 1:
+            dist.all_reduce(hist)                                # merge_histograms! (parallel_multicanonical.jl:38-52)
+        check(lib().mcx_flat_update(h))                          # every rank applies the same update!: no broadcast needed
+
+    iteration()                                                  # warm-up (also an iteration of the weights)
+    barrier()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iterations):
+        iteration()
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.launch_count() - l0
+    lw = np.empty(N + 1, dtype=np.float64)
+    check(lib().mcx_flat_get_logweight(h, lw.ctypes.data))
+    hv = np.empty(N + 1, dtype=np.float64)
+    check(lib().mcx_flat_get_histogram(h, hv.ctypes.data))
+    # e2e: the host ensemble objects stay the source of truth (flat.py DeviceFlat): tables in, histogram + tables out
+    t0 = time.perf_counter()
+    check(lib().mcx_flat_set_logweight(h, lw.ctypes.data))
+    iteration()
+    check(lib().mcx_flat_get_logweight(h, lw.ctypes.data))
+    check(lib().mcx_flat_get_histogram(h, hv.ctypes.data))
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sweeps = iterations * (therm + record)
+    attempts = sweeps * chains * N
+    peak, _ = measured_peak()
+    achieved = 2.0 * attempts / world / (ms * 1e-3) / 1e9
+    out = {"metric": METRIC, "value": attempts / (ms * 1e6), "unit": UNIT, "iterations_per_s": iterations / (ms * 1e-3), "ms": ms,
+           "gpu_launches": int(launches), "n_gpus": world,
+           "config": {"workload": "2D Blume-Capel L=%d multicanonical weight iteration in sum s^2, %d chains (BASELINE.json configs[3])" % (L, chains),
+                      "iterations": iterations, "therm_sweeps": therm, "record_sweeps": record, "T_pair": 0.9,
+                      "parallelism": "chains sharded over the ranks; one all-reduce of the %d-bin histogram per iteration" % (N + 1)},
+           "roofline": {"bound": "hbm", "kernel": "k_flat_warp (one warp per chain; serial in the chain's sum s^2)", "achieved": achieved,
+                        "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "note": "2 B/attempt (read + conditional write of the site); latency-bound by construction (BASELINE.md section 3)"},
+           "e2e": {"value": (therm + record) * chains * N / (e2e_s * 1e9), "unit": UNIT, "h2d_bytes_per_step": int(lw.nbytes),
+                   "d2h_bytes_per_step": int(lw.nbytes + hv.nbytes), "api": "mcx_flat_set_logweight + iteration + mcx_flat_get_logweight/_histogram"},
+           "parity": {"kind": "identical at every rank count (chains keyed by global id, integer histogram)",
+                      "histogram_sha": _sha(hv), "logweight_sha": _sha(lw), "visits": float(hv.sum())}}
+    check(lib().mcx_flat_destroy(h))
+    if cpu and rank == 0:
+        try:
+            out["cpu_baseline"] = cpu_leg_c4(_threads())
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)}
+    return out
+
+
+def cpu_leg_c5(nthreads, L=256):
+    """config 5 on the host: one Wang-Landau walker of the 3-D Ising L = 256 lattice per thread, one sweep each, the window
+    being the whole upper half of the spectrum around E = 0 (oracle mcxo_flat_sweep_policy, policy 1)"""
+    from oracle import oracle
+    oracle.build()
+    N = L ** 3
+    sysv = [oracle.System(oracle.ISING, [L, L, L]) for _ in range(nthreads)]
+    for i, s_ in enumerate(sysv):
+        s_.init_random(42, i)
+    flats = [oracle.Flat(-(1 << 22), 4, (1 << 21) + 1) for _ in range(nthreads)]
+    algs = [oracle.Alg(0, 0.0) for _ in range(nthreads)]
+    dt = _run_threads(lambda i: sysv[i].flat_sweep(algs[i], flats[i], 1, 0, 0.0, 42, i, 0, 1, policy=1), nthreads)
+    return {"value": nthreads * N / (dt * 1e9), "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "%d walker(s) x 1 Wang-Landau sweep of 3-D Ising L=%d, one walker per thread (%.1f s)" % (nthreads, L, dt)}
+
+
+def bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers=32, L=256, sweeps=1, cpu=True):
+    """configs[4]: 3-D Ising L = 256 Wang-Landau, energy windows dealt to the ranks, `walkers` walkers per window with one
+    table each (windows.py).  Timed: `sweeps` sweeps of every walker, tables left on the device."""
+    import numpy as np
+    backend = m.GPUBackend()
+    nwin = windows_per_gpu * world
+    wl = m.WangLandauWindows([L] * 3, nwindows=nwin, walkers=walkers, overlap=0.5, seed=42, backend=backend, replicate_seed=True)
+    t0 = time.perf_counter()
+    wl.prepare_()
+    t_prepare = time.perf_counter() - t0
+    l0 = sum(e.ctx.launch_count() for e in wl.local)
+    barrier()
+    t0 = time.perf_counter()
+    wl.sweep_device_(sweeps)
+    wl.sync_()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    launches = sum(e.ctx.launch_count() for e in wl.local) - l0
+    barrier()
+    energies = np.concatenate([np.asarray(e) for e in wl.energies()])
+    inside = all(((wl.window_energies(wl.first + j)[0] <= e) & (e <= wl.window_energies(wl.first + j)[1])).all()
+                 for j, e in enumerate(wl.energies()))
+    if world > 1:
+        import torch.distributed as dist
+        gathered = [None] * world
+        dist.all_gather_object(gathered, energies)
+        energies = np.concatenate(gathered)
+    # e2e: the same sweeps followed by the read-back of every table (what WangLandauWindows.sweep_ returns to the host)
+    t0 = time.perf_counter()
+    wl.sweep_(sweeps)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    table_bytes = sum(a.nbytes for a in wl._lw)
+    attempts = sweeps * wl.N * walkers * nwin
+    peak, _ = measured_peak()
+    achieved = 2.0 * attempts / world / dt / 1e9
+    out = {"metric": METRIC, "value": attempts / (dt * 1e9), "unit": UNIT, "ms": dt * 1e3, "gpu_launches": int(launches), "n_gpus": world,
+           "config": {"workload": "3D Ising L=%d Wang-Landau, %d energy windows x %d walkers over %d GPU(s) (BASELINE.json configs[4])"
+                                  % (L, nwin, walkers, world),
+                      "bins_per_window": wl.width, "overlap": 0.5, "logf": wl.logf, "sweeps": sweeps, "seeding": "one driven walker per window, replicated",
+                      "parallelism": "windows dealt to the ranks in contiguous blocks; no collective while sampling"},
+           "prepare_seconds": t_prepare, "walkers_inside_windows": bool(inside),
+           "roofline": {"bound": "hbm", "kernel": "k_flat_warp (one warp per walker, private log-weight table, window of it in shared memory)",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "note": "2 B/attempt; serial in the walker's energy, latency-bound by construction (BASELINE.md section 3)"},
+           "e2e": {"value": attempts / (e2e_s * 1e9), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(table_bytes),
+                   "api": "WangLandauWindows.sweep_ (mcx_flat_sweep + mcx_flat_get_logweight of every walker)"},
+           "parity": {"kind": "identical at every rank count (walkers keyed by global number)", "energies_sha": _sha(energies.astype(np.int64))}}
+    wl.close()
+    if cpu and rank == 0:
+        try:
+            out["cpu_baseline"] = cpu_leg_c5(min(_threads(), 32))
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)}
+    return out
 
 
 if __name__ == "__main__":

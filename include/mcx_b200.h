@@ -54,6 +54,8 @@ enum mcx_status {
 };
 enum mcx_model { MCX_ISING = 0, MCX_BLUME_CAPEL = 1 };
 enum mcx_rule { MCX_METROPOLIS = 0, MCX_GLAUBER = 1, MCX_HEATBATH = 2 };
+/* device storage of the spins (the reference's `spins::Vector{Int8}`, ising.jl:433): one byte per spin, or -- Ising in 2 / 3
+ * dimensions with Lx % 32 == 0 -- one bit per spin.  Same RNG positions, same decisions: trajectories do not depend on it. */
 enum mcx_storage { MCX_STORAGE_INT8 = 0, MCX_STORAGE_BIT = 1 };
 enum mcx_init_mode { MCX_INIT_UP = 0, MCX_INIT_DOWN = 1, MCX_INIT_ZERO = 2, MCX_INIT_RANDOM = 3 };
 enum mcx_flat_kind { MCX_FLAT_MUCA = 0, MCX_FLAT_WANG_LANDAU = 1 };
@@ -114,6 +116,12 @@ int32_t mcx_lattice_download(mcx_lattice *lat, int8_t *host_spins);      /* read
  * is pending is MCX_ERR_STATE. */
 int32_t mcx_lattice_upload_begin(mcx_lattice *lat, const int8_t *host_spins);
 int32_t mcx_lattice_upload_commit(mcx_lattice *lat);
+/* The same assignments / read with host buffers at one bit per spin: site i of a chain is bit (i & 7) of byte (i >> 3) of
+ * that chain's N / 8 bytes, 1 = up (+1), 0 = down (-1); [nchains][N / 8].  An eighth of the bytes over PCIe; either device
+ * storage takes them.  Ising only, N % 32 == 0.  _bits_begin pairs with mcx_lattice_upload_commit like _upload_begin. */
+int32_t mcx_lattice_upload_bits(mcx_lattice *lat, const uint8_t *host_bits);
+int32_t mcx_lattice_upload_bits_begin(mcx_lattice *lat, const uint8_t *host_bits);
+int32_t mcx_lattice_download_bits(mcx_lattice *lat, uint8_t *host_bits);
 /* init!(sys, :up/:down/:zero/:random; rng) ising.jl:74, blume_capel.jl:106 (INIT stream) */
 int32_t mcx_lattice_init(mcx_lattice *lat, int32_t mode, uint64_t seed);
 

@@ -150,12 +150,15 @@ mutable struct DeviceIsing <: SpinSystems.AbstractIsing     # dispatches like an
     rule_key::Any
 end
 
-function DeviceIsing(ctx::DeviceCtx, dims::Vector{Int}; J=1, h=0, nchains::Integer=1)
+# storage = :int8 (one byte per spin, like `spins::Vector{Int8}` of ising.jl:433) or :bit (one bit per spin on the device;
+# 2-D / 3-D with Lx % 32 == 0).  Trajectories and observables do not depend on it.
+function DeviceIsing(ctx::DeviceCtx, dims::Vector{Int}; J=1, h=0, nchains::Integer=1, storage::Symbol=:int8)
+    storage in (:int8, :bit) || throw(ArgumentError("storage must be :int8 or :bit"))
     out = Ref{Ptr{Cvoid}}()
     d = Int32.(dims)
     check(ccall((:mcx_lattice_create, libmcx), Int32,
                 (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Int32, Int32, Ref{Ptr{Cvoid}}),
-                ctx.h, 0, length(d), d, nchains, 0, out))
+                ctx.h, 0, length(d), d, nchains, storage === :bit ? 1 : 0, out))
     check(ccall((:mcx_lattice_set_couplings, libmcx), Int32, (Ptr{Cvoid}, Float64, Float64, Float64), out[], J, h, 0.0))
     sys = DeviceIsing(out[], dims, nchains, J, h, nothing)
     finalizer(s -> ccall((:mcx_lattice_destroy, libmcx), Int32, (Ptr{Cvoid},), s.h), sys)
@@ -178,6 +181,18 @@ upload_begin!(sys::DeviceIsing, host::Vector{Int8}) =
     check(ccall((:mcx_lattice_upload_begin, libmcx), Int32, (Ptr{Cvoid}, Ptr{Int8}), getfield(sys, :h), host))
 upload_commit!(sys::DeviceIsing) =
     check(ccall((:mcx_lattice_upload_commit, libmcx), Int32, (Ptr{Cvoid},), getfield(sys, :h)))
+
+# The same transfers with a BitVector-like host buffer: site i is bit (i-1) & 7 of byte ((i-1) >> 3) + 1, 1 = up
+# (`reinterpret(UInt8, (spins .> 0).chunks)` is this format); an eighth of the bytes over PCIe.
+upload_bits!(sys::DeviceIsing, host::Vector{UInt8}) =
+    check(ccall((:mcx_lattice_upload_bits, libmcx), Int32, (Ptr{Cvoid}, Ptr{UInt8}), getfield(sys, :h), host))
+upload_bits_begin!(sys::DeviceIsing, host::Vector{UInt8}) =
+    check(ccall((:mcx_lattice_upload_bits_begin, libmcx), Int32, (Ptr{Cvoid}, Ptr{UInt8}), getfield(sys, :h), host))
+function download_bits(sys::DeviceIsing)
+    buf = Vector{UInt8}(undef, (prod(getfield(sys, :dims)) * getfield(sys, :nchains)) >> 3)
+    GC.@preserve buf check(ccall((:mcx_lattice_download_bits, libmcx), Int32, (Ptr{Cvoid}, Ptr{UInt8}), getfield(sys, :h), buf))
+    return buf
+end
 
 function sums(sys::DeviceIsing)
     n = sys.nchains

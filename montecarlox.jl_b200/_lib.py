@@ -53,6 +53,9 @@ SIGNATURES = {
     "mcx_lattice_download": (_i32, [_vp, _vp]),
     "mcx_lattice_upload_begin": (_i32, [_vp, _vp]),
     "mcx_lattice_upload_commit": (_i32, [_vp]),
+    "mcx_lattice_upload_bits": (_i32, [_vp, _vp]),
+    "mcx_lattice_upload_bits_begin": (_i32, [_vp, _vp]),
+    "mcx_lattice_download_bits": (_i32, [_vp, _vp]),
     "mcx_lattice_init": (_i32, [_vp, _i32, _u64]),
     "mcx_set_rule": (_i32, [_vp, _i32, _vp, _i32, _i32]),
     "mcx_set_labels": (_i32, [_vp, _vp]),

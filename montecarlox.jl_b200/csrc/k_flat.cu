@@ -41,6 +41,8 @@ struct FlatParams {
     uint64_t sweep0;
     int nsweeps, policy, step_shift;
     int wl_spec;                // Wang-Landau decisions at once: -1 adaptive (serial / 8 / 32), 0 serial only, 8, 32
+    int win_half, win_len;      // shared-memory window of the log-weight table around the chain's bin (WIN kernels):
+                                // win_half = the farthest a batch can move the bin, win_len = 4 * win_half + 1 entries
 };
 
 // rand < exp(log_ratio) for rand = m * 2^-32, m = hi << 16 | lo, decided exactly but cheaply:
@@ -100,10 +102,18 @@ __device__ __forceinline__ int neighbour_sum(const LatView &L, const uint8_t *ot
 //   phase 2 (lane 0):   the serial recurrence in the global observable: bin lookup, log-ratio,
 //                       _accept!, record_visit! / Wang-Landau update, running sums;
 //   phase 3 (32 lanes): accepted sites are written back.
-template <int OBS, int KIND, bool SMEM_HIST>
+//
+// WIN: the serial recurrence reads (Wang-Landau: and writes) log-weights of bins next to the chain's current one -- an
+// attempt moves the bin by at most a few -- so each warp keeps a window of the table, 4 x the farthest one batch can
+// travel, in shared memory: the dependent chain of an attempt then waits for a shared-memory load (~30 cycles) instead
+// of an L2 / HBM round trip per decision.  The window is recentred (dirty entries written back first) only when the next
+// batch could leave it; values are the table's own doubles, so trajectories are unchanged.
+template <int OBS, int KIND, bool SMEM_HIST, bool WIN>
 __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
 {
-    extern __shared__ uint32_t s_hist[];
+    extern __shared__ double s_dyn[];
+    double *s_win = s_dyn;                                                              // [kWarps][win_len]
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_dyn + (WIN ? kWarps * P.win_len : 0));
     __shared__ int32_t s_d[kWarps][kBatch];      // packed deltas of each prepared site
     __shared__ float s_hi[kWarps][kBatch];       // high half of the site's Float64 draw, as a float (exact)
     __shared__ uint8_t s_b[kWarps][kBatch];      // Bool draw (Blume-Capel proposal)
@@ -126,6 +136,26 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
         int dead = io < 0 || io >= P.nbins;
         if (dead && lane == 0) atomicExch(P.error, 1);
         double lw_old = dead ? 0.0 : lw[io];
+        double *win = s_win + (WIN ? w * P.win_len : 0);
+        int64_t wbase = 0;                       // bin of win[0]
+        bool win_valid = false;
+        int dlo = 0x7fffffff, dhi = -1;          // window entries lane 0 has written since the last load (Wang-Landau)
+        auto win_flush = [&]() {
+            if (WIN && KIND == MCX_FLAT_WANG_LANDAU && win_valid) {
+                __syncwarp();
+                const int lo = __shfl_sync(0xffffffffu, dlo, 0), hi = __shfl_sync(0xffffffffu, dhi, 0);
+                for (int k = lo + lane; k <= hi; k += 32) lw[wbase + k] = win[k];
+                dlo = 0x7fffffff; dhi = -1;
+                __syncwarp();
+            }
+        };
+        auto LWR = [&](int64_t b) -> double { return WIN ? win[b - wbase] : lw[b]; };
+        auto LWW = [&](int64_t b, double v) {
+            if (WIN) {
+                const int k = (int)(b - wbase);
+                win[k] = v; dlo = min(dlo, k); dhi = max(dhi, k);
+            } else lw[b] = v;
+        };
         // Boltzmann part of the two-component observable: H1 = J * sum_pair_interactions (a Float64 in the
         // reference, blume_capel.jl:123) carried as a running double; exact for integer-valued J
         double Ho1 = P.J * (P.J * (double)pair);
@@ -192,6 +222,15 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                     // the trajectory is unchanged; the cost drops from one dependent evaluation per attempt to
                     // one per ACCEPTED attempt (+ 1 per 32).  Wang-Landau changes lw at every attempt: serial loop.
                     const long long nacc_before = nacc;
+                    if (WIN && (!win_valid || io - P.win_half < wbase || io + P.win_half >= wbase + P.win_len)) {
+                        win_flush();
+                        wbase = io - P.win_len / 2;
+                        for (int k = lane; k < P.win_len; k += 32) {
+                            const int64_t b = wbase + k;
+                            win[k] = b >= 0 && b < P.nbins ? __ldcg(lw + b) : 0.0;
+                        }
+                        win_valid = true;
+                    }
                     // a decision loop that stops early (BoundsError, policy 0) must not leave the previous batch's
                     // flags behind for phase 3: attempts that are never decided are not accepted
 #pragma unroll
@@ -222,7 +261,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                                 bool acc_i = false;
                                 double lw_new = lw_old, Hn1 = Ho1;
                                 if (live && inside) {
-                                    lw_new = in == io ? lw_old : lw[in];
+                                    lw_new = in == io ? lw_old : LWR(in);
                                     double log_ratio;
                                     if (OBS == MCX_OBS_ENERGY) {
                                         log_ratio = lw_new - lw_old;
@@ -312,7 +351,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                                 bool acc_i = false;
                                 double lw_new = lw_cur, Hn1 = Ho1;
                                 if (live && inside) {
-                                    lw_new = in == io ? lw_cur : lw[in];
+                                    lw_new = in == io ? lw_cur : LWR(in);
                                     double log_ratio;
                                     if (OBS == MCX_OBS_ENERGY) {
                                         log_ratio = lw_new - lw_cur;
@@ -337,13 +376,13 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                                 const double lw_after = k < gend ? lw_last : lw_last - P.logf;
                                 if (k >= gend) {
                                     lw_old = lw_after;
-                                    if (lane == 0) lw[io] = lw_old;
+                                    if (lane == 0) LWW(io, lw_old);
                                     break;
                                 }
                                 if (__shfl_sync(0xffffffffu, (int)oob_i, k)) {
                                     lw_old = lw_after;
                                     if (lane == 0) {
-                                        if (nrej > 0) lw[io] = lw_old;
+                                        if (nrej > 0) LWW(io, lw_old);
                                         atomicExch(P.error, 1);
                                     }
                                     dead = 1;
@@ -357,10 +396,10 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                                 spin2 += __shfl_sync(0xffffffffu, dspin2, k);
                                 nacc += 1;
                                 Ho1 = __shfl_sync(0xffffffffu, Hn1, k);
-                                if (lane == 0 && nrej > 0) lw[io] = lw_after;
+                                if (lane == 0 && nrej > 0) LWW(io, lw_after);
                                 io = in_k;
                                 lw_old = lw_new_k - P.logf;                 // lw_old = lw_new; lw_old -= logf
-                                if (lane == 0) lw[io] = lw_old;
+                                if (lane == 0) LWW(io, lw_old);
                                 if (lane == k) mine_accepted = true;
                                 __syncwarp();                               // lane 0's stores before the next round's loads
                                 start = k + 1;
@@ -392,7 +431,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                             bool accepted = false;
                             double lw_new = lw_old, Hn1 = Ho1;
                             if (inside) {
-                                lw_new = in == io ? lw_old : lw[in];
+                                lw_new = in == io ? lw_old : LWR(in);
                                 double log_ratio;
                                 if (OBS == MCX_OBS_ENERGY) {
                                     log_ratio = lw_new - lw_old;
@@ -423,7 +462,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                                 }
                             } else {
                                 lw_old -= P.logf;
-                                lw[io] = lw_old;
+                                LWW(io, lw_old);
                             }
                         }
                     }
@@ -467,6 +506,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_flat_warp(FlatParams P)
                     __syncwarp();
                 }
             }
+        win_flush();
         if (lane == 0) {
             if (KIND == MCX_FLAT_MUCA && !SMEM_HIST && run_cnt) atomicAdd(P.hist + run_bin, run_cnt);
             st[SUM_PAIR] = pair; st[SUM_SPIN] = spin;
@@ -490,17 +530,38 @@ __global__ void k_muca_update(double *__restrict__ lw, const unsigned long long 
     if (hh > 0) lw[i] -= log((double)hh);
 }
 
-template <int OBS, int KIND>
-void launch_sweep_t(mcx_flat *f, const FlatParams &P)
+template <int OBS, int KIND, bool SMEM_HIST, bool WIN>
+void launch_sweep_k(mcx_flat *f, const FlatParams &P, size_t smem)
 {
     mcx_lattice *lat = f->lat;
     const int blocks = (lat->nchains + kWarps - 1) / kWarps;
-    const bool smem = KIND == MCX_FLAT_MUCA && f->nbins <= kSmemBins;
-    if (smem)
-        k_flat_warp<OBS, KIND, true><<<blocks, kWarps * 32, (size_t)f->nbins * sizeof(uint32_t), lat->ctx->stream>>>(P);
-    else
-        k_flat_warp<OBS, KIND, false><<<blocks, kWarps * 32, 0, lat->ctx->stream>>>(P);
+    auto kern = k_flat_warp<OBS, KIND, SMEM_HIST, WIN>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<blocks, kWarps * 32, smem, lat->ctx->stream>>>(P);
     lat->ctx->launches++;
+}
+
+template <int OBS, int KIND>
+void launch_sweep_t(mcx_flat *f, FlatParams &P)
+{
+    const bool smem_hist = KIND == MCX_FLAT_MUCA && f->nbins <= kSmemBins;
+    // window of the log-weight table per warp: an attempt moves the bin by at most `maxstep` bins
+    // (|dE| <= 2 nn for the Ising energy, |d sum s^2| <= 1), a batch of kBatch attempts by kBatch * maxstep
+    const int64_t max_dx = OBS == MCX_OBS_ENERGY ? 2 * f->lat->nn : 1;
+    const int64_t maxstep = (max_dx + f->step - 1) / f->step;
+    P.win_half = (int)(kBatch * (maxstep < 1 ? 1 : maxstep));
+    P.win_len = 4 * P.win_half + 1;
+    const size_t hist_bytes = smem_hist ? (size_t)f->nbins * sizeof(uint32_t) : 0;
+    const size_t win_bytes = (size_t)kWarps * P.win_len * sizeof(double);
+    const bool win = knobs().flat_window != 0 && win_bytes + hist_bytes <= 96 * 1024;
+    if (!win) P.win_half = P.win_len = 0;
+    if (smem_hist) {
+        if (win) launch_sweep_k<OBS, KIND, true, true>(f, P, win_bytes + hist_bytes);
+        else launch_sweep_k<OBS, KIND, true, false>(f, P, hist_bytes);
+    } else {
+        if (win) launch_sweep_k<OBS, KIND, false, true>(f, P, win_bytes);
+        else launch_sweep_k<OBS, KIND, false, false>(f, P, 0);
+    }
 }
 
 }  // namespace
@@ -560,6 +621,7 @@ int32_t mcx_flat_create(mcx_lattice *lat, int32_t kind, int32_t observable, int6
     FREQ(bin_step > 0 && nbins >= 1, MCX_ERR_ARGUMENT, "bins need step > 0 and at least one bin");
     FREQ(out_of_range_policy == 0 || out_of_range_policy == 1, MCX_ERR_ARGUMENT, "policy must be 0 (BoundsError) or 1 (reject)");
     FREQ(lat->view.halfN < ((int64_t)1 << 31), MCX_ERR_UNSUPPORTED, "flat-histogram chains support up to 2^32 sites per lattice");
+    FREQ(lat->storage == MCX_STORAGE_INT8, MCX_ERR_UNSUPPORTED, "flat-histogram chains visit single sites: they need int8 planes");
     if (observable == MCX_OBS_ENERGY)
         FREQ(lat->model == MCX_ISING && lat->J == 1.0 && lat->h == 0.0, MCX_ERR_UNSUPPORTED,
              "the energy observable is the integer path: Ising with J = 1, h = 0");

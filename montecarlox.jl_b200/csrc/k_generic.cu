@@ -191,6 +191,7 @@ static dim3 site_grid(const mcx_lattice *lat, int64_t n, int threads)
 
 void launch_pack(mcx_lattice *lat)
 {
+    if (lat->storage == MCX_STORAGE_BIT) { launch_pack_bits(lat); return; }
     if (launch_pack_ising2d(lat)) return;
     k_pack<<<site_grid(lat, lat->N, 256), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_staging, lat->N);
     lat->ctx->launches++;
@@ -198,6 +199,7 @@ void launch_pack(mcx_lattice *lat)
 
 void launch_unpack(mcx_lattice *lat)
 {
+    if (lat->storage == MCX_STORAGE_BIT) { launch_unpack_bits(lat); return; }
     if (launch_unpack_ising2d(lat)) return;
     k_unpack<<<site_grid(lat, lat->N, 256), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_staging, lat->N);
     lat->ctx->launches++;
@@ -205,6 +207,7 @@ void launch_unpack(mcx_lattice *lat)
 
 void launch_init(mcx_lattice *lat, int mode, uint64_t seed)
 {
+    if (lat->storage == MCX_STORAGE_BIT) { launch_init_bits(lat, mode, seed); return; }
     if (launch_init_ising2d(lat, mode, seed)) return;
     k_init<<<site_grid(lat, lat->N, 256), 256, 0, lat->ctx->stream>>>(
         lat->view, lat->N, mode, (uint32_t)seed, (uint32_t)(seed >> 32), lat->first_chain);
@@ -216,6 +219,7 @@ void launch_recompute(mcx_lattice *lat)
     const int n = lat->nchains * SUM_FIELDS;
     k_zero_sums<<<(n + 127) / 128, 128, 0, lat->ctx->stream>>>(lat->d_sums, lat->nchains, 1);
     lat->ctx->launches++;
+    if (lat->storage == MCX_STORAGE_BIT) { launch_recompute_bits(lat); return; }
     if (launch_recompute_ising2d(lat)) return;
     k_recompute<<<site_grid(lat, lat->view.halfN, 256), 256, 0, lat->ctx->stream>>>(lat->view, lat->d_sums);
     lat->ctx->launches++;

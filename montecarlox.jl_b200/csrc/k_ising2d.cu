@@ -704,6 +704,7 @@ void launch_t(mcx_lattice *lat, uint64_t t)
 template <int COLOUR>
 void launch_c(mcx_lattice *lat, uint64_t t)
 {
+    if (lat->storage == MCX_STORAGE_BIT) { launch_half_sweep_bits2d(lat, COLOUR, t); return; }   // k_bits.cu, same launch ranges
     const bool track = lat->track_sums;
     if (lat->rule == MCX_HEATBATH) {
         if (track) launch_t<COLOUR, true, true>(lat, t); else launch_t<COLOUR, true, false>(lat, t);
@@ -784,7 +785,7 @@ static bool aux_streams(mcx_ctx *ctx)
 
 bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
+    if (lat->slab) return false;
     // which vectorised half-sweep serves this lattice (each launcher re-checks its own conditions)
     const bool d3 = lat->ndim == 3 && lat->model == MCX_ISING && lat->view.Lx % 32 == 0 && knobs().ising3d != 0;
     const bool bc = lat->fast2d && lat->model == MCX_BLUME_CAPEL;
@@ -829,7 +830,7 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 
 bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->nchains != 1) return false;
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->nchains != 1) return false;
     if (lat->slab && !(lat->slab->attached && lat->slab->remote)) return false;      // in-process slabs advance in lockstep
     if (knobs().variant >= 0 || knobs().rows_per_strip >= 0) return false;
     const int bands_env = knobs().bands;
@@ -875,7 +876,8 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
 
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
 {
-    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8) return false;
+    if (!lat->fast2d || lat->model != MCX_ISING) return false;
+    if (lat->storage == MCX_STORAGE_BIT) { launch_half_sweep_bits2d(lat, colour, t); return true; }   // the only 2-D kernel on bit planes
     // small lattices: a chain yields fewer than one CTA of 16-byte segments x strips, so most lanes of
     // this kernel would idle; the rows-of-8 kernel (8 sites per thread) fills the machine instead
     {

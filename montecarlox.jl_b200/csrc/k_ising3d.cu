@@ -8,6 +8,7 @@
 // Randomness and decision exactly as in k_ising2d (two Philox4x32-10 blocks per thread-row, packed 15-bit
 // comparison against a pair-threshold table, exact redo on ties), with #up-neighbours in 0..6:
 // table index s * 7 + nup.  Bit-identical to k_sweep_rows8 and k_sweep_generic.
+#include "k_bits.cuh"
 #include "mcx_internal.h"
 
 #include <cstdlib>
@@ -245,6 +246,126 @@ k_ising3d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
 }
 
 
+// The same half-sweep on one-bit-per-spin planes (MCX_STORAGE_BIT, layout in k_bits.cuh): a trip loads one word of
+// the target plane (both rows), one new word of the other plane and one word each of the z - 1 / z + 1 planes, expands
+// them to 0/1 bytes and runs update_row3 unchanged.
+template <int COLOUR, bool HEATBATH, bool TRACK>
+__global__ void __launch_bounds__(k3Threads, 5)
+k_ising3d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g, const int32_t *__restrict__ labels,
+               long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi, uint64_t t, uint32_t first_chain, int R,
+               int strips_per_plane, int blocks_per_chain, int nitems)
+{
+    __shared__ uint32_t s_pair[k3PairWords];
+    __shared__ uint32_t s_thi[k3Table], s_tlo[k3Table];
+    int cur_label = -1;
+
+    const int half = L.half;
+    const int nseg = half >> 4;
+    const int64_t G = (int64_t)strips_per_plane * L.Lz * nseg;
+    const int lane = threadIdx.x & 31;
+    const uint32_t t_lo = (uint32_t)t;
+    const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP), c2lo = ctr_word2(t, 1, TAG_SWEEP);
+    const int64_t plane_words = (int64_t)(L.Ly >> 1) * nseg;      // words of one z-plane of a colour plane
+
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int chain = item / blocks_per_chain;
+        const int label = labels[chain];
+        if (label != cur_label) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < k3Table; i += k3Threads) {
+                s_thi[i] = thi_g[label * k3Table + i];
+                s_tlo[i] = tlo_g[label * k3Table + i];
+            }
+            for (int i = threadIdx.x; i < k3Table * k3Table; i += k3Threads) {
+                const int i1 = i / k3Table, i0 = i - i1 * k3Table;
+                const uint32_t a = min(thi_g[label * k3Table + i0] >> 1, 0x7fffu);
+                const uint32_t b = min(thi_g[label * k3Table + i1] >> 1, 0x7fffu);
+                s_pair[i1 * k3RowWords + i0] = a | (b << 16);
+            }
+            __syncthreads();
+            cur_label = label;
+        }
+        const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * k3Threads + threadIdx.x;
+        const bool active = g0 < G;
+        const int64_t g = active ? g0 : G - 1;
+        const int sidx = (int)(g / nseg);
+        const int seg = (int)(g - (int64_t)sidx * nseg);
+        const int z = sidx / strips_per_plane;
+        const int y0 = (sidx - z * strips_per_plane) * R;         // even
+        const uint32_t chain_id = first_chain + (uint32_t)chain;
+        const int pa = (COLOUR + z) & 1;
+
+        uint32_t *tgt = reinterpret_cast<uint32_t *>(plane_ptr(L, chain, COLOUR)) + (int64_t)z * plane_words;
+        const uint32_t *__restrict__ othp = reinterpret_cast<const uint32_t *>(plane_ptr(L, chain, COLOUR ^ 1));
+        const uint32_t *__restrict__ oth = othp + (int64_t)z * plane_words;
+        const uint32_t *__restrict__ othF = othp + (int64_t)(z == 0 ? L.Lz - 1 : z - 1) * plane_words;
+        const uint32_t *__restrict__ othB = othp + (int64_t)(z == L.Lz - 1 ? 0 : z + 1) * plane_words;
+        const int col = seg << 4;
+        const int colL = (seg == 0 ? half : col) - 1;
+        const int colR = (seg == nseg - 1) ? 0 : col + 16;
+        const bool loadL = (lane == 0) || (seg == 0);
+        const bool loadR = (lane == 31) || (seg == nseg - 1);
+        const bool edgeA = pa == 0 ? loadL : loadR, edgeB = pa == 0 ? loadR : loadL;
+        const int colA = pa == 0 ? colL : colR, colB = pa == 0 ? colR : colL;
+        const int segA = colA >> 4, segB = colB >> 4;
+        const int bitA = bit_pos(0, colA & 15), bitB = bit_pos(1, colB & 15);
+
+        const int yU = y0 == 0 ? L.Ly - 1 : y0 - 1;               // odd: second row of its word
+        int64_t woff = (int64_t)(y0 >> 1) * nseg;                 // word offset of this trip's row pair inside a z-plane
+        uint4 U = bits_expand(oth[(int64_t)(yU >> 1) * nseg + seg], 1);
+        uint32_t Wc = oth[woff + seg];
+        uint4 C = bits_expand(Wc, 0);
+        uint32_t blk = (uint32_t)((((int64_t)z * L.Ly + y0) * half + col) >> 3);
+        const uint32_t blk_step = (uint32_t)(half >> 3);
+        Acc3 acc;
+
+#pragma unroll 1
+        for (int r = 0; r < R; r += 2) {
+            const int y = y0 + r;
+            const uint32_t We = oth[((y + 2 == L.Ly) ? 0 : woff + nseg) + seg];
+            const uint32_t Tw = tgt[woff + seg];
+            const uint32_t Fw = othF[woff + seg], Bw = othB[woff + seg];
+            uint32_t sideA = 0, sideB = 0;
+            if (edgeA) sideA = (oth[woff + segA] >> bitA) & 1u;
+            if (edgeB) sideB = (oth[woff + segB] >> bitB) & 1u;
+            const uint4 D = bits_expand(Wc, 1);
+            const uint32_t cl = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24, cr = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
+            const uint32_t dl = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24, dr = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
+            uint32_t sA = pa == 0 ? cl : cr, sB = pa == 0 ? dr : dl;
+            if (edgeA) sA = sideA;
+            if (edgeB) sB = sideB;
+            const uint4 Na = update_row3<HEATBATH, TRACK>(bits_expand(Tw, 0), U, C, D, add4(bits_expand(Fw, 0), bits_expand(Bw, 0)), sA, pa,
+                                                          blk, t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
+            uint32_t out = bits_compress(Na);
+            const uint4 E = bits_expand(We, 0);
+            const uint4 Nb = update_row3<HEATBATH, TRACK>(bits_expand(Tw, 1), C, D, E, add4(bits_expand(Fw, 1), bits_expand(Bw, 1)), sB,
+                                                          pa ^ 1, blk + blk_step, t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_pair, s_thi,
+                                                          s_tlo, acc, active);
+            out += bits_compress(Nb) << 4;
+            if (active) tgt[woff + seg] = out;
+            U = D; C = E; Wc = We;
+            woff += nseg; blk += 2 * blk_step;
+        }
+
+        const int nflip = warp_sum((int)acc.flips);
+        int dspin = 0, dpair = 0;
+        if (TRACK) {
+            const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
+            dspin = 2 * nflip - 4 * ss;
+            dpair = -8 * sn + 24 * ss + 4 * nn_ - 12 * nflip;
+        }
+        if (lane == 0) {
+            unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
+            if (nflip) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nflip);
+            if (TRACK) {
+                if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
+                if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
+            }
+        }
+    }
+}
+
+
 template <int COLOUR, bool HEATBATH, bool TRACK>
 void launch_3d(mcx_lattice *lat, uint64_t t)
 {
@@ -268,8 +389,9 @@ void launch_3d(mcx_lattice *lat, uint64_t t)
     const int64_t G = (int64_t)strips_per_plane * L.Lz * nseg;
     const int blocks_per_chain = (int)((G + k3Threads - 1) / k3Threads);
     const int nitems = (int)((int64_t)blocks_per_chain * nch);
-    auto kern = k_ising3d<COLOUR, HEATBATH, TRACK>;
-    static thread_local int resident = 0;
+    auto kern = lat->storage == MCX_STORAGE_BIT ? k_ising3d_bits<COLOUR, HEATBATH, TRACK> : k_ising3d<COLOUR, HEATBATH, TRACK>;
+    static thread_local int resident_of[2] = {0, 0};
+    int &resident = resident_of[lat->storage == MCX_STORAGE_BIT ? 1 : 0];
     if (!resident) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, k3Threads, 0);
         if (resident < 1) resident = 1;
@@ -287,9 +409,10 @@ void launch_3d(mcx_lattice *lat, uint64_t t)
 // false: not applicable (shape or table layout), nothing launched
 bool launch_sweep_ising3d(mcx_lattice *lat, int colour, uint64_t t)
 {
-    if (lat->ndim != 3 || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->view.Lx % 32 != 0) return false;
-    if (lat->view.Ly % 2 != 0 || lat->table_len != k3Table || knobs().ising3d == 0) return false;
-    if ((int64_t)(lat->view.Ly / 2) * lat->view.Lz * (lat->view.half >> 4) < 96) return false;     // tiny: rows-of-8 kernel
+    if (lat->ndim != 3 || lat->model != MCX_ISING || lat->view.Lx % 32 != 0) return false;
+    const bool bits = lat->storage == MCX_STORAGE_BIT;          // bit planes have no other kernel: always here
+    if (lat->view.Ly % 2 != 0 || lat->table_len != k3Table || (knobs().ising3d == 0 && !bits)) return false;
+    if (!bits && (int64_t)(lat->view.Ly / 2) * lat->view.Lz * (lat->view.half >> 4) < 96) return false;     // tiny: rows-of-8 kernel
     const bool track = lat->track_sums, hb = lat->rule == MCX_HEATBATH;
     if (colour == 0) {
         if (hb) { if (track) launch_3d<0, true, true>(lat, t); else launch_3d<0, true, false>(lat, t); }

@@ -62,7 +62,7 @@ void knobs_refresh()
     k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
     k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
     k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
-    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST");
+    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST"); k.flat_window = knob("MCX_FLAT_WINDOW");
     g_knobs_ready = true;
 }
 const Knobs &knobs()
@@ -237,6 +237,7 @@ static void lattice_free(mcx_lattice *lat)
     cudaFree(lat->d_tlo);
     cudaFree(lat->d_labels);
     cudaFree(lat->d_staging);
+    cudaFree(lat->d_hostbits);
     cudaFree(lat->d_queue);
     cudaFree(lat->d_series);
     if (lat->copy_stream) {
@@ -256,7 +257,9 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
     REQUIRE(model == MCX_ISING || model == MCX_BLUME_CAPEL, MCX_ERR_ARGUMENT, "unknown model %d", model);
     REQUIRE(ndim >= 1 && ndim <= 3, MCX_ERR_ARGUMENT, "ndim must be 1, 2 or 3 (got %d)", ndim);
     REQUIRE(nchains >= 1 && nchains <= 65535, MCX_ERR_ARGUMENT, "nchains must be in [1, 65535] (got %d)", nchains);
-    REQUIRE(storage == MCX_STORAGE_INT8, MCX_ERR_UNSUPPORTED, "storage %d not available (int8 planes only)", storage);
+    REQUIRE(storage == MCX_STORAGE_INT8 || storage == MCX_STORAGE_BIT, MCX_ERR_ARGUMENT, "unknown storage %d", storage);
+    REQUIRE(storage == MCX_STORAGE_INT8 || bits_shape_ok(model, ndim, dims), MCX_ERR_UNSUPPORTED,
+            "one-bit storage holds Ising lattices in 2 or 3 dimensions with Lx %% 32 == 0 (Blume-Capel has three states; other shapes: int8)");
     int64_t N = 1;
     for (int d = 0; d < ndim; ++d) {
         REQUIRE(dims[d] >= 4 && dims[d] % 2 == 0, MCX_ERR_ARGUMENT,
@@ -278,7 +281,7 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
     v.Lx = lat->dims[0]; v.Ly = lat->dims[1]; v.Lz = lat->dims[2]; v.half = v.Lx / 2;
     v.ndim = ndim; v.nn = 2 * ndim; v.model = model; v.nchains = nchains;
     v.halfN = N / 2;
-    v.plane_stride = (v.halfN + 255) / 256 * 256;
+    v.plane_stride = ((storage == MCX_STORAGE_BIT ? v.halfN / 8 : v.halfN) + 255) / 256 * 256;     // bytes
     lat->fast2d = (ndim == 2) && (v.Lx % 32 == 0);
     lat->track_sums = true;
     const size_t plane_bytes = (size_t)v.plane_stride * 2 * (size_t)nchains;
@@ -380,6 +383,8 @@ int32_t mcx_lattice_upload_commit(mcx_lattice *lat)
     REQUIRE(lat->upload_pending, MCX_ERR_STATE, "no upload pending on this handle: call mcx_lattice_upload_begin first");
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     CUDA_TRY(cudaStreamWaitEvent(lat->ctx->stream, lat->ev_copied, 0));
+    if (lat->pending_bits) launch_hostbits_to_staging(lat, lat->d_hostbits, lat->ctx->stream);
+    lat->pending_bits = false;
     launch_pack(lat);
     CUDA_TRY(cudaEventRecord(lat->ev_packed, lat->ctx->stream));
     lat->packed_recorded = true;
@@ -399,6 +404,79 @@ int32_t mcx_lattice_download(mcx_lattice *lat, int8_t *host_spins)
     launch_unpack(lat);
     CUDA_TRY(cudaMemcpyAsync(host_spins, lat->d_staging, (size_t)lat->N * (size_t)lat->nchains,
                              cudaMemcpyDeviceToHost, lat->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
+    return check_launch(lat->ctx);
+}
+
+// ---- the same transfers with host buffers at one bit per spin (bit i & 7 of byte i >> 3 of a chain = site i, 1 = up):
+// an eighth of the bytes over PCIe; converted on the device through the staging buffer, so either storage takes them
+static int32_t ensure_hostbits(mcx_lattice *lat)
+{
+    REQUIRE(lat->model == MCX_ISING, MCX_ERR_UNSUPPORTED, "bit buffers hold two-state (Ising) spins only");
+    REQUIRE(lat->N % 32 == 0, MCX_ERR_UNSUPPORTED, "bit buffers need a site count divisible by 32 (N = %lld)", (long long)lat->N);
+    if (lat->d_hostbits) return MCX_OK;
+    CUDA_TRY(cudaMalloc(&lat->d_hostbits, (size_t)lat->N / 8 * (size_t)lat->nchains));
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_upload_bits(mcx_lattice *lat, const uint8_t *host_bits)
+{
+    REQUIRE(lat && host_bits, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(!lat->upload_pending, MCX_ERR_STATE, "an upload is pending on this handle (the staging buffer is in use): commit it first");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    int32_t st = ensure_staging(lat);
+    if (st == MCX_OK) st = ensure_hostbits(lat);
+    if (st != MCX_OK) return st;
+    CUDA_TRY(cudaMemcpyAsync(lat->d_hostbits, host_bits, (size_t)lat->N / 8 * (size_t)lat->nchains, cudaMemcpyHostToDevice,
+                             lat->ctx->stream));
+    launch_hostbits_to_staging(lat, lat->d_hostbits, lat->ctx->stream);
+    launch_pack(lat);
+    if (lat->copy_stream) {
+        CUDA_TRY(cudaEventRecord(lat->ev_packed, lat->ctx->stream));
+        lat->packed_recorded = true;
+    }
+    launch_recompute(lat);
+    lat->sums_dirty = false;
+    return check_launch(lat->ctx);
+}
+
+int32_t mcx_lattice_upload_bits_begin(mcx_lattice *lat, const uint8_t *host_bits)
+{
+    REQUIRE(lat && host_bits, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(!lat->upload_pending, MCX_ERR_STATE, "an upload is already pending on this handle: commit it first");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    int32_t st = ensure_staging(lat);
+    if (st == MCX_OK) st = ensure_hostbits(lat);
+    if (st != MCX_OK) return st;
+    if (!lat->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&lat->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&lat->ev_copied, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&lat->ev_packed, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(lat->ev_packed, lat->ctx->stream));
+        lat->packed_recorded = true;
+    }
+    // d_hostbits is read by the conversion that mcx_lattice_upload_commit queues before it records ev_packed
+    if (lat->packed_recorded) CUDA_TRY(cudaStreamWaitEvent(lat->copy_stream, lat->ev_packed, 0));
+    CUDA_TRY(cudaMemcpyAsync(lat->d_hostbits, host_bits, (size_t)lat->N / 8 * (size_t)lat->nchains, cudaMemcpyHostToDevice,
+                             lat->copy_stream));
+    CUDA_TRY(cudaEventRecord(lat->ev_copied, lat->copy_stream));
+    lat->upload_pending = true;
+    lat->pending_bits = true;
+    return MCX_OK;
+}
+
+int32_t mcx_lattice_download_bits(mcx_lattice *lat, uint8_t *host_bits)
+{
+    REQUIRE(lat && host_bits, MCX_ERR_ARGUMENT, "NULL argument");
+    REQUIRE(!lat->upload_pending, MCX_ERR_STATE, "an upload is pending on this handle (the staging buffer is in use): commit it first");
+    CUDA_TRY(cudaSetDevice(lat->ctx->device));
+    int32_t st = ensure_staging(lat);
+    if (st == MCX_OK) st = ensure_hostbits(lat);
+    if (st != MCX_OK) return st;
+    launch_unpack(lat);
+    launch_staging_to_hostbits(lat, lat->d_hostbits, lat->ctx->stream);
+    CUDA_TRY(cudaMemcpyAsync(host_bits, lat->d_hostbits, (size_t)lat->N / 8 * (size_t)lat->nchains, cudaMemcpyDeviceToHost,
+                             lat->ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(lat->ctx->stream));
     return check_launch(lat->ctx);
 }
@@ -537,7 +615,7 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
         return check_launch(lat->ctx);
     }
     // test hooks: MCX_FORCE_GENERIC=1 -> shape-generic kernel, =2 -> rows-of-8 kernel
-    const int force = knobs().force_generic > 0 ? knobs().force_generic : 0;
+    const int force = knobs().force_generic > 0 && lat->storage == MCX_STORAGE_INT8 ? knobs().force_generic : 0;   // byte-plane kernels
     bool try_series = force == 0;        // whole-series launchers (resident kernel, chain groups) still worth asking
     for (int64_t s = 0; s < nsweeps;) {
         if (try_series) {

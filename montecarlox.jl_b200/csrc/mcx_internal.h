@@ -45,6 +45,8 @@ struct mcx_lattice {
     int64_t steps;              // attempts per chain since the last reset (same for every chain)
     double J, h, D;
     int8_t *d_staging;          // [nchains][N] reference-order spins for upload/download
+    void *d_hostbits;           // [nchains][N / 8] reference-order spins at one bit each (mcx_lattice_upload_bits / _download_bits)
+    bool pending_bits;          // the pending split upload is a bit buffer (in d_hostbits), not an int8 one
     // split upload (mcx_lattice_upload_begin / _commit): H2D into d_staging on a copy stream of the handle
     cudaStream_t copy_stream;
     cudaEvent_t ev_copied, ev_packed;   // copy finished; last conversion out of d_staging finished
@@ -110,6 +112,7 @@ struct Knobs {
     int queue;        // MCX_QUEUE: 1 = series of sweeps through the ticket-queue kernel (k_queue.cu)
     int queue_grid;   // MCX_QUEUE_GRID: CTAs of the persistent rounds kernel (tuning hook; default: every resident slot)
     int pt_persist;   // MCX_PT_PERSIST: 1 = mcx_pt_run as one persistent launch whenever the shape allows, 0 = never
+    int flat_window;  // MCX_FLAT_WINDOW: 0 = flat-histogram chains read the log-weight table from global memory (no shared-memory window)
     int wl_spec;      // MCX_WL_SPEC: Wang-Landau attempts decided at once (0 = serial loop, 8, 32; unset = adaptive)
 };
 const Knobs &knobs();
@@ -144,7 +147,18 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps);
 // k_bc2d.cu: vectorised 2-D Blume-Capel half-sweep (Metropolis / Glauber, Lx % 32 == 0)
 bool launch_sweep_bc2d(mcx_lattice *lat, int colour, uint64_t t);       // false: not applicable, nothing launched
 
-// k_ising3d.cu: vectorised 3-D Ising half-sweep (Lx % 32 == 0)
+// k_bits.cu: MCX_STORAGE_BIT (one bit per spin; Ising, Lx % 32 == 0, 2-D / 3-D): layout conversion, init, recompute and the
+// 2-D half-sweep (whole batch, chain group or row band as set in g_launch_range); host bit buffers <-> staging for both storages
+bool bits_shape_ok(int model, int ndim, const int32_t *dims);
+void launch_pack_bits(mcx_lattice *lat);
+void launch_unpack_bits(mcx_lattice *lat);
+void launch_init_bits(mcx_lattice *lat, int mode, uint64_t seed);
+void launch_recompute_bits(mcx_lattice *lat);
+void launch_half_sweep_bits2d(mcx_lattice *lat, int colour, uint64_t t);
+void launch_hostbits_to_staging(mcx_lattice *lat, const void *d_bits, cudaStream_t stream);
+void launch_staging_to_hostbits(mcx_lattice *lat, void *d_bits, cudaStream_t stream);
+
+// k_ising3d.cu: vectorised 3-D Ising half-sweep (Lx % 32 == 0), int8 or bit planes
 bool launch_sweep_ising3d(mcx_lattice *lat, int colour, uint64_t t);    // false: not applicable, nothing launched
 
 // k_slab.cu

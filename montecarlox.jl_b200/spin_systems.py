@@ -56,6 +56,7 @@ def default_context(device=0):
     return _contexts[device]
 
 
+_STORAGE = {"int8": _lib.STORAGE_INT8, "bit": _lib.STORAGE_BIT}
 _INIT = {"up": _lib.INIT_UP, "down": _lib.INIT_DOWN, "zero": _lib.INIT_ZERO, "random": _lib.INIT_RANDOM}
 
 
@@ -63,9 +64,12 @@ class AbstractSpinSystem:
     """abstractions.jl:12; a batch of `nchains` independent lattices of identical shape."""
     model = None
 
-    def __init__(self, dims, J=1, h=0, D=0, nchains=1, ctx=None, periodic=True):
+    def __init__(self, dims, J=1, h=0, D=0, nchains=1, ctx=None, periodic=True, storage="int8"):
         if not periodic:
             raise ValueError("the checkerboard backend supports periodic lattices only")
+        if storage not in _STORAGE:
+            raise ValueError("storage must be 'int8' or 'bit' (got %r)" % (storage,))
+        self.storage = storage
         self.dims = [int(d) for d in dims]
         self.J, self.h, self.D = J, h, D
         self.nchains = int(nchains)
@@ -73,7 +77,7 @@ class AbstractSpinSystem:
         self.ctx = ctx or default_context()
         hd = C.c_void_p()
         d = (C.c_int32 * len(self.dims))(*self.dims)
-        check(lib().mcx_lattice_create(self.ctx.h, self.model, len(self.dims), d, self.nchains, _lib.STORAGE_INT8,
+        check(lib().mcx_lattice_create(self.ctx.h, self.model, len(self.dims), d, self.nchains, _STORAGE[storage],
                                        C.byref(hd)))
         self.h_lat = hd
         check(lib().mcx_lattice_set_couplings(hd, float(J), float(h), float(D)))
@@ -96,12 +100,12 @@ class AbstractSpinSystem:
         return {"cls_dims": self.dims, "J": self.J, "h": self.h, "D": self.D, "nchains": self.nchains,
                 "device": self.ctx.device, "spins": self.spins.copy(), "seed": seed.value, "next_sweep": nxt.value,
                 "labels": self.get_labels(), "rule": getattr(self, "_rule_tables", None),
-                "first_chain": getattr(self, "_first_chain", 0),
+                "first_chain": getattr(self, "_first_chain", 0), "storage": self.storage,
                 "accepted": np.atleast_1d(acc).astype(np.int64), "steps": int(np.atleast_1d(steps)[0])}
 
     def __setstate__(self, st):
         AbstractSpinSystem.__init__(self, st["cls_dims"], st["J"], st["h"], st["D"], st["nchains"],
-                                    default_context(st["device"]))
+                                    default_context(st["device"]), storage=st.get("storage", "int8"))
         self.spins = st["spins"]
         if st["rule"] is not None:
             self.set_rule(*st["rule"])
@@ -129,6 +133,25 @@ class AbstractSpinSystem:
         if v.size != self.nchains * self.N:
             raise ValueError("spins must have nchains*N = %d entries" % (self.nchains * self.N))
         check(lib().mcx_lattice_upload(self.h_lat, v.ctypes.data))
+
+    # ---- the same field at one bit per spin on the host side (site i = bit i & 7 of byte i >> 3, 1 = up): an eighth of
+    # the PCIe traffic; numpy's packbits(bitorder="little") of (spins > 0) is this format
+    @property
+    def spin_bits(self):
+        out = np.empty(self.nchains * self.N // 8, dtype=np.uint8)
+        check(lib().mcx_lattice_download_bits(self.h_lat, out.ctypes.data))
+        return out if self.nchains == 1 else out.reshape(self.nchains, self.N // 8)
+
+    @spin_bits.setter
+    def spin_bits(self, v):
+        v = np.ascontiguousarray(v, dtype=np.uint8).reshape(-1)
+        if v.size * 8 != self.nchains * self.N:
+            raise ValueError("spin_bits must have nchains*N/8 = %d bytes" % (self.nchains * self.N // 8))
+        check(lib().mcx_lattice_upload_bits(self.h_lat, v.ctypes.data))
+
+    def upload_bits_begin(self, host_ptr):
+        """`upload_begin` for a bit buffer (raw pointer); `upload_commit` makes it the lattice."""
+        check(lib().mcx_lattice_upload_bits_begin(self.h_lat, C.c_void_p(host_ptr)))
 
     def upload_from(self, host_ptr):
         """Upload from a raw host pointer (e.g. pinned memory) without touching numpy."""
@@ -253,14 +276,15 @@ class AbstractIsing(AbstractSpinSystem):
 
 
 class Ising(AbstractIsing):
-    """Ising(dims; J=1, periodic=true, h=0) (ising.jl:413-424) on a periodic grid."""
+    """Ising(dims; J=1, periodic=true, h=0) (ising.jl:413-424) on a periodic grid.  `storage="bit"` keeps the spins at
+    one bit each on the device (2-D / 3-D, Lx % 32 == 0); trajectories and observables do not depend on it."""
 
 
 class IsingLatticeOptim(AbstractIsing):
     """IsingLatticeOptim(Lx, Ly) (ising.jl:430-461): 2-D, J=1, h=0."""
 
-    def __init__(self, Lx, Ly, nchains=1, ctx=None):
-        super().__init__([Lx, Ly], 1, 0, 0, nchains, ctx)
+    def __init__(self, Lx, Ly, nchains=1, ctx=None, storage="int8"):
+        super().__init__([Lx, Ly], 1, 0, 0, nchains, ctx, storage=storage)
 
 
 class AbstractBlumeCapel(AbstractSpinSystem):

@@ -205,7 +205,7 @@ class WangLandauWindows:
     """
 
     def __init__(self, dims, nwindows, walkers=1, overlap=0.5, seed=42, logf=1.0, bins=None, backend=None,
-                 device=None, window_factory=None, windows=None):
+                 device=None, window_factory=None, windows=None, replicate_seed=False):
         self.dims = [int(d) for d in dims]
         if len(self.dims) not in (2, 3) or any(d % 2 or d < 4 for d in self.dims):
             raise ValueError("windowed Wang-Landau needs a 2-D or 3-D lattice with even dimensions >= 4")
@@ -237,6 +237,10 @@ class WangLandauWindows:
         # global walker number = window * walkers + walker: the random streams do not depend on the rank count
         self.local = [make(self.dims, self.walkers, self.seed, w * self.walkers)
                       for w in range(self.first, self.first + self.count)]
+        # replicate_seed: drive ONE walker per window into it and start all the window's walkers from that
+        # configuration (their random streams differ, so they separate at once); the drive then costs one walker per
+        # window instead of `walkers` -- what makes thousands of walkers per GPU practical
+        self._make, self.replicate_seed = make, bool(replicate_seed)
         self._lw = [None] * self.count          # last tables read back, [walkers, width] per local window
         self._lw_stage = [None] * self.count    # tables at the start of the current logf stage
         self.steps = 0
@@ -271,7 +275,14 @@ class WangLandauWindows:
         for j, eng in enumerate(self.local):
             w = self.first + j
             lo, hi = self.window_energies(w)
-            self._drive(eng, lo, hi)
+            if self.replicate_seed and self.walkers > 1:
+                one = self._make(self.dims, 1, self.seed, w * self.walkers)
+                self._drive(one, lo, hi)
+                first = np.asarray(one.spins()).reshape(1, self.N)
+                one.close()
+                eng.set_spins(np.repeat(first, self.walkers, axis=0))
+            else:
+                self._drive(eng, lo, hi)
             eng.open_window(lo, self.bins.step, self.width)
             self._lw[j] = np.zeros((self.walkers, self.width))
             self._lw_stage[j] = self._lw[j].copy()
@@ -279,7 +290,7 @@ class WangLandauWindows:
         return self
 
     def _drive(self, eng, lo, hi):
-        k = self.walkers
+        k = eng.k
         centre = 0.5 * (lo + hi)
         sign = 1.0 if centre <= 0 else -1.0                       # E > 0 is reached with beta < 0
         ground = np.tile(self._ground_state(sign < 0), (k, 1))
@@ -327,6 +338,24 @@ class WangLandauWindows:
             self._lw[j] = eng.logweight()
         self.steps += int(nsweeps) * self.N * self.walkers * self.count
         return None
+
+    def sweep_device_(self, nsweeps=1):
+        """`sweep_` without reading the tables back: queues the sweeps of every local window and returns; `sync_()`
+        waits for them.  The host copies of the tables go stale until the next `sweep_` / `refresh_()`."""
+        if not self.prepared:
+            raise AssertionError("call prepare_() first")
+        for eng in self.local:
+            eng.wl_sweep_(nsweeps, self.logf)
+        self.steps += int(nsweeps) * self.N * self.walkers * self.count
+        return None
+
+    def sync_(self):
+        for eng in self.local:
+            eng.ctx.sync()
+
+    def refresh_(self):
+        for j, eng in enumerate(self.local):
+            self._lw[j] = eng.logweight()
 
     def visits(self):
         """[count][walkers, width] visits per bin since the last update_ (the histogram the reference's
