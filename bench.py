@@ -161,6 +161,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.config != "c2":
+        # the other configs: the same oracle legs that cpu_baseline reports, on all host threads
+        leg = {"c1": lambda: cpu_leg_c1(_threads(), 20000), "c3": lambda: cpu_leg_c3(_threads(), args.cpu_seconds),
+               "c4": lambda: cpu_leg_c4(_threads()), "c5": lambda: cpu_leg_c5(min(_threads(), 32))}[args.config]()
+        print(json.dumps({"impl": "reference", "metric": "pt_sweeps_per_s" if args.config == "c3" else METRIC, "value": leg["value"],
+                          "unit": leg["unit"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "BASELINE.json config %s on the host cores (oracle port)" % args.config},
+                          "cpu_baseline": leg, "e2e": {"value": leg["value"], "unit": leg["unit"], "h2d_bytes_per_step": 0,
+                                                       "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
     from oracle import oracle
     oracle.build()
     try:
@@ -192,6 +203,29 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def numa_bind(local):
+    """Run this rank's host thread (and, by first touch, its pinned buffers) on the NUMA node its GPU hangs off: eight
+    ranks streaming 256 MiB steps through one socket's memory controllers is what bent the 8-GPU e2e curve."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return {"node": None, "why": "no NUMA affinity reported for %s" % bdf}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus), "gpu": bdf}
+    except Exception as e:
+        return {"node": None, "why": repr(e)}
+
+
 # ------------------------------------------------------------------ ours
 def run_ours(args):
     import numpy as np
@@ -205,6 +239,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = numa_bind(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # an explicit (non-default) stream shared by torch and libmcx_b200, so that torch.cuda.Event
@@ -225,10 +260,35 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.config != "c2":
+        # another BASELINE.json config as the line's own metric
+        if args.config == "c1":
+            leg = bench_c1(m, ctx, stream, args, cpu=not args.no_cpu and rank == 0)
+        elif args.config == "c3":
+            leg = bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, rounds=max(args.steps, 1), every=200)
+            leg["every_sweep"] = bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, rounds=300, every=1)
+            leg["config"] = {"workload": "2D Ising L=1024 ParallelTempering, 256 replicas sharded over %d GPU(s), exchange every 200 sweeps "
+                                         "(BASELINE.json configs[2])" % world}
+            if rank == 0 and not args.no_cpu:
+                leg["cpu_baseline"] = cpu_leg_c3(_threads(), args.cpu_seconds)
+        elif args.config == "c4":
+            leg = bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, cpu=not args.no_cpu)
+        else:
+            leg = bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=16, walkers=64, cpu=not args.no_cpu)
+        leg.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                    "scaling": "strong" if args.config in ("c3", "c4") else "weak", "vs_baseline": None,
+                    "dtype": "u8" if args.config in ("c1", "c3") else "f64", "data": "synthetic", "clocks": None})
+        if rank == 0:
+            print(json.dumps(leg))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     L, S = args.L, args.sweeps_per_step
     N = L * L
     rule = {"metropolis": 0, "glauber": 1, "heatbath": 2}[args.rule]
-    sys_ = m.Ising([L, L], ctx=ctx)
+    bit = args.storage == "bit"
+    sys_ = m.Ising([L, L], ctx=ctx, storage=args.storage)
     sys_.set_tracking(bool(args.track))
     rng = m.PhiloxRNG(42, rank)
     alg = (m.Metropolis, m.Glauber, m.HeatBath)[rule](rng, beta=BETA_C)
@@ -275,11 +335,13 @@ def run_ours(args):
 
     value = world * args.steps * S * N / (ms * 1e6)
     peak, peak_src = measured_peak()
-    bytes_per_launch = 3 * (N // 2)                                   # 3 B/attempt x N/2 attempts per half-sweep
+    bytes_per_attempt = 0.375 if bit else 3.0                        # 3 x storage bytes per spin
+    bytes_per_launch = bytes_per_attempt * (N // 2)                   # x N/2 attempts per half-sweep
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
-    traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_ising2d (half-sweep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "bytes_per_attempt": 3,
+    traffic = None if bit else ncu_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_ising2d_bits (half-sweep)" if bit else "k_ising2d (half-sweep)", "achieved": achieved,
+                "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "bytes_per_attempt": bytes_per_attempt,
                 "attempts_per_launch": (N // 2) / launches_per_half_sweep, "launches_per_half_sweep": launches_per_half_sweep,
                 "attempts_per_half_sweep": N // 2, "kernel_ms": kernel_ms,
                 "kernel_ms_is": "one half-sweep (all its concurrent band launches), CUDA events on the launching stream",
@@ -328,8 +390,41 @@ def run_ours(args):
            "d2h_bytes_per_step": 40, "ms_per_step": e2e_s / args.steps * 1e3,
            "api": "mcx_lattice_upload_begin/_commit + mcx_sweep + mcx_observables (C ABI, two pinned host buffers; "
                   "the H2D copy of step k+1 overlaps the sweeps of step k)",
+           "numa": numa,
            "serial": {"value": world * args.steps * S * N / (serial_s * 1e9), "ms_per_step": serial_s / args.steps * 1e3,
                       "api": "mcx_lattice_upload + mcx_sweep + mcx_observables, nothing overlapped"}}
+
+    # the same pipelined steps with the host side at one bit per spin (N / 8 bytes in), and with the step's result being the
+    # whole configuration (N / 8 bytes out) instead of five integers
+    hbits = [torch.empty(N // 8, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    hbits[0].copy_(torch.from_numpy(np.ascontiguousarray(sys_.spin_bits)))
+    hbits[1].copy_(hbits[0])
+    out_bits = torch.empty(N // 8, dtype=torch.uint8).pin_memory()
+
+    def e2e_bits(nsteps, download):
+        sys_.upload_bits_begin(hbits[0].data_ptr())
+        for k in range(nsteps):
+            sys_.upload_commit()
+            if k + 1 < nsteps and not download:
+                sys_.upload_bits_begin(hbits[(k + 1) & 1].data_ptr())        # behind step k's sweeps
+            check(lib().mcx_sweep(h, S))
+            if download:                                                     # the download shares the handle's bit staging buffer:
+                check(lib().mcx_lattice_download_bits(h, out_bits.data_ptr()))   # D2H N / 8 bytes (syncs), then the next upload
+                if k + 1 < nsteps:
+                    sys_.upload_bits_begin(hbits[(k + 1) & 1].data_ptr())
+            check(lib().mcx_observables(h, *[o.ctypes.data for o in obs]))
+
+    for download, key in ((False, "bit_buffers"), (True, "bit_buffers_with_download")):
+        e2e_bits(2, download)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_bits(args.steps, download)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        e2e[key] = {"value": world * args.steps * S * N / (sec * 1e9), "ms_per_step": sec / args.steps * 1e3,
+                    "h2d_bytes_per_step": N // 8, "d2h_bytes_per_step": 40 + (N // 8 if download else 0),
+                    "api": "mcx_lattice_upload_bits_begin/_commit + mcx_sweep" + (" + mcx_lattice_download_bits" if download else "") +
+                           " + mcx_observables"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -345,6 +440,28 @@ def run_ours(args):
             out["pt_every_sweep"] = bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, rounds=300, every=1)
         except Exception as e:   # auxiliary metric must not take the headline down
             out["pt"] = {"error": repr(e)}
+
+    # ---- short legs of the other configs (each with its own cpu_baseline at N = 1), the tracked-sums rate and the bit planes
+    if not args.no_extras:
+        extras = {}
+        try:
+            extras["tracked_sums"] = bench_plain(m, ctx, stream, L, S, rule, rank, "int8", True, barrier, max_over_ranks, world)
+            extras["bit" if not bit else "int8"] = bench_plain(m, ctx, stream, L, S, rule, rank, "int8" if bit else "bit", False, barrier,
+                                                               max_over_ranks, world)
+        except Exception as e:
+            extras["tracked_sums"] = {"error": repr(e)}
+        cpu = world == 1 and not args.no_cpu
+        for key, fn in (("c1", lambda: bench_c1(m, ctx, stream, args, cpu=cpu and rank == 0)),
+                        ("c4", lambda: bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, iterations=2, therm=1, record=4, cpu=cpu)),
+                        ("c5", lambda: bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers=32, cpu=cpu))):
+            if key == "c1" and rank != 0:
+                continue
+            try:
+                extras[key] = fn()
+            except Exception as e:
+                extras[key] = {"error": repr(e)}
+            barrier()
+        out["configs"] = extras
 
     # ---- auxiliary: ONE lattice split by rows over the ranks (slab decomposition, halo rows read over NVLink)
     if world > 1 and not args.no_slab:
@@ -363,6 +480,35 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_plain(m, ctx, stream, L, S, rule, rank, storage, track, barrier, max_over_ranks, world):
+    """attempts/ns of the configs[1] lattice in another mode (tracked sums = modify!-like bookkeeping per flip; the other storage)"""
+    import torch
+    from mcx_b200._lib import check, lib
+    s = m.Ising([L, L], ctx=ctx, storage=storage)
+    s.set_tracking(track)
+    rng = m.PhiloxRNG(42, rank)
+    alg = (m.Metropolis, m.Glauber, m.HeatBath)[rule](rng, beta=BETA_C)
+    s._bind_alg(alg)
+    s.init_("random", rng=rng)
+    check(lib().mcx_sweep(s.h_lat, 10))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    check(lib().mcx_sweep(s.h_lat, S))
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    N = L * L
+    bpa = 0.375 if storage == "bit" else 3.0
+    peak, _ = measured_peak()
+    pair = int(s.pair_sum())
+    return {"metric": METRIC, "value": world * S * N / (ms * 1e6), "unit": UNIT, "storage": storage, "track_sums": bool(track),
+            "per_gpu_attempts_per_ns": S * N / (ms * 1e6), "algorithmic_GBps": bpa * S * N / (ms * 1e-3) / 1e9,
+            "frac_of_hbm_peak": bpa * S * N / (ms * 1e-3) / 1e9 / peak,
+            "note": ("%d MiB of planes: L2-resident, bound by instruction issue (Philox + decision), not by memory" % (N >> 22)) if storage == "bit" else None,
+            "pair_sum_rank0": pair}
 
 
 def bench_slab(m, ctx, world, barrier, max_over_ranks, stream, dims, sweeps):
@@ -389,6 +535,7 @@ def bench_slab(m, ctx, world, barrier, max_over_ranks, stream, dims, sweeps):
     n = dims[0] * dims[1]
     return {"metric": METRIC, "value": sweeps * n / (ms * 1e6), "unit": UNIT, "dims": dims, "rows_per_gpu": dims[1] // world,
             "sweeps": sweeps, "us_per_half_sweep": ms * 1e3 / (2 * sweeps), "energy_per_site": s.energy(full=True) / n,
+            "parity": {"kind": "identical at every rank count (randomness positioned by global row)", "energy": float(s.energy(full=True))},
             "wait_timed_out": int(timed_out),
             "halo": "2 rows x %d B per half-sweep per GPU, peer loads over NVLink (CUDA IPC), no copies" % (dims[0] // 2)}
 
@@ -414,7 +561,14 @@ def bench_pt(m, ctx, world, rank, barrier, max_over_ranks, stream, L=1024, n=256
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     sweeps = rounds * every
+    # parity across rank counts: ladder labels and the energies of the last exchange are the same at every N
+    # (replicas keyed by global slot, u keyed by round), so their digest must not change along the scaling run
+    try:
+        parity = {"kind": "identical at every rank count", "labels_and_energies_sha": _sha(__import__("numpy").asarray(pt.index()), pt.energies())}
+    except Exception as e:
+        parity = {"error": repr(e)}
     return {"metric": "pt_sweeps_per_s", "value": sweeps / (ms * 1e-3), "unit": "PT sweeps/s (all %d replicas swept once)" % n,
+            "parity": parity,
             "attempts_per_ns": sweeps * n * L * L / (ms * 1e6), "L": L, "replicas": n, "exchange_every": every,
             "rounds": rounds, "scaling": "strong", "exchange_acceptance": pt.acceptance_rate(),
             "collective": "none (1 rank)" if world == 1 else

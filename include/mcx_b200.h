@@ -65,6 +65,7 @@ typedef struct mcx_ctx mcx_ctx;
 typedef struct mcx_lattice mcx_lattice;
 typedef struct mcx_pt mcx_pt;
 typedef struct mcx_flat mcx_flat;
+typedef struct mcx_graph mcx_graph;
 
 /* ---- library / context ------------------------------------------------------------------ */
 int32_t     mcx_abi_version(void);
@@ -157,6 +158,13 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps);
  * without a host round trip per measurement: nmeasure x (interval sweeps, snapshot of the sums).
  * out is int64 [nmeasure][nchains][4] = {pair_sum, spin_sum, spin2_sum, accepted}; synchronises. */
 int32_t mcx_sweep_series(mcx_lattice *lat, int64_t nmeasure, int64_t interval, int64_t *out);
+
+/* integrated_autocorrelation_time(samples; max_lag, c) (src/measurements/autocorrelations.jl:28-65) of the series the last
+ * mcx_sweep_series left on the device, one value per chain, without moving the series: observable 0 = energy(sys),
+ * 1 = magnetization(sys), 2 = |magnetization|; max_lag 0 = floor(n / 2); first `nmeasure` snapshots; synchronises.
+ * Same estimator, same errors (MCX_ERR_ARGUMENT for the reference's ArgumentErrors); sums are deterministic block
+ * reductions, so the value agrees with the sequential formula to rounding (1e-12 relative), not bit for bit. */
+int32_t mcx_series_tau_int(mcx_lattice *lat, int64_t nmeasure, int32_t observable, int64_t max_lag, double c, double *tau);
 
 /* cached sums per chain (any pointer may be NULL), synchronises:
  *   pair_sum  = sum_<ij> s_i s_j (unweighted; sys.sum_pair_interactions / J)   ising.jl:90
@@ -270,6 +278,36 @@ int32_t mcx_flat_sweep(mcx_flat *flat, int64_t nsweeps);
 int32_t mcx_flat_update(mcx_flat *flat);                 /* update!(ens): muca :simple, WL halves logf */
 int32_t mcx_flat_device_histogram(mcx_flat *flat, void **device_ptr, int64_t *nbins);
 int32_t mcx_flat_device_logweight(mcx_flat *flat, void **device_ptr, int64_t *nbins);
+
+/* ---- general topologies: IsingGraph / IsingMatrix with site fields -----------------------------
+ * mcx_graph_create <- Ising(graph::SimpleGraph, J::Real; h) / IsingGraph ising.jl:117-139 (J_ij == NULL: one global J),
+ *                     Ising(J::SparseMatrixCSC; h) / IsingMatrix ising.jl:264-293 and Ising(graph, J::Vector) :383-404
+ *                     (J_ij: one coupling per CSR entry), Ising(dims; periodic=false) :406-417 (a grid graph).
+ * rowptr[n + 1] / col[nnz]: 0-based neighbour lists in the reference's adjacency order (ascending neighbour index);
+ * field_mode 0: h = 0, 1: uniform h, 2: per-site h_i[n] (ising.jl:95-115).  An asymmetric neighbour relation or J_ij
+ * is MCX_ERR_STATE (the reference's AssertionError "Sparse J must be symmetric", :250-262).  `nchains` independent copies.
+ * Sweeps visit the colour classes of a greedy first-fit colouring in site order (the checkerboard generalised); the
+ * stream of an attempt is (chain, t = ncolours * sweep + colour, slot = rank of the site inside its colour class) of
+ * RNG layout v1.  Couplings are doubles, so the acceptance is the reference's Float64 expression evaluated on the
+ * device (accept! metropolis.jl:14-17,121-127; _accept! importance_sampling.jl:80-85; heat bath ising.jl:43-58). */
+int32_t mcx_graph_create(mcx_ctx *ctx, int64_t n, const int64_t *rowptr, const int64_t *col, const double *J_ij, double J,
+                         int32_t field_mode, double h, const double *h_i, int32_t nchains, mcx_graph **out);
+int32_t mcx_graph_destroy(mcx_graph *g);
+/* number of colours and (optional, int32[n]) the colour of every site */
+int32_t mcx_graph_colours(mcx_graph *g, int32_t *ncolours, int32_t *colour_of_site);
+int32_t mcx_graph_upload(mcx_graph *g, const int8_t *host_spins);      /* sys.spins .= host, [nchains][n], -1 / +1 */
+int32_t mcx_graph_download(mcx_graph *g, int8_t *host_spins);
+int32_t mcx_graph_init(mcx_graph *g, int32_t mode, uint64_t seed);     /* init!(sys, :up / :down / :random; rng) ising.jl:74 */
+int32_t mcx_graph_set_rule(mcx_graph *g, int32_t rule, double beta);   /* Metropolis / Glauber / HeatBath(rng; beta) */
+int32_t mcx_graph_set_rng(mcx_graph *g, uint64_t seed, uint64_t next_sweep, uint32_t first_chain_id);
+int32_t mcx_graph_get_rng(mcx_graph *g, uint64_t *seed, uint64_t *next_sweep);
+int32_t mcx_graph_sweep(mcx_graph *g, int64_t nsweeps);                /* nsweeps x every colour class once; asynchronous */
+/* per chain (any pointer may be NULL), formed from the spins like _recompute_cached! (ising.jl:127-144); synchronises:
+ * pair_sum = sum_pair_interactions, spin_sum = sum_spins, field_sum = sum_field_interactions, alg.accepted, alg.steps */
+int32_t mcx_graph_observables(mcx_graph *g, double *pair_sum, int64_t *spin_sum, double *field_sum, int64_t *accepted,
+                              int64_t *steps);
+int32_t mcx_graph_energies(mcx_graph *g, double *energy);              /* energy(sys; full=true) per chain */
+int32_t mcx_graph_reset_counters(mcx_graph *g);
 
 #ifdef __cplusplus
 }

@@ -14,13 +14,14 @@ from .flat import (DeviceFlat, PairBoltzmannSpin2Ensemble, ParallelMulticanonica
 from .ising2d_exact import distribution_exact_ising2D, distribution_from_logdos, logdos_exact_ising2D
 from .checkpointing import CheckpointSession, checkpoint_, finalize_, init_checkpoint, restore_checkpoint
 from .measurements import (integrated_autocorrelation_time, integrated_autocorrelation_times,
-                           optimize_exchange_interval_, sweep_series_, tau_int)
+                           optimize_exchange_interval_, series_tau_int_, sweep_series_, tau_int)
 from .parallel import (GPUBackend, ParallelChains, ParallelTempering, ReplicaExchange, SlabIsing, ThreadsBackend,
                        attempt_exchange_pair_, exchange_log_ratio, partition_slots, philox_family, set_betas,
                        update_)
 from .rng import PhiloxRNG, exchange_u, philox4x32_10
 from .spin_systems import (BlumeCapel, Context, Ising, IsingLatticeOptim, default_context, energy, init_,
                            magnetization, sweep_)
+from .graph_systems import IsingGraph, IsingMatrix, grid_graph
 from .tables import build_table, table_len
 from .windows import DeviceWindow, WangLandauWindows, join_logdos, partition_windows
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "mcx_get_rng": (_i32, [_vp, _P(_u64), _P(_u64)]),
     "mcx_sweep": (_i32, [_vp, _i64]),
     "mcx_sweep_series": (_i32, [_vp, _i64, _i64, _vp]),
+    "mcx_series_tau_int": (_i32, [_vp, _i64, _i32, _i64, _dbl, _vp]),
     "mcx_observables": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mcx_energies": (_i32, [_vp, _vp]),
     "mcx_reset_counters": (_i32, [_vp]),
@@ -102,6 +103,19 @@ SIGNATURES = {
     "mcx_flat_update": (_i32, [_vp]),
     "mcx_flat_device_histogram": (_i32, [_vp, _P(_vp), _P(_i64)]),
     "mcx_flat_device_logweight": (_i32, [_vp, _P(_vp), _P(_i64)]),
+    "mcx_graph_create": (_i32, [_vp, _i64, _vp, _vp, _vp, _dbl, _i32, _dbl, _vp, _i32, _P(_vp)]),
+    "mcx_graph_destroy": (_i32, [_vp]),
+    "mcx_graph_colours": (_i32, [_vp, _P(_i32), _vp]),
+    "mcx_graph_upload": (_i32, [_vp, _vp]),
+    "mcx_graph_download": (_i32, [_vp, _vp]),
+    "mcx_graph_init": (_i32, [_vp, _i32, _u64]),
+    "mcx_graph_set_rule": (_i32, [_vp, _i32, _dbl]),
+    "mcx_graph_set_rng": (_i32, [_vp, _u64, _u64, _u32]),
+    "mcx_graph_get_rng": (_i32, [_vp, _P(_u64), _P(_u64)]),
+    "mcx_graph_sweep": (_i32, [_vp, _i64]),
+    "mcx_graph_observables": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mcx_graph_energies": (_i32, [_vp, _vp]),
+    "mcx_graph_reset_counters": (_i32, [_vp]),
 }
 
 _lib = None

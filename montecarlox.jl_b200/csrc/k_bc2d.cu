@@ -12,7 +12,11 @@
 // acceptance draws).  The decision is the packed 15-bit comparison of k_ising2d: two sites per instruction
 // against a pair-threshold table in shared memory (54 rows of 256 B: byte address = v1 * 256 + v0 * 4),
 // ties (2^-15 per site) redone exactly with the 32-bit draws.  Bit-identical to k_sweep_rows8 and
-// k_sweep_generic.  Heat bath (two thresholds per draw) stays on k_sweep_rows8.
+// k_sweep_generic.
+//
+// Heat bath (blume_capel.jl:61-85): ONE Float64 draw per site (planes 0 / 1) against two thresholds that depend on the
+// neighbour sum only, new = m < T0[raw] ? -1 : m < T1[raw] ? 0 : +1 -- two Philox blocks per thread-row instead of four,
+// two packed comparisons per pair of sites against two 9 x 9 pair tables, new encoding = [m >= T0] + [m >= T1].
 #include "mcx_internal.h"
 
 #include <cstdlib>
@@ -65,16 +69,38 @@ __device__ __noinline__ uint4 bc_row_exact(uint4 tq, uint4 nq, uint4 bq, const u
     return make_uint4(tw[0], tw[1], tw[2], tw[3]);
 }
 
-template <int PARITY, bool TRACK>
+
+// heat bath: exact redo of one thread-row with the full 32-bit draws
+__device__ __noinline__ uint4 bc_row_exact_hb(uint4 nq, const uint32_t *thi, const uint32_t *tlo, Philox4 a0, Philox4 b0, Philox4 a1,
+                                              Philox4 b1)
+{
+    uint32_t out[4] = {0u, 0u, 0u, 0u};
+    const uint32_t nr[4] = {nq.x, nq.y, nq.z, nq.w};
+#pragma unroll 1
+    for (int i = 0; i < 16; ++i) {
+        const int w = i >> 2, k = i & 3;
+        const uint32_t n = (nr[w] >> (8 * k)) & 0xffu;
+        const uint32_t hi = lane16(i < 8 ? a0 : b0, i & 7), lo = lane16(i < 8 ? a1 : b1, i & 7);
+        const uint64_t m = ((uint64_t)hi << 16) | lo;
+        const uint64_t T0 = ((uint64_t)thi[n] << 16) | tlo[n], T1 = ((uint64_t)thi[9 + n] << 16) | tlo[9 + n];
+        out[w] |= (m < T0 ? 0u : m < T1 ? 1u : 2u) << (8 * k);
+    }
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+constexpr int kHbTable = 18;                  // 2 * (2 nn + 1): thresholds T0[raw], T1[raw]
+constexpr int kHbT1Words = 9 * kBcRowWords;   // the T1 pair table starts after nine rows of the T0 pair table
+
+template <int PARITY, bool TRACK, bool HB>
 __device__ __forceinline__ uint4 bc_update_row(const uint4 tq, const uint4 U, const uint4 C, const uint4 D, const uint32_t side,
-                                               const uint32_t blk, const uint32_t t_lo, const uint32_t c2p0, const uint32_t c2p2,
-                                               const uint32_t c2p3, const uint32_t chain_id, const uint32_t seed_lo,
+                                               const uint32_t blk, const uint32_t t_lo, const uint32_t c2p0, const uint32_t c2p1,
+                                               const uint32_t c2p2, const uint32_t c2p3, const uint32_t chain_id, const uint32_t seed_lo,
                                                const uint32_t seed_hi, const uint32_t *s_pair, const uint32_t *s_thi,
                                                const uint32_t *s_tlo, BcAcc &acc, const bool active)
 {
     // Bool draws: bit 15 of every 16-bit lane of plane 0, as one byte per site
-    uint32_t B4[4];
-    {
+    uint32_t B4[4] = {0u, 0u, 0u, 0u};
+    if (!HB) {
         const Philox4 pa = philox4x32_10(blk, t_lo, c2p0, chain_id, seed_lo, seed_hi);
         const Philox4 pb = philox4x32_10(blk + 1, t_lo, c2p0, chain_id, seed_lo, seed_hi);
         B4[0] = (__byte_perm(pa.x, pa.y, 0x7531) >> 7) & 0x01010101u;
@@ -82,8 +108,8 @@ __device__ __forceinline__ uint4 bc_update_row(const uint4 tq, const uint4 U, co
         B4[2] = (__byte_perm(pb.x, pb.y, 0x7531) >> 7) & 0x01010101u;
         B4[3] = (__byte_perm(pb.z, pb.w, 0x7531) >> 7) & 0x01010101u;
     }
-    const Philox4 ra = philox4x32_10(blk, t_lo, c2p2, chain_id, seed_lo, seed_hi);
-    const Philox4 rb = philox4x32_10(blk + 1, t_lo, c2p2, chain_id, seed_lo, seed_hi);
+    const Philox4 ra = philox4x32_10(blk, t_lo, HB ? c2p0 : c2p2, chain_id, seed_lo, seed_hi);
+    const Philox4 rb = philox4x32_10(blk + 1, t_lo, HB ? c2p0 : c2p2, chain_id, seed_lo, seed_hi);
 
     uint32_t S[4];
     if (PARITY == 0) {
@@ -104,7 +130,7 @@ __device__ __forceinline__ uint4 bc_update_row(const uint4 tq, const uint4 U, co
     uint32_t tie_min = 0x7fff7fffu;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
-        const uint32_t X = tw[w] * 18u + B4[w] * 9u + raw[w];      // byte = table index (e * 2 + b) * 9 + raw  (<= 53)
+        const uint32_t X = HB ? raw[w] : tw[w] * 18u + B4[w] * 9u + raw[w];   // byte = table index: raw, or (e * 2 + b) * 9 + raw (<= 53)
         const uint32_t A = X + 3u * (X & 0x00ff00ffu);              // even bytes * 4: halfword = v1 * 256 + v0 * 4
         const uint32_t ttA = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (A & 0xffffu));
         const uint32_t ttB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (A >> 16));
@@ -114,16 +140,28 @@ __device__ __forceinline__ uint4 bc_update_row(const uint4 tq, const uint4 U, co
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rA) : "r"(ttA), "r"(hA));
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rB) : "r"(ttB), "r"(hB));
         tie_min = __vmins2(__vmins2(tie_min, rA), rB);
-        uint32_t P;   // 0xFF per site that is NOT accepted
+        uint32_t P;   // 0xFF per site that is NOT accepted (heat bath: whose draw is not below T0)
         asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(P) : "r"(rA), "r"(rB));
-        nw[w] = (tw[w] & P) | (bc_prop4(tw[w], B4[w]) & ~P);
+        if (HB) {
+            const uint32_t uuA = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair + kHbT1Words) + (A & 0xffffu));
+            const uint32_t uuB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair + kHbT1Words) + (A >> 16));
+            uint32_t qA, qB, Q;
+            asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(qA) : "r"(uuA), "r"(hA));
+            asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(qB) : "r"(uuB), "r"(hB));
+            tie_min = __vmins2(__vmins2(tie_min, qA), qB);
+            asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(Q) : "r"(qA), "r"(qB));
+            nw[w] = (P & 0x01010101u) + (Q & 0x01010101u);         // new encoding = [m >= T0] + [m >= T1]
+        } else {
+            nw[w] = (tw[w] & P) | (bc_prop4(tw[w], B4[w]) & ~P);
+        }
     }
     const bool tie = ((tie_min & 0x7fffu) == 0u) || ((tie_min & 0x7fff0000u) == 0u);
     if (tie) {
-        const Philox4 la = philox4x32_10(blk, t_lo, c2p3, chain_id, seed_lo, seed_hi);
-        const Philox4 lb = philox4x32_10(blk + 1, t_lo, c2p3, chain_id, seed_lo, seed_hi);
-        const uint4 ex = bc_row_exact(tq, make_uint4(raw[0], raw[1], raw[2], raw[3]), make_uint4(B4[0], B4[1], B4[2], B4[3]),
-                                      s_thi, s_tlo, ra, rb, la, lb);
+        const Philox4 la = philox4x32_10(blk, t_lo, HB ? c2p1 : c2p3, chain_id, seed_lo, seed_hi);
+        const Philox4 lb = philox4x32_10(blk + 1, t_lo, HB ? c2p1 : c2p3, chain_id, seed_lo, seed_hi);
+        const uint4 ex = HB ? bc_row_exact_hb(make_uint4(raw[0], raw[1], raw[2], raw[3]), s_thi, s_tlo, ra, rb, la, lb)
+                            : bc_row_exact(tq, make_uint4(raw[0], raw[1], raw[2], raw[3]), make_uint4(B4[0], B4[1], B4[2], B4[3]),
+                                           s_thi, s_tlo, ra, rb, la, lb);
         nw[0] = ex.x; nw[1] = ex.y; nw[2] = ex.z; nw[3] = ex.w;
     }
     if (active) {
@@ -153,7 +191,7 @@ __device__ __forceinline__ uint4 bc_update_row(const uint4 tq, const uint4 U, co
 
 __device__ __forceinline__ uint4 bc_ldg128(const uint8_t *p) { return *reinterpret_cast<const uint4 *>(p); }
 
-template <int COLOUR, bool TRACK>
+template <int COLOUR, bool TRACK, bool HB>
 __global__ void __launch_bounds__(kBcThreads, 5)
 k_bc2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g, const int32_t *__restrict__ labels,
        long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi, uint64_t t, uint32_t first_chain, int R, int nstrips,
@@ -168,7 +206,9 @@ k_bc2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict
     const int64_t G = (int64_t)nstrips * nseg;
     const int lane = threadIdx.x & 31;
     const uint32_t t_lo = (uint32_t)t;
-    const uint32_t c2p0 = ctr_word2(t, 0, TAG_SWEEP), c2p2 = ctr_word2(t, 2, TAG_SWEEP), c2p3 = ctr_word2(t, 3, TAG_SWEEP);
+    const uint32_t c2p0 = ctr_word2(t, 0, TAG_SWEEP), c2p1 = ctr_word2(t, 1, TAG_SWEEP), c2p2 = ctr_word2(t, 2, TAG_SWEEP),
+                   c2p3 = ctr_word2(t, 3, TAG_SWEEP);
+    constexpr int kTab = HB ? kHbTable : kBcTable;
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int chain = item / blocks_per_chain;
@@ -176,15 +216,25 @@ k_bc2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict
         if (label != cur_label) {
             // pair table of this chain's ensemble: word (v1, v0) = t15[v0] | t15[v1] << 16, t15 = min(T >> 17, 0x7fff)
             __syncthreads();
-            for (int i = threadIdx.x; i < kBcTable; i += kBcThreads) {
-                s_thi[i] = thi_g[label * kBcTable + i];
-                s_tlo[i] = tlo_g[label * kBcTable + i];
+            for (int i = threadIdx.x; i < kTab; i += kBcThreads) {
+                s_thi[i] = thi_g[label * kTab + i];
+                s_tlo[i] = tlo_g[label * kTab + i];
             }
-            for (int i = threadIdx.x; i < kBcTable * kBcTable; i += kBcThreads) {
-                const int v1 = i / kBcTable, v0 = i - v1 * kBcTable;
-                const uint32_t a = min(thi_g[label * kBcTable + v0] >> 1, 0x7fffu);
-                const uint32_t b = min(thi_g[label * kBcTable + v1] >> 1, 0x7fffu);
-                s_pair[v1 * kBcRowWords + v0] = a | (b << 16);
+            if (HB) {
+                // two 9 x 9 pair tables: T0[raw] (word offset 0) and T1[raw] (word offset kHbT1Words)
+                for (int i = threadIdx.x; i < 2 * 81; i += kBcThreads) {
+                    const int k = i / 81, j = i - k * 81, v1 = j / 9, v0 = j - v1 * 9;
+                    const uint32_t a = min(thi_g[label * kTab + k * 9 + v0] >> 1, 0x7fffu);
+                    const uint32_t b = min(thi_g[label * kTab + k * 9 + v1] >> 1, 0x7fffu);
+                    s_pair[k * kHbT1Words + v1 * kBcRowWords + v0] = a | (b << 16);
+                }
+            } else {
+                for (int i = threadIdx.x; i < kBcTable * kBcTable; i += kBcThreads) {
+                    const int v1 = i / kBcTable, v0 = i - v1 * kBcTable;
+                    const uint32_t a = min(thi_g[label * kBcTable + v0] >> 1, 0x7fffu);
+                    const uint32_t b = min(thi_g[label * kBcTable + v1] >> 1, 0x7fffu);
+                    s_pair[v1 * kBcRowWords + v0] = a | (b << 16);
+                }
             }
             __syncthreads();
             cur_label = label;
@@ -238,11 +288,11 @@ k_bc2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict
             }
             if (edgeA) sA = sideA;
             if (edgeB) sB = sideB;
-            const uint4 Na = bc_update_row<COLOUR, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2p0, c2p2, c2p3, chain_id, seed_lo, seed_hi,
+            const uint4 Na = bc_update_row<COLOUR, TRACK, HB>(Ta, U, C, D, sA, blk, t_lo, c2p0, c2p1, c2p2, c2p3, chain_id, seed_lo, seed_hi,
                                                          s_pair, s_thi, s_tlo, acc, active);
             if (active) *reinterpret_cast<uint4 *>(pt) = Na;
             asm volatile("" ::: "memory");
-            const uint4 Nb = bc_update_row<COLOUR ^ 1, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2p0, c2p2, c2p3, chain_id,
+            const uint4 Nb = bc_update_row<COLOUR ^ 1, TRACK, HB>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2p0, c2p1, c2p2, c2p3, chain_id,
                                                              seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
             if (active) *reinterpret_cast<uint4 *>(pt + half) = Nb;
             U = D; C = E;
@@ -273,7 +323,7 @@ k_bc2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict
 }
 
 
-template <int COLOUR, bool TRACK>
+template <int COLOUR, bool TRACK, bool HB>
 void launch_bc(mcx_lattice *lat, uint64_t t)
 {
     // a chain sub-range (launch_sweeps_ising2d_grouped) is the same launch on shifted base pointers
@@ -296,7 +346,7 @@ void launch_bc(mcx_lattice *lat, uint64_t t)
     const int64_t G = (int64_t)nstrips * nseg;
     const int blocks_per_chain = (int)((G + kBcThreads - 1) / kBcThreads);
     const int nitems = (int)((int64_t)blocks_per_chain * nch);
-    auto kern = k_bc2d<COLOUR, TRACK>;
+    auto kern = k_bc2d<COLOUR, TRACK, HB>;
     static thread_local int resident = 0;
     if (!resident) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kBcThreads, 0);
@@ -316,11 +366,17 @@ void launch_bc(mcx_lattice *lat, uint64_t t)
 bool launch_sweep_bc2d(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (!lat->fast2d || lat->model != MCX_BLUME_CAPEL || lat->storage != MCX_STORAGE_INT8 || lat->slab) return false;
-    if (lat->rule == MCX_HEATBATH || lat->table_len != kBcTable || knobs().bc2d == 0) return false;
+    const bool hb = lat->rule == MCX_HEATBATH;
+    if (lat->table_len != (hb ? kHbTable : kBcTable) || knobs().bc2d == 0) return false;
     if ((int64_t)(lat->view.Ly / 2) * (lat->view.half >> 4) < 96) return false;       // tiny lattices: rows-of-8 kernel
     const bool track = lat->track_sums;
-    if (colour == 0) { if (track) launch_bc<0, true>(lat, t); else launch_bc<0, false>(lat, t); }
-    else             { if (track) launch_bc<1, true>(lat, t); else launch_bc<1, false>(lat, t); }
+    if (hb) {
+        if (colour == 0) { if (track) launch_bc<0, true, true>(lat, t); else launch_bc<0, false, true>(lat, t); }
+        else             { if (track) launch_bc<1, true, true>(lat, t); else launch_bc<1, false, true>(lat, t); }
+    } else {
+        if (colour == 0) { if (track) launch_bc<0, true, false>(lat, t); else launch_bc<0, false, false>(lat, t); }
+        else             { if (track) launch_bc<1, true, false>(lat, t); else launch_bc<1, false, false>(lat, t); }
+    }
     return true;
 }
 

@@ -203,47 +203,24 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
                 if (edgeA) sideA = po[colA];
                 if (edgeB) sideB = po[half + colB];
             }
-#ifdef MCX_OPT_PHILOX_FIRST
-            // probe: generate the first row's Philox blocks before the loaded rows are first touched
-            const Philox4 ra = philox4x32_10(blk, t_lo, c2, chain_id, seed_lo, seed_hi);
-            const Philox4 rb = philox4x32_10(blk + 1, t_lo, c2, chain_id, seed_lo, seed_hi);
-            const uint32_t z = opaque_zero(ra.x ^ rb.x);
-            D.x |= z; D.y |= z; D.z |= z; D.w |= z;
-            Ta.x |= z; Ta.y |= z; Ta.z |= z; Ta.w |= z;
-            sideA |= z; sideB |= z;
-#else
-            const uint32_t z = 0;
-#endif
             uint32_t sA, sB;
             if (COLOUR == 0) {
-                sA = __shfl_up_sync(0xffffffffu, C.w | z, 1) >> 24;
+                sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
                 sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
             } else {
-                sA = __shfl_down_sync(0xffffffffu, C.x | z, 1) & 0xffu;
+                sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
                 sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
             }
             if (edgeA) sA = sideA;
             if (edgeB) sB = sideB;
-#ifdef MCX_OPT_PHILOX_FIRST
-            const uint4 Na = update_row_with<COLOUR, HEATBATH, TRACK>(ra, rb, Ta, U, C, D, sA, blk, t_lo, c2lo, chain_id, seed_lo,
-                                                                      seed_hi, s_pair, s_thi, s_tlo, acc, active);
-#else
             const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
                                                                  seed_hi, s_pair, s_thi, s_tlo, acc, active);
-#endif
-#ifndef MCX_OPT_INTERLEAVE_ROWS
             // finish (and store) row a before starting row b: fewer live registers, measured +4 %
             if (active) *reinterpret_cast<uint4 *>(pt) = Na;
             asm volatile("" ::: "memory");
-#endif
             const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
                                                                      seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            if (active) {
-#ifdef MCX_OPT_INTERLEAVE_ROWS
-                *reinterpret_cast<uint4 *>(pt) = Na;
-#endif
-                *reinterpret_cast<uint4 *>(pt + half) = Nb;
-            }
+            if (active) *reinterpret_cast<uint4 *>(pt + half) = Nb;
             U = D; C = E;
             if (PREFETCH) { D = Dn; Ta = Tan; Tb = Tbn; sideA = sideAn; sideB = sideBn; }
             po += 2 * (int64_t)half; pt += 2 * (int64_t)half; blk += 2 * blk_step;
@@ -281,162 +258,6 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         g_trace[12 * blockIdx.x + 3] = (unsigned long long)trace_items;
     }
 #endif
-}
-
-// ---------------------------------------------------------------------------------------------
-// Same half-sweep with the row loads staged through shared memory by cp.async (LDGSTS): every
-// thread keeps a private ring of STAGES trips (4 x 16 B per trip: the two new other-plane rows and
-// the two target rows, plus one 4-byte word holding the out-of-segment neighbour byte for edge
-// lanes), issued STAGES trips ahead.  The copies never occupy registers while in flight, so the
-// DRAM latency is covered without the register cost of a software prefetch.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, int STAGES>
-__global__ void __launch_bounds__(kThreads, MINB)
-k_ising2d_ring(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
-               const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
-               uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
-{
-    __shared__ uint32_t s_pair[kPairWords];
-    __shared__ uint32_t s_thi[kTableLen], s_tlo[kTableLen];
-    __shared__ uint4 s_ring[STAGES][4][kThreads];        // [stage][D, E, Ta, Tb][thread]
-    __shared__ uint32_t s_side[STAGES][2][kThreads];     // [stage][A, B][thread]
-    int cur_label = -1;
-
-    const int half = L.half;
-    const int nseg = half >> 4;
-    const int64_t G = (int64_t)nstrips * nseg;
-    const int lane = threadIdx.x & 31;
-    const int tid = threadIdx.x;
-    const uint32_t t_lo = (uint32_t)t;
-    const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
-    const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
-    const int ntrips = R >> 1;
-
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-        const int chain = item / blocks_per_chain;
-        const int label = labels[chain];
-        if (label != cur_label) {
-            __syncthreads();
-            if (threadIdx.x < kTableLen) {
-                s_thi[threadIdx.x] = thi_g[label * kTableLen + threadIdx.x];
-                s_tlo[threadIdx.x] = tlo_g[label * kTableLen + threadIdx.x];
-            }
-            if (threadIdx.x < kTableLen * kTableLen) {
-                const int i1 = threadIdx.x / kTableLen, i0 = threadIdx.x - i1 * kTableLen;
-                const uint32_t a = min(thi_g[label * kTableLen + i0] >> 1, 0x7fffu);
-                const uint32_t b = min(thi_g[label * kTableLen + i1] >> 1, 0x7fffu);
-                s_pair[i1 * kPairRowWords + i0] = a | (b << 16);
-            }
-            __syncthreads();
-            cur_label = label;
-        }
-        const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
-        const bool active = g0 < G;
-        const int64_t g = active ? g0 : G - 1;
-        const int strip = (int)(g / nseg);
-        const int seg = (int)(g - (int64_t)strip * nseg);
-        const int row0 = strip * R;                               // even
-        const uint32_t chain_id = first_chain + (uint32_t)chain;
-
-        uint8_t *tgt = plane_ptr(L, chain, COLOUR);
-        const uint8_t *__restrict__ oth = plane_ptr(L, chain, COLOUR ^ 1);
-        const int col = seg << 4;
-        const int colL = (seg == 0 ? half : col) - 1;
-        const int colR = (seg == nseg - 1) ? 0 : col + 16;
-        const bool loadL = (lane == 0) || (seg == 0);
-        const bool loadR = (lane == 31) || (seg == nseg - 1);
-        const bool edgeA = COLOUR == 0 ? loadL : loadR;
-        const bool edgeB = COLOUR == 0 ? loadR : loadL;
-        const int colA = COLOUR == 0 ? colL : colR;
-        const int colB = COLOUR == 0 ? colR : colL;
-
-        const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
-        const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, row of the current trip
-        uint8_t *pt = tgt + (int64_t)row0 * half + col;
-        // stage trip k (rows row0 + 2k, row0 + 2k + 1) into ring slot k % STAGES
-        auto issue = [&](int k) {
-            if (k < ntrips) {
-                const int slot = k % STAGES;
-                const int row = row0 + 2 * k;
-                const uint8_t *pk = oth + (int64_t)row * half;
-                const uint8_t *pe = (row + 2 == L.Ly) ? oth : pk + 2 * (int64_t)half;
-                cp_async16(&s_ring[slot][0][tid], pk + half + col);
-                cp_async16(&s_ring[slot][1][tid], pe + col);
-                cp_async16(&s_ring[slot][2][tid], tgt + (int64_t)row * half + col);
-                cp_async16(&s_ring[slot][3][tid], tgt + (int64_t)(row + 1) * half + col);
-                if (edgeA) cp_async4(&s_side[slot][0][tid], pk + (colA & ~3));
-                if (edgeB) cp_async4(&s_side[slot][1][tid], pk + half + (colB & ~3));
-            }
-            cp_async_commit();
-        };
-#pragma unroll
-        for (int k = 0; k < STAGES; ++k) issue(k);
-        uint4 U = ldg128(oth + (int64_t)rowU * half + col);
-        uint4 C = ldg128(po + col);
-        uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
-        const uint32_t blk_step = (uint32_t)(half >> 3);
-        Acc acc;
-
-#pragma unroll 1
-        for (int k = 0; k < ntrips; ++k) {
-            const int slot = k % STAGES;
-            cp_async_wait<STAGES - 1>();
-            const uint4 D = s_ring[slot][0][tid];
-            const uint4 E = s_ring[slot][1][tid];
-            const uint4 Ta = s_ring[slot][2][tid];
-            const uint4 Tb = s_ring[slot][3][tid];
-            uint32_t sA, sB;
-            if (COLOUR == 0) {
-                sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
-                sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
-            } else {
-                sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
-                sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
-            }
-            if (edgeA) sA = (s_side[slot][0][tid] >> (8 * (colA & 3))) & 0xffu;
-            if (edgeB) sB = (s_side[slot][1][tid] >> (8 * (colB & 3))) & 0xffu;
-            issue(k + STAGES);                                   // refill the slot just consumed
-            const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
-                                                                 seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
-                                                                     seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            if (active) {
-                *reinterpret_cast<uint4 *>(pt) = Na;
-                *reinterpret_cast<uint4 *>(pt + half) = Nb;
-            }
-            U = D; C = E;
-            pt += 2 * (int64_t)half; blk += 2 * blk_step;
-        }
-        cp_async_wait<0>();
-
-        const int nflip = warp_sum((int)acc.flips);
-        int dspin = 0, dpair = 0;
-        if (TRACK) {
-            const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
-            dspin = 2 * nflip - 4 * ss;
-            dpair = -8 * sn + 16 * ss + 4 * nn_ - 8 * nflip;
-        }
-        if (lane == 0) {
-            unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
-            if (nflip) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nflip);
-            if (TRACK) {
-                if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
-                if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
-            }
-        }
-    }
 }
 
 // _recompute_cached! for row-aligned 2-D Ising planes: one thread per 16-byte segment of the colour-0
@@ -659,44 +480,15 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     lat->ctx->launches++;
 }
 
-template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, int STAGES>
-void launch_ring(mcx_lattice *lat, uint64_t t)
-{
-    const LatView &L = lat->view;
-    const int R = auto_rows_per_strip(lat);
-    const int nstrips = L.Ly / R;
-    const int nseg = L.half >> 4;
-    const int64_t G = (int64_t)nstrips * nseg;
-    const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
-    const int nitems = (int)((int64_t)blocks_per_chain * lat->nchains);
-    auto kern = k_ising2d_ring<COLOUR, HEATBATH, TRACK, MINB, STAGES>;
-    static thread_local int resident = 0;
-    if (!resident) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kThreads, 0);
-        if (resident < 1) resident = 1;
-    }
-    const int ctas_per_sm = knobs().ctas_per_sm >= 0 ? knobs().ctas_per_sm : resident;
-    // persistent grid: every SM gets its full complement of CTAs (trimming the grid so that all CTAs
-    // run the same number of items was measured 8 % slower: SMs with fewer CTAs do not finish sooner)
-    int grid = lat->ctx->sm_count * ctas_per_sm;
-    if (grid > nitems) grid = nitems;
-    kern<<<grid, kThreads, 0, lat->ctx->stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels, lat->d_sums,
-                                                 (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain, R,
-                                                 nstrips, blocks_per_chain, nitems);
-    lat->ctx->launches++;
-}
-
 // MCX_VARIANT (tuning hook; every variant produces the same trajectories): default = 6 CTAs/SM with the
-// trip's loads issued before the Philox rounds; 0 = 5 CTAs/SM with a one-trip register prefetch;
-// 6 = 6 CTAs/SM with a 3-stage cp.async ring.  Measured in profiles/r01_tune_variants.log.
+// trip's loads issued before the Philox rounds; 0 = 5 CTAs/SM with a one-trip register prefetch.  (A cp.async staging
+// ring was measured slower -- latency is not the limiter, profiles/r01_tune_variants.log -- and is no longer built.)
 template <int COLOUR, bool HEATBATH, bool TRACK>
 void launch_t(mcx_lattice *lat, uint64_t t)
 {
     const int variant = lat->slab || knobs().variant < 0 ? 3 : knobs().variant;
     switch (variant) {
     case 0: launch_v<COLOUR, HEATBATH, TRACK, 5, true>(lat, t); break;
-    case 6: launch_ring<COLOUR, HEATBATH, TRACK, 6, 3>(lat, t); break;
     default: launch_v<COLOUR, HEATBATH, TRACK, 6, false>(lat, t); break;
     }
 }
@@ -790,7 +582,7 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
     const bool d3 = lat->ndim == 3 && lat->model == MCX_ISING && lat->view.Lx % 32 == 0 && knobs().ising3d != 0;
     const bool bc = lat->fast2d && lat->model == MCX_BLUME_CAPEL;
     if (!d3 && !lat->fast2d) return false;
-    if (bc && (lat->rule == MCX_HEATBATH || knobs().bc2d == 0)) return false;
+    if (bc && knobs().bc2d == 0) return false;
     if (knobs().variant >= 0 || knobs().rows_per_strip >= 0) return false;
     const int groups_env = knobs().groups;
     if (groups_env == 0 || groups_env == 1) return false;

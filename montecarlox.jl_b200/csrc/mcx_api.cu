@@ -240,6 +240,7 @@ static void lattice_free(mcx_lattice *lat)
     cudaFree(lat->d_hostbits);
     cudaFree(lat->d_queue);
     cudaFree(lat->d_series);
+    cudaFree(lat->d_tau);
     if (lat->copy_stream) {
         cudaStreamSynchronize(lat->copy_stream);
         cudaStreamDestroy(lat->copy_stream);
@@ -697,6 +698,7 @@ int32_t mcx_sweep_series(mcx_lattice *lat, int64_t nmeasure, int64_t interval, i
             st = fail(MCX_ERR_CUDA, "snapshot copy failed");
     }
     lat->track_sums = was_tracking;
+    lat->series_n = st == MCX_OK ? nmeasure : 0;
     if (st == MCX_OK) {
         cudaError_t e = cudaMemcpyAsync(out, d_series, sizeof(long long) * stride * (size_t)nmeasure, cudaMemcpyDeviceToHost,
                                         lat->ctx->stream);

@@ -55,6 +55,9 @@ struct mcx_lattice {
     size_t queue_bytes;
     long long *d_series;        // mcx_sweep_series: snapshots of the sums, grown on demand
     size_t series_bytes;
+    int64_t series_n;           // snapshots the last mcx_sweep_series left in d_series
+    double *d_tau;              // mcx_series_tau_int: centred series per chain + the results
+    size_t tau_bytes;
     bool fast2d;                // Lx % 32 == 0 && ndim == 2: row-aligned 128-bit kernels apply
     bool track_sums;            // fast kernels accumulate pair/spin sums per flip (else recompute lazily)
     bool sums_dirty;            // pair/spin sums are stale (untracked sweeps ran)

@@ -109,3 +109,18 @@ def sweep_series_(sys, alg, nmeasure, interval=1):
         alg.accepted += int(acc[-1].sum()) - before
     return {"energy": sys._energy_from(pair, spin, spin2), "magnetization": spin, "pair_sum": pair,
             "spin2_sum": spin2, "accepted": acc}
+
+
+_TAU_OBS = {"energy": 0, "magnetization": 1, "abs_magnetization": 2}
+
+
+def series_tau_int_(sys, nmeasure, observable="energy", max_lag=None, c=5.0):
+    """integrated_autocorrelation_time (autocorrelations.jl:28-65) of the series `sweep_series_` just left on the device,
+    per chain, computed there (mcx_series_tau_int): float64[nchains].  Agrees with `integrated_autocorrelation_time` on the
+    copied-back series to rounding."""
+    if observable not in _TAU_OBS:
+        raise ValueError("observable must be one of %s" % sorted(_TAU_OBS))
+    out = np.empty(sys.nchains, dtype=np.float64)
+    check(lib().mcx_series_tau_int(sys.h_lat, int(nmeasure), _TAU_OBS[observable], 0 if max_lag is None else int(max_lag), float(c),
+                                   out.ctypes.data))
+    return out

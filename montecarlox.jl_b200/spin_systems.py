@@ -276,8 +276,17 @@ class AbstractIsing(AbstractSpinSystem):
 
 
 class Ising(AbstractIsing):
-    """Ising(dims; J=1, periodic=true, h=0) (ising.jl:413-424) on a periodic grid.  `storage="bit"` keeps the spins at
-    one bit each on the device (2-D / 3-D, Lx % 32 == 0); trajectories and observables do not depend on it."""
+    """Ising(dims; J=1, periodic=true, h=0) (ising.jl:406-417) on a periodic grid.  `storage="bit"` keeps the spins at
+    one bit each on the device (2-D / 3-D, Lx % 32 == 0); trajectories and observables do not depend on it.
+    Open boundaries (`periodic=False`), a per-site field vector `h` or one coupling per edge (vector `J`) give the grid
+    graph of the reference (Graphs.SimpleGraphs.grid) on the general-topology path (graph_systems.IsingGraph)."""
+
+    def __new__(cls, dims, J=1, h=0, D=0, nchains=1, ctx=None, periodic=True, storage="int8"):
+        if not periodic or np.ndim(h) != 0 or np.ndim(J) != 0:
+            from .graph_systems import IsingGraph, grid_graph
+            edges, n = grid_graph(dims, periodic)
+            return IsingGraph(edges, n, J=J, h=h, nchains=nchains, ctx=ctx)      # not an instance of cls: __init__ is skipped
+        return super().__new__(cls)
 
 
 class IsingLatticeOptim(AbstractIsing):
@@ -322,6 +331,8 @@ def sweep_(sys, alg, nsweeps=1):
     (pt_Ising2D.jl:52-57) with the update order changed from random-site to checkerboard.
     Asynchronous; `alg.steps` / `alg.accepted` follow the reference's counters
     (importance_sampling.jl:80-85) and are read back lazily."""
+    if hasattr(sys, "_graph_sweep"):           # general topology (graph_systems.py): coloured sweeps
+        return sys._graph_sweep(alg, nsweeps)
     if hasattr(alg, "sweep_system_"):          # ReplicaExchange: every replica with its own label
         return alg.sweep_system_(sys, nsweeps)
     ens = getattr(alg, "ensemble", None)

@@ -888,3 +888,191 @@ void mcxo_rx_update(int64_t n, int64_t *stage, int64_t *indices, int64_t *steps,
     }
     *stage = 1 - *stage;
 }
+
+/* =====================================================================================================
+ * General topologies: IsingGraph (global J, SpinSystems/src/ising.jl:86-205) and IsingMatrix (sparse J_ij,
+ * ising.jl:207-360) with no / uniform / per-site fields.  Neighbour lists are CSR in the reference's adjacency
+ * order (ascending neighbour index: Graphs.jl adjacency lists and SparseMatrixCSC columns are sorted).
+ * Sweeps visit the colour classes of a greedy first-fit colouring in site order (generalising the checkerboard);
+ * the random stream of an attempt is positioned at (chain, t = ncolours * sweep + colour, slot = rank of the site
+ * inside its colour class).
+ * ===================================================================================================== */
+mcxo_graph *mcxo_graph_create(int64_t n, const int64_t *rowptr, const int64_t *col, const double *val, double J,
+                              int hmode, double h, const double *hvec)
+{
+    mcxo_graph *g = (mcxo_graph *)calloc(1, sizeof(*g));
+    int64_t nnz = rowptr[n];
+    g->n = n;
+    g->rowptr = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    g->col = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nnz > 0 ? nnz : 1));
+    memcpy(g->rowptr, rowptr, sizeof(int64_t) * (size_t)(n + 1));
+    memcpy(g->col, col, sizeof(int64_t) * (size_t)nnz);
+    g->matrix = val != 0;
+    if (val) {
+        g->val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+        memcpy(g->val, val, sizeof(double) * (size_t)nnz);
+    }
+    g->J = J; g->hmode = hmode; g->h = h;
+    if (hmode == 2) {
+        g->hvec = (double *)malloc(sizeof(double) * (size_t)n);
+        memcpy(g->hvec, hvec, sizeof(double) * (size_t)n);
+    }
+    g->spins = (int8_t *)malloc((size_t)n);
+    for (int64_t i = 0; i < n; ++i) g->spins[i] = 1;            /* constructors start all-up (ising.jl:118, 271) */
+    mcxo_graph_recompute(g);
+    return g;
+}
+
+void mcxo_graph_destroy(mcxo_graph *g)
+{
+    if (!g) return;
+    free(g->rowptr); free(g->col); free(g->val); free(g->hvec); free(g->spins); free(g);
+}
+
+void mcxo_graph_set_spins(mcxo_graph *g, const int8_t *spins) { memcpy(g->spins, spins, (size_t)g->n); mcxo_graph_recompute(g); }
+void mcxo_graph_get_spins(const mcxo_graph *g, int8_t *spins) { memcpy(spins, g->spins, (size_t)g->n); }
+
+void mcxo_graph_init_random(mcxo_graph *g, uint64_t seed, uint32_t chain)
+{
+    uint32_t out[4];
+    for (int64_t i = 0; i < g->n; ++i) {
+        if ((i & 127) == 0) stream_block(seed, chain, MCXO_TAG_INIT, 0, (uint64_t)i >> 7, 0, out);
+        g->spins[i] = ((out[(i >> 5) & 3] >> (i & 31)) & 1u) ? 1 : -1;
+    }
+    mcxo_graph_recompute(g);
+}
+
+/* local_pair_interactions: graph s_i * sum_j s_j (abstractions.jl:41-48); matrix sum_j s_i J_ij s_j, j != i (ising.jl:295-305) */
+double mcxo_graph_local_pair(const mcxo_graph *g, int64_t i)
+{
+    if (!g->matrix) {
+        int64_t si = g->spins[i], acc = 0;
+        for (int64_t p = g->rowptr[i]; p < g->rowptr[i + 1]; ++p) acc += si * g->spins[g->col[p]];
+        return (double)acc;
+    }
+    double acc = 0.0, si = (double)g->spins[i];
+    for (int64_t p = g->rowptr[i]; p < g->rowptr[i + 1]; ++p) {
+        int64_t j = g->col[p];
+        if (j != i) acc += si * g->val[p] * (double)g->spins[j];
+    }
+    return acc;
+}
+
+/* _pair_sum (ising.jl:163-169, 307-313), _field_sum (:171-179, 315-323) */
+static double graph_pair_sum(const mcxo_graph *g)
+{
+    double acc = 0.0;
+    for (int64_t i = 0; i < g->n; ++i) acc += mcxo_graph_local_pair(g, i);
+    return g->matrix ? acc / 2 : g->J * (acc / 2);
+}
+static double graph_field_sum(const mcxo_graph *g)
+{
+    if (g->hmode == 0) return 0.0;
+    if (g->hmode == 1) {
+        int64_t s = 0;
+        for (int64_t i = 0; i < g->n; ++i) s += g->spins[i];
+        return g->h * (double)s;
+    }
+    double acc = 0.0;
+    for (int64_t i = 0; i < g->n; ++i) acc += g->hvec[i] * (double)g->spins[i];
+    return acc;
+}
+
+void mcxo_graph_recompute(mcxo_graph *g)
+{
+    g->sum_pair = graph_pair_sum(g);
+    g->sum_spins = 0;
+    for (int64_t i = 0; i < g->n; ++i) g->sum_spins += g->spins[i];
+    g->sum_field = graph_field_sum(g);
+}
+
+double mcxo_graph_energy(const mcxo_graph *g, int full)
+{
+    if (full) return -graph_pair_sum(g) - graph_field_sum(g);     /* _full_energy */
+    return g->hmode == 0 ? -g->sum_pair : -g->sum_pair - g->sum_field;
+}
+int64_t mcxo_graph_magnetization(const mcxo_graph *g) { return g->sum_spins; }
+
+/* flip_changes + delta_energy (ising.jl:187-198, 339-351) */
+static inline void graph_flip_changes(const mcxo_graph *g, int64_t i, double *dpair, int64_t *dspin)
+{
+    double lp = mcxo_graph_local_pair(g, i);
+    *dpair = g->matrix ? -2.0 * lp : (-2 * g->J) * lp;
+    *dspin = -2 * (int64_t)g->spins[i];
+}
+static inline double graph_dfield(const mcxo_graph *g, int64_t dspin, int64_t i)
+{
+    return g->hmode == 0 ? 0.0 : g->hmode == 1 ? g->h * (double)dspin : g->hvec[i] * (double)dspin;
+}
+double mcxo_graph_delta_energy(const mcxo_graph *g, int64_t i)
+{
+    double dpair; int64_t dspin;
+    graph_flip_changes(g, i, &dpair, &dspin);
+    return -dpair - graph_dfield(g, dspin, i);
+}
+/* modify! (ising.jl:200-214, 353-367) */
+void mcxo_graph_flip(mcxo_graph *g, int64_t i)
+{
+    double dpair; int64_t dspin;
+    graph_flip_changes(g, i, &dpair, &dspin);
+    g->spins[i] = (int8_t)(-g->spins[i]);
+    g->sum_pair += dpair;
+    g->sum_spins += dspin;
+    g->sum_field += graph_dfield(g, dspin, i);
+}
+
+/* spin_flip! without pick_site (ising.jl:35-58) */
+void mcxo_graph_attempt_at(mcxo_graph *g, mcxo_alg *a, int64_t i, mcxo_rng *r)
+{
+    double dE = mcxo_graph_delta_energy(g, i);
+    if (a->rule == MCXO_HEATBATH) {
+        int s_old = g->spins[i];
+        double p_plus = mcxo_logistic(a->beta * (double)s_old * dE);
+        int s_new = mcxo_rand_f64(r) < p_plus ? 1 : -1;
+        if (s_new != s_old) mcxo_graph_flip(g, i);
+        a->steps += 1;
+    } else if (accept_delta(a, dE, r)) {
+        mcxo_graph_flip(g, i);
+    }
+}
+
+/* greedy first-fit colouring in site order; returns the number of colours */
+int mcxo_graph_colour(const mcxo_graph *g, int32_t *colour)
+{
+    int ncol = 0;
+    int64_t maxdeg = 0;
+    for (int64_t i = 0; i < g->n; ++i) {
+        int64_t d = g->rowptr[i + 1] - g->rowptr[i];
+        if (d > maxdeg) maxdeg = d;
+    }
+    int64_t *mark = (int64_t *)malloc(sizeof(int64_t) * (size_t)(maxdeg + 2));
+    for (int64_t k = 0; k < maxdeg + 2; ++k) mark[k] = -1;
+    for (int64_t i = 0; i < g->n; ++i) {
+        for (int64_t p = g->rowptr[i]; p < g->rowptr[i + 1]; ++p) {
+            int64_t j = g->col[p];
+            if (j < i && j != i && colour[j] <= maxdeg) mark[colour[j]] = i;
+        }
+        int c = 0;
+        while (mark[c] == i) ++c;
+        colour[i] = c;
+        if (c + 1 > ncol) ncol = c + 1;
+    }
+    free(mark);
+    return ncol;
+}
+
+void mcxo_graph_sweep_coloured(mcxo_graph *g, mcxo_alg *a, uint64_t seed, uint32_t chain, uint64_t sweep0, int64_t nsweeps,
+                               const int32_t *colour, int ncolours)
+{
+    mcxo_rng r; r.seed = seed; r.chain = chain;
+    for (int64_t sw = 0; sw < nsweeps; ++sw)
+        for (int c = 0; c < ncolours; ++c) {
+            uint64_t t = (uint64_t)ncolours * (sweep0 + (uint64_t)sw) + (uint64_t)c;
+            uint64_t slot = 0;
+            for (int64_t i = 0; i < g->n; ++i) {
+                if (colour[i] != c) continue;
+                mcxo_rng_position(&r, MCXO_TAG_SWEEP, t, slot++);
+                mcxo_graph_attempt_at(g, a, i, &r);
+            }
+        }
+}

@@ -154,6 +154,39 @@ void   mcxo_set_betas(int64_t n, double bmin, double bmax, int geometric, double
 void   mcxo_rx_update(int64_t n, int64_t *stage, int64_t *indices, int64_t *steps, int64_t *accepted,
                       double *beta_of_slot, const double *xs, const double *u_of_slot);
 
+
+/* ---------------- general topologies (IsingGraph / IsingMatrix, ising.jl:86-360) ---------------- */
+typedef struct {
+    int64_t  n;
+    int64_t *rowptr, *col;   /* CSR neighbour lists, 0-based, the reference's adjacency order (ascending) */
+    double  *val;            /* J_ij per entry (IsingMatrix) or NULL (IsingGraph: global J) */
+    int      matrix;
+    double   J;
+    int      hmode;          /* 0: no field, 1: uniform h, 2: per-site h_i */
+    double   h, *hvec;
+    int8_t  *spins;
+    double   sum_pair;       /* sum_pair_interactions */
+    int64_t  sum_spins;
+    double   sum_field;      /* sum_field_interactions */
+} mcxo_graph;
+
+mcxo_graph *mcxo_graph_create(int64_t n, const int64_t *rowptr, const int64_t *col, const double *val, double J,
+                              int hmode, double h, const double *hvec);
+void    mcxo_graph_destroy(mcxo_graph *g);
+void    mcxo_graph_set_spins(mcxo_graph *g, const int8_t *spins);
+void    mcxo_graph_get_spins(const mcxo_graph *g, int8_t *spins);
+void    mcxo_graph_init_random(mcxo_graph *g, uint64_t seed, uint32_t chain);
+void    mcxo_graph_recompute(mcxo_graph *g);
+double  mcxo_graph_local_pair(const mcxo_graph *g, int64_t i);
+double  mcxo_graph_energy(const mcxo_graph *g, int full);
+int64_t mcxo_graph_magnetization(const mcxo_graph *g);
+double  mcxo_graph_delta_energy(const mcxo_graph *g, int64_t i);
+void    mcxo_graph_flip(mcxo_graph *g, int64_t i);                       /* modify!(sys, i, flip_changes(sys, i)...) */
+void    mcxo_graph_attempt_at(mcxo_graph *g, mcxo_alg *a, int64_t i, mcxo_rng *r);
+int     mcxo_graph_colour(const mcxo_graph *g, int32_t *colour);         /* greedy first-fit in site order */
+void    mcxo_graph_sweep_coloured(mcxo_graph *g, mcxo_alg *a, uint64_t seed, uint32_t chain, uint64_t sweep0,
+                                  int64_t nsweeps, const int32_t *colour, int ncolours);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,27 @@ def lib():
     L.mcxo_resolve_pair.argtypes = [i64, i64, i64, pi64]
     L.mcxo_set_betas.argtypes = [i64, dbl, dbl, ci, pd]
     L.mcxo_rx_update.argtypes = [i64, pi64, pi64, pi64, pi64, pd, pd, pd]
+    # general topologies
+    L.mcxo_graph_create.argtypes = [i64, vp, vp, vp, dbl, ci, dbl, vp]
+    L.mcxo_graph_create.restype = vp
+    L.mcxo_graph_destroy.argtypes = [vp]
+    L.mcxo_graph_set_spins.argtypes = [vp, vp]
+    L.mcxo_graph_get_spins.argtypes = [vp, vp]
+    L.mcxo_graph_init_random.argtypes = [vp, u64, u32]
+    L.mcxo_graph_recompute.argtypes = [vp]
+    L.mcxo_graph_local_pair.argtypes = [vp, i64]
+    L.mcxo_graph_local_pair.restype = dbl
+    L.mcxo_graph_energy.argtypes = [vp, ci]
+    L.mcxo_graph_energy.restype = dbl
+    L.mcxo_graph_magnetization.argtypes = [vp]
+    L.mcxo_graph_magnetization.restype = i64
+    L.mcxo_graph_delta_energy.argtypes = [vp, i64]
+    L.mcxo_graph_delta_energy.restype = dbl
+    L.mcxo_graph_flip.argtypes = [vp, i64]
+    L.mcxo_graph_attempt_at.argtypes = [vp, C.POINTER(_Alg), i64, C.POINTER(_Rng)]
+    L.mcxo_graph_colour.argtypes = [vp, vp]
+    L.mcxo_graph_colour.restype = ci
+    L.mcxo_graph_sweep_coloured.argtypes = [vp, C.POINTER(_Alg), u64, u32, u64, i64, vp, ci]
     _lib = L
     return L
 
@@ -314,3 +335,96 @@ def stats_random_site(L, beta, nchains, therm, sweeps, interval, nthreads=8, see
     lib().mcxo_stats_random_site(L, beta, nchains, therm, sweeps, interval, nthreads, seed,
                                  out.ctypes.data_as(C.POINTER(C.c_double)))
     return out
+
+
+class Graph:
+    """IsingGraph (val=None: global J) / IsingMatrix (val: J_ij per CSR entry) with h = 0, a scalar or a vector
+    (SpinSystems/src/ising.jl:86-360).  rowptr / col: 0-based CSR neighbour lists in ascending neighbour order."""
+
+    def __init__(self, rowptr, col, val=None, J=1.0, h=0):
+        self.rowptr = np.ascontiguousarray(rowptr, dtype=np.int64)
+        self.col = np.ascontiguousarray(col, dtype=np.int64)
+        self.val = None if val is None else np.ascontiguousarray(val, dtype=np.float64)
+        self.n = len(self.rowptr) - 1
+        if np.ndim(h) == 0:
+            hmode, hs, hv = (0 if h == 0 else 1), float(h), None
+        else:
+            hv = np.ascontiguousarray(h, dtype=np.float64)
+            hmode, hs = 2, 0.0
+        self.hvec = hv
+        self.p = lib().mcxo_graph_create(self.n, self.rowptr.ctypes.data, self.col.ctypes.data,
+                                         None if self.val is None else self.val.ctypes.data, float(J), hmode, hs,
+                                         None if hv is None else hv.ctypes.data)
+
+    def __del__(self):
+        try:
+            lib().mcxo_graph_destroy(self.p)
+        except Exception:
+            pass
+
+    @property
+    def spins(self):
+        out = np.empty(self.n, dtype=np.int8)
+        lib().mcxo_graph_get_spins(self.p, out.ctypes.data)
+        return out
+
+    @spins.setter
+    def spins(self, v):
+        v = np.ascontiguousarray(v, dtype=np.int8)
+        lib().mcxo_graph_set_spins(self.p, v.ctypes.data)
+
+    def init_random(self, seed, chain=0):
+        lib().mcxo_graph_init_random(self.p, seed, chain)
+
+    def energy(self, full=False):
+        return lib().mcxo_graph_energy(self.p, int(full))
+
+    def magnetization(self):
+        return lib().mcxo_graph_magnetization(self.p)
+
+    def local_pair_interactions(self, i):
+        return lib().mcxo_graph_local_pair(self.p, i)
+
+    def delta_energy(self, i):
+        return lib().mcxo_graph_delta_energy(self.p, i)
+
+    def flip(self, i):
+        lib().mcxo_graph_flip(self.p, i)
+
+    def colour(self):
+        c = np.empty(self.n, dtype=np.int32)
+        n = lib().mcxo_graph_colour(self.p, c.ctypes.data)
+        return c, n
+
+    def sweep_coloured(self, alg, seed, chain, sweep0, nsweeps, colour=None, ncolours=None):
+        if colour is None:
+            colour, ncolours = self.colour()
+        colour = np.ascontiguousarray(colour, dtype=np.int32)
+        lib().mcxo_graph_sweep_coloured(self.p, C.byref(alg.a), seed, chain, sweep0, nsweeps, colour.ctypes.data, int(ncolours))
+
+
+def grid_csr(dims, periodic=True):
+    """CSR neighbour lists of Graphs.SimpleGraphs.grid(dims; periodic): site i = x + Lx*(y + Ly*z), neighbours ascending,
+    duplicate edges of length-2 periodic dimensions merged as a SimpleGraph does"""
+    dims = [int(d) for d in dims]
+    n = int(np.prod(dims))
+    strides = np.cumprod([1] + dims[:-1])
+    rows = [set() for _ in range(n)]
+    for i in range(n):
+        for ax, (L, st) in enumerate(zip(dims, strides)):
+            x = (i // st) % L
+            for dx in (-1, 1):
+                y = x + dx
+                if periodic:
+                    y %= L
+                elif y < 0 or y >= L:
+                    continue
+                j = i + (y - x) * st
+                if j != i:
+                    rows[i].add(j)
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    col = []
+    for i, r in enumerate(rows):
+        col.extend(sorted(r))
+        rowptr[i + 1] = len(col)
+    return rowptr, np.array(col, dtype=np.int64)

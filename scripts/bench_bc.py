@@ -7,13 +7,14 @@ from mcx_b200._lib import check, lib
 
 stream = torch.cuda.Stream()
 ctx = m.Context(0, stream=stream.cuda_stream)
+RULE = os.environ.get("BC_RULE", "metropolis")       # BC_RULE=heatbath: the two-threshold rule (blume_capel.jl:61-85)
 for L, n in ((8192, 1), (1024, 64), (512, 256)):
-    row = {"L": L, "chains": n}
+    row = {"L": L, "chains": n, "rule": RULE}
     for mode in ("1", "0"):
         os.environ["MCX_BC2D"] = mode
         for track in (False, True):
             s = m.BlumeCapel([L, L], J=1, D=0.5, nchains=n, ctx=ctx); s.set_tracking(track)
-            rng = m.PhiloxRNG(3); alg = m.Metropolis(rng, beta=0.9)
+            rng = m.PhiloxRNG(3); alg = (m.HeatBath if RULE == 'heatbath' else m.Metropolis)(rng, beta=0.9)
             m.init_(s, "random", rng=rng)
             ns = 20
             m.sweep_(s, alg, ns)

@@ -123,3 +123,38 @@ def test_parallel_tempering_restart(m, oracle, tmp_path):
     assert all(0 < a.accepted < a.steps for a in ref_pt.replica.algs)
     assert sum(ref_pt.accepted) > 0
     m.finalize_(ck)
+
+
+def test_device_tau_int_matches_host_estimator(m):
+    """mcx_series_tau_int reduces the on-device series to one tau_int per chain (autocorrelations.jl:28-65); it must agree
+    with the reference's estimator applied to the copied-back series (deterministic block sums: tolerance 1e-10 relative),
+    give 0.5 for a constant signal (test/test_measurements.jl:154) and reject the same arguments."""
+    L, nch, n = 32, 5, 600
+    sys_ = m.Ising([L, L], nchains=nch)
+    alg = m.Metropolis(m.PhiloxRNG(17, 0), beta=0.42)
+    sys_.init_("random", rng=alg.rng)
+    m.sweep_(sys_, alg, 50)
+    series = m.sweep_series_(sys_, alg, n, interval=2)
+    for obs, key, f in (("energy", "energy", lambda x: x), ("magnetization", "magnetization", lambda x: x),
+                        ("abs_magnetization", "magnetization", np.abs)):
+        for max_lag, c in ((None, 5.0), (50, 5.0), (None, 2.5)):
+            dev = m.series_tau_int_(sys_, n, obs, max_lag=max_lag, c=c)
+            host = [m.integrated_autocorrelation_time(f(np.asarray(series[key][:, ch], dtype=np.float64)), max_lag=max_lag, c=c)
+                    for ch in range(nch)]
+            assert np.allclose(dev, host, rtol=1e-10, atol=0), (obs, max_lag, c, dev, host)
+            assert np.all(dev >= 0.5)
+    # shorter prefix of the same series
+    dev = m.series_tau_int_(sys_, 100, "energy")
+    host = [m.integrated_autocorrelation_time(np.asarray(series["energy"][:100, ch], dtype=np.float64)) for ch in range(nch)]
+    assert np.allclose(dev, host, rtol=1e-10, atol=0)
+    # a frozen lattice (beta -> infinity from all-up): constant series, tau_int == 0.5
+    cold = m.Ising([L, L])
+    calg = m.Metropolis(m.PhiloxRNG(1, 0), beta=50.0)
+    m.sweep_series_(cold, calg, 64, interval=1)
+    assert m.series_tau_int_(cold, 64, "energy")[0] == 0.5
+    with pytest.raises(ValueError):
+        m.series_tau_int_(sys_, n, "energy", max_lag=n // 2 + 1)
+    with pytest.raises(ValueError):
+        m.series_tau_int_(sys_, n, "energy", c=0.0)
+    with pytest.raises(AssertionError):
+        m.series_tau_int_(sys_, n + 1, "energy")

@@ -219,3 +219,48 @@ def test_wang_landau_group_decisions_bit_exact(m, oracle, spec, monkeypatch):
     N = 64
     _wl_device_vs_oracle(m, oracle, 1, [8, 8], 2, 3, 81, "up", 0, 1, N + 1, 0, [0.7, 0.35], 30,
                          observable=m._lib.OBS_SPIN2_WITH_PAIR_BOLTZMANN, beta_pair=1 / 0.9)
+
+
+@pytest.mark.parametrize("window", [None, "0"])
+def test_logweight_window_recentres_bit_exact(m, oracle, window, monkeypatch):
+    """The chains keep a window of the log-weight table in shared memory (k_flat_warp<WIN>) and recentre it -- dirty
+    Wang-Landau entries written back first -- when a batch could leave it.  Tables much wider than the window, walkers
+    that start at the edge of the spectrum and travel: every table entry, spin and counter must still equal the
+    oracle's, with the window (default) and without it (MCX_FLAT_WINDOW=0)."""
+    if window is None:
+        monkeypatch.delenv("MCX_FLAT_WINDOW", raising=False)
+    else:
+        monkeypatch.setenv("MCX_FLAT_WINDOW", window)
+    # Wang-Landau, 2-D 64 x 64 from the ground state: 4097 bins against a 1025-entry window
+    r = _wl_device_vs_oracle(m, oracle, 0, [64, 64], 3, 2, 90, "up", -8192, 4, 4097, 0, [1.0, 0.25], 12)
+    assert min(r) > 0.05
+    # the same in an energy window of 1500 bins (policy 1), and 3-D (window 1537 entries against 3073 bins)
+    _wl_device_vs_oracle(m, oracle, 0, [64, 64], 2, 0, 91, "up", -8192, 4, 1500, 1, [0.5], 10)
+    _wl_device_vs_oracle(m, oracle, 0, [16, 16, 16], 2, 4, 92, "up", -12288, 4, 3073 * 2 - 1, 0, [1.0], 6)
+    # multicanonical chains on the (pair, sum s^2) observable, 4097 bins against a 513-entry window, non-flat weights
+    import ctypes as C
+    lib, check = m.lib(), m._lib.check
+    L, nch, seed, nsweeps = 64, 3, 93, 6
+    N = L * L
+    lw0 = 1e-3 * (np.arange(N + 1, dtype=np.float64) - 0.6 * N) ** 2 / N
+    sys_ = m.BlumeCapel([L, L], nchains=nch)
+    check(lib.mcx_lattice_set_first_chain_id(sys_.h_lat, 1))
+    sys_.set_rng(seed, 0)
+    h = C.c_void_p()
+    check(lib.mcx_flat_create(sys_.h_lat, m._lib.FLAT_MUCA, m._lib.OBS_SPIN2_WITH_PAIR_BOLTZMANN, 0, 1, N + 1, 1 / 0.9, 0, C.byref(h)))
+    check(lib.mcx_flat_set_logweight(h, lw0.ctypes.data))
+    check(lib.mcx_flat_sweep(h, nsweeps))
+    hist = np.empty(N + 1, dtype=np.float64)
+    check(lib.mcx_flat_get_histogram(h, hist.ctypes.data))
+    spins = np.asarray(sys_.spins).reshape(nch, N)
+    ref_hist = np.zeros(N + 1)
+    for c in range(nch):
+        s = oracle.System(oracle.BLUME_CAPEL, [L, L])
+        s.spins = np.ones(N, dtype=np.int8)
+        f = oracle.Flat(0, 1, N + 1)
+        f.logweight[:] = lw0
+        assert s.flat_sweep(oracle.Alg(0, 0.0), f, 0, 1, 1 / 0.9, seed, 1 + c, 0, nsweeps) == 0
+        assert np.array_equal(spins[c], s.spins), c
+        ref_hist += f.histogram
+    assert np.array_equal(hist, ref_hist)
+    check(lib.mcx_flat_destroy(h))

@@ -69,7 +69,7 @@ def test_fast_kernel_equals_generic_kernel(m, L):
     keys = ("MCX_FORCE_GENERIC", "MCX_ROWS_PER_STRIP", "MCX_VARIANT", "MCX_RESIDENT", "MCX_FULL")
     envs = [{"MCX_FORCE_GENERIC": "1"}, {}, {"MCX_RESIDENT": "0"}, {"MCX_FULL": "0"}, {"MCX_FULL": "1"}, {"MCX_FORCE_GENERIC": "2"},
             {"MCX_ROWS_PER_STRIP": "2"}, {"MCX_ROWS_PER_STRIP": "64"}]
-    envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in (0, 3, 6) for r in ("4", "16")]
+    envs += [{"MCX_VARIANT": str(v), "MCX_ROWS_PER_STRIP": r} for v in (0, 3) for r in ("4", "16")]
     for env in envs:
         for k in keys:
             os.environ.pop(k, None)
@@ -185,10 +185,11 @@ def test_ising3d_vectorised_kernel(m, oracle, dims, rule):
 
 
 @pytest.mark.parametrize("dims", [[64, 64], [256, 64], [32, 128], [512, 256]])
-@pytest.mark.parametrize("rule", [0, 1])
+@pytest.mark.parametrize("rule", [0, 1, 2])
 def test_blume_capel_vectorised_kernel(m, oracle, dims, rule):
-    """k_bc2d (packed 15-bit decisions, four Philox blocks per thread-row) against the oracle and against the
-    rows-of-8 kernel, tracked and untracked sums, several couplings"""
+    """k_bc2d (packed 15-bit decisions; four Philox blocks per thread-row for Metropolis / Glauber, two and a pair of
+    thresholds per draw for the heat bath) against the oracle and against the rows-of-8 kernel, tracked and untracked
+    sums, several couplings"""
     for beta, J, D, h, tracking in ((0.8, 1, 0, 0, True), (1.1, 1.0, 0.5, 0.0, False), (0.6, 1.0, 0.2, 0.1, True), (2.5, 1, 1.9, 0, True)):
         nsweeps = 6
         outs = []
@@ -200,13 +201,15 @@ def test_blume_capel_vectorised_kernel(m, oracle, dims, rule):
             alg = _make_alg(m, rule, beta, 77, 2)
             sys_.init_("random", rng=alg.rng)
             m.sweep_(sys_, alg, nsweeps)
-            outs.append((sys_.spins.copy(), sys_.pair_sum(), sys_.magnetization(), sys_.spin2_sum(), alg.accepted))
+            outs.append((sys_.spins.copy(), sys_.pair_sum(), sys_.magnetization(), sys_.spin2_sum(), getattr(alg, "accepted", None),
+                         sys_.accepted()))
         os.environ.pop("MCX_BC2D", None)
         assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1:] == outs[1][1:]
         s_or, a_or = _oracle_run(oracle, oracle.BLUME_CAPEL, dims, rule, beta, J, h, D, 77, 2, nsweeps)
         assert np.array_equal(outs[0][0], s_or.spins)
         assert outs[0][1] == s_or.pair_count() and outs[0][2] == s_or.magnetization(full=True) and outs[0][3] == s_or.spin2_sum()
-        assert outs[0][4] == a_or.accepted
+        if rule != 2:
+            assert outs[0][4] == a_or.accepted
 
 
 def test_blume_capel_vectorised_batched_labels(m, oracle):
