@@ -622,7 +622,10 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps)
 
 bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
 {
-    if (!lat->fast2d || lat->model != MCX_ISING || lat->nchains != 1) return false;
+    // one Ising lattice: 2-D in bands of rows, 3-D in bands of z-planes (k_ising3d.cu runs a z-range per launch)
+    const bool d3 = lat->ndim == 3 && lat->model == MCX_ISING && lat->view.Lx % 32 == 0 && lat->table_len == 14 && knobs().ising3d != 0 &&
+                    !lat->slab;
+    if ((!d3 && (!lat->fast2d || lat->model != MCX_ISING)) || lat->nchains != 1) return false;
     if (lat->slab && !(lat->slab->attached && lat->slab->remote)) return false;      // in-process slabs advance in lockstep
     if (knobs().variant >= 0 || knobs().rows_per_strip >= 0) return false;
     const int bands_env = knobs().bands;
@@ -630,13 +633,21 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
     // 8 bands (the hardware queues a process gets by default) of 16-row strips, each at least ~100 CTA items:
     // measured +8 % at L = 8192, +17 % at 16384, +10 % at 32768; 2 bands gain nothing (each waits for the other),
     // 4 bands gain less, shorter strips or smaller bands lose (profiles/r01_bands_groups.md).  MCX_BANDS forces a count.
-    const int Ly = lat->view.Ly;
+    const int Ly = d3 ? lat->view.Lz : lat->view.Ly;      // the banded dimension
     const bool forced = bands_env > 1;
     int bands = forced ? (bands_env > 16 ? 16 : bands_env) : 8;
     const int R = 16;
-    if (Ly % (R * bands) != 0) return false;
-    const int64_t items_per_band = ((int64_t)(Ly / bands / R) * (lat->view.half >> 4) + kThreads - 1) / kThreads;
-    if (!forced && items_per_band < 100) bands = 0;
+    if (d3) {
+        // a band must leave its neighbours a plane of their own: at least two planes per band
+        if (Ly % bands != 0 || Ly / bands < 2 || lat->view.Ly % 2 != 0) return false;
+        if (lat->storage != MCX_STORAGE_BIT && (int64_t)(lat->view.Ly / 2) * lat->view.Lz * (lat->view.half >> 4) < 96) return false;   // rows-of-8 territory
+        const int64_t items_per_band = ((int64_t)(Ly / bands) * (lat->view.Ly / 4) * (lat->view.half >> 4) + kThreads - 1) / kThreads;
+        if (!forced && items_per_band < 64) return false;
+    } else {
+        if (Ly % (R * bands) != 0) return false;
+        const int64_t items_per_band = ((int64_t)(Ly / bands / R) * (lat->view.half >> 4) + kThreads - 1) / kThreads;
+        if (!forced && items_per_band < 100) bands = 0;
+    }
     if (!bands) return false;
     const int nr = Ly / bands;
     mcx_ctx *ctx = lat->ctx;
@@ -657,7 +668,8 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
                 g_launch_range = LaunchRange();
                 g_launch_range.row0 = b * nr; g_launch_range.nrows = nr; g_launch_range.R = R; g_launch_range.stream = ctx->aux[b]; g_launch_range.use_stream = true;
                 const uint64_t t = 2 * (lat->sweep + (uint64_t)s) + (uint64_t)colour;
-                if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
+                if (d3) launch_sweep_ising3d(lat, colour, t);
+                else if (colour == 0) launch_c<0>(lat, t); else launch_c<1>(lat, t);
                 cudaEventRecord(ctx->aux_join[b], ctx->aux[b]);
             }
         }

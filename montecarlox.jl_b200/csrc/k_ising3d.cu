@@ -132,7 +132,7 @@ template <int COLOUR, bool HEATBATH, bool TRACK>
 __global__ void __launch_bounds__(k3Threads, 5)
 k_ising3d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g, const int32_t *__restrict__ labels,
           long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi, uint64_t t, uint32_t first_chain, int R,
-          int strips_per_plane, int blocks_per_chain, int nitems)
+          int strips_per_plane, int blocks_per_chain, int nitems, int z0, int nz)
 {
     __shared__ uint32_t s_pair[k3PairWords];
     __shared__ uint32_t s_thi[k3Table], s_tlo[k3Table];
@@ -140,7 +140,7 @@ k_ising3d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
 
     const int half = L.half;
     const int nseg = half >> 4;
-    const int64_t G = (int64_t)strips_per_plane * L.Lz * nseg;
+    const int64_t G = (int64_t)strips_per_plane * nz * nseg;      // this launch: z-planes [z0, z0 + nz)
     const int lane = threadIdx.x & 31;
     const uint32_t t_lo = (uint32_t)t;
     const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP), c2lo = ctr_word2(t, 1, TAG_SWEEP);
@@ -169,8 +169,9 @@ k_ising3d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         const int64_t g = active ? g0 : G - 1;
         const int sidx = (int)(g / nseg);                         // strip index over all planes
         const int seg = (int)(g - (int64_t)sidx * nseg);
-        const int z = sidx / strips_per_plane;
-        const int y0 = (sidx - z * strips_per_plane) * R;         // even
+        const int zl = sidx / strips_per_plane;
+        const int z = z0 + zl;
+        const int y0 = (sidx - zl * strips_per_plane) * R;         // even
         const uint32_t chain_id = first_chain + (uint32_t)chain;
         const int pa = (COLOUR + z) & 1;                          // in-row pairing of the strip's even rows
 
@@ -253,7 +254,7 @@ template <int COLOUR, bool HEATBATH, bool TRACK>
 __global__ void __launch_bounds__(k3Threads, 5)
 k_ising3d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g, const int32_t *__restrict__ labels,
                long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi, uint64_t t, uint32_t first_chain, int R,
-               int strips_per_plane, int blocks_per_chain, int nitems)
+               int strips_per_plane, int blocks_per_chain, int nitems, int z0, int nz)
 {
     __shared__ uint32_t s_pair[k3PairWords];
     __shared__ uint32_t s_thi[k3Table], s_tlo[k3Table];
@@ -261,7 +262,7 @@ k_ising3d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__
 
     const int half = L.half;
     const int nseg = half >> 4;
-    const int64_t G = (int64_t)strips_per_plane * L.Lz * nseg;
+    const int64_t G = (int64_t)strips_per_plane * nz * nseg;      // this launch: z-planes [z0, z0 + nz)
     const int lane = threadIdx.x & 31;
     const uint32_t t_lo = (uint32_t)t;
     const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP), c2lo = ctr_word2(t, 1, TAG_SWEEP);
@@ -290,8 +291,9 @@ k_ising3d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__
         const int64_t g = active ? g0 : G - 1;
         const int sidx = (int)(g / nseg);
         const int seg = (int)(g - (int64_t)sidx * nseg);
-        const int z = sidx / strips_per_plane;
-        const int y0 = (sidx - z * strips_per_plane) * R;         // even
+        const int zl = sidx / strips_per_plane;
+        const int z = z0 + zl;
+        const int y0 = (sidx - zl * strips_per_plane) * R;         // even
         const uint32_t chain_id = first_chain + (uint32_t)chain;
         const int pa = (COLOUR + z) & 1;
 
@@ -377,7 +379,11 @@ void launch_3d(mcx_lattice *lat, uint64_t t)
     cudaStream_t stream = g_launch_range.use_stream ? g_launch_range.stream : lat->ctx->stream;
     const int nseg = L.half >> 4;
     const int64_t ctas = (int64_t)lat->ctx->sm_count * 5;
+    // a band of z-planes (launch_sweeps_ising2d_banded): the same launch over planes [z0, z0 + nz)
+    const bool band = g_launch_range.nrows > 0;
+    const int z0 = band ? g_launch_range.row0 : 0, nz = band ? g_launch_range.nrows : L.Lz;
     // strips never cross a z-plane: the tallest even divisor of Ly up to 16 that still gives ~4 items per resident CTA
+    // (counted over the whole lattice, so that all bands of a half-sweep use the same strips)
     int R = 2;
     for (int r = 16; r >= 2; r -= 2) {
         if (L.Ly % r != 0) continue;
@@ -386,7 +392,7 @@ void launch_3d(mcx_lattice *lat, uint64_t t)
         if (items >= 4 * ctas || r <= 4) break;
     }
     const int strips_per_plane = L.Ly / R;
-    const int64_t G = (int64_t)strips_per_plane * L.Lz * nseg;
+    const int64_t G = (int64_t)strips_per_plane * nz * nseg;
     const int blocks_per_chain = (int)((G + k3Threads - 1) / k3Threads);
     const int nitems = (int)((int64_t)blocks_per_chain * nch);
     auto kern = lat->storage == MCX_STORAGE_BIT ? k_ising3d_bits<COLOUR, HEATBATH, TRACK> : k_ising3d<COLOUR, HEATBATH, TRACK>;
@@ -400,7 +406,7 @@ void launch_3d(mcx_lattice *lat, uint64_t t)
     if (grid > nitems) grid = nitems;
     kern<<<grid, k3Threads, 0, stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels + c0, lat->d_sums + (int64_t)c0 * SUM_FIELDS,
                                         (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain + (uint32_t)c0, R,
-                                        strips_per_plane, blocks_per_chain, nitems);
+                                        strips_per_plane, blocks_per_chain, nitems, z0, nz);
     lat->ctx->launches++;
 }
 

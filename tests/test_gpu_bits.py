@@ -79,6 +79,7 @@ def test_bits_3d_bit_exact_with_oracle(m, oracle, dims, rule):
     ([512, 512], 6, {"MCX_GROUPS": "3"}),
     ([512, 512], 6, {"MCX_GROUPS": "0"}),
     ([128, 64, 32], 3, {}),
+    ([128, 32, 32], 1, {"MCX_BANDS": "4"}),
 ])
 def test_bits_equal_int8(m, dims, nchains, env):
     """the two storages side by side at sizes the oracle would take long for: spins, sums and counters identical,

@@ -89,6 +89,7 @@ def test_fast_kernel_equals_generic_kernel(m, L):
     ([1024, 1024], 1, [{"MCX_BANDS": "2"}, {"MCX_BANDS": "4"}, {"MCX_BANDS": "8"}]),
     ([2048, 512], 1, [{"MCX_BANDS": "4"}]),
     ([512, 512], 6, [{"MCX_GROUPS": "2"}, {"MCX_GROUPS": "4"}, {"MCX_GROUPS": "6"}]),
+    ([64, 32, 32], 1, [{"MCX_BANDS": "4"}, {"MCX_BANDS": "8"}, {"MCX_BANDS": "16"}]),        # 3-D: bands of z-planes
 ])
 def test_bands_and_groups_equal_plain_launches(m, dims, nchains, envs):
     """a half-sweep issued as several overlapping launches (row bands of one lattice, chain groups of a
