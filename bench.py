@@ -274,7 +274,7 @@ def run_ours(args):
         elif args.config == "c4":
             leg = bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, cpu=not args.no_cpu)
         else:
-            leg = bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=16, walkers=64, cpu=not args.no_cpu)
+            leg = bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=16, walkers=64, cpu=not args.no_cpu, read_tables=True)
         leg.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                     "scaling": "strong" if args.config in ("c3", "c4") else "weak", "vs_baseline": None,
                     "dtype": "u8" if args.config in ("c1", "c3") else "f64", "data": "synthetic", "clocks": None})
@@ -453,7 +453,7 @@ def run_ours(args):
         cpu = world == 1 and not args.no_cpu
         for key, fn in (("c1", lambda: bench_c1(m, ctx, stream, args, cpu=cpu and rank == 0)),
                         ("c4", lambda: bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, iterations=2, therm=1, record=4, cpu=cpu)),
-                        ("c5", lambda: bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers=32, cpu=cpu))):
+                        ("c5", lambda: bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=16, walkers=32, cpu=cpu))):
             if key == "c1" and rank != 0:
                 continue
             try:
@@ -828,7 +828,7 @@ def cpu_leg_c5(nthreads, L=256):
             "sample": "%d walker(s) x 1 Wang-Landau sweep of 3-D Ising L=%d, one walker per thread (%.1f s)" % (nthreads, L, dt)}
 
 
-def bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers=32, L=256, sweeps=1, cpu=True):
+def bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers=32, L=256, sweeps=1, cpu=True, read_tables=False):
     """configs[4]: 3-D Ising L = 256 Wang-Landau, energy windows dealt to the ranks, `walkers` walkers per window with one
     table each (windows.py).  Timed: `sweeps` sweeps of every walker, tables left on the device."""
     import numpy as np
@@ -854,11 +854,16 @@ def bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers
         gathered = [None] * world
         dist.all_gather_object(gathered, energies)
         energies = np.concatenate(gathered)
-    # e2e: the same sweeps followed by the read-back of every table (what WangLandauWindows.sweep_ returns to the host)
+    # e2e: the same sweeps followed by the step's result on the host -- every walker's energy, or (read_tables: what
+    # WangLandauWindows.sweep_ hands back) every walker's whole log-weight table
     t0 = time.perf_counter()
-    wl.sweep_(sweeps)
+    if read_tables:
+        wl.sweep_(sweeps)
+        table_bytes = sum(a.nbytes for a in wl._lw)
+    else:
+        wl.sweep_device_(sweeps)
+        table_bytes = sum(np.asarray(e).nbytes for e in wl.energies())      # waits for the sweeps
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    table_bytes = sum(a.nbytes for a in wl._lw)
     attempts = sweeps * wl.N * walkers * nwin
     peak, _ = measured_peak()
     achieved = 2.0 * attempts / world / dt / 1e9
@@ -872,7 +877,8 @@ def bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=8, walkers
                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                         "note": "2 B/attempt; serial in the walker's energy, latency-bound by construction (BASELINE.md section 3)"},
            "e2e": {"value": attempts / (e2e_s * 1e9), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(table_bytes),
-                   "api": "WangLandauWindows.sweep_ (mcx_flat_sweep + mcx_flat_get_logweight of every walker)"},
+                   "api": "WangLandauWindows.sweep_ (mcx_flat_sweep + mcx_flat_get_logweight of every walker)" if read_tables else
+                          "WangLandauWindows.sweep_device_ + energies() (mcx_flat_sweep + mcx_observables); the tables stay on the device"},
            "parity": {"kind": "identical at every rank count (walkers keyed by global number)", "energies_sha": _sha(energies.astype(np.int64))}}
     wl.close()
     if cpu and rank == 0:

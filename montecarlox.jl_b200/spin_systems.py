@@ -281,8 +281,8 @@ class Ising(AbstractIsing):
     Open boundaries (`periodic=False`), a per-site field vector `h` or one coupling per edge (vector `J`) give the grid
     graph of the reference (Graphs.SimpleGraphs.grid) on the general-topology path (graph_systems.IsingGraph)."""
 
-    def __new__(cls, dims, J=1, h=0, D=0, nchains=1, ctx=None, periodic=True, storage="int8"):
-        if not periodic or np.ndim(h) != 0 or np.ndim(J) != 0:
+    def __new__(cls, dims=None, J=1, h=0, D=0, nchains=1, ctx=None, periodic=True, storage="int8"):
+        if dims is not None and (not periodic or np.ndim(h) != 0 or np.ndim(J) != 0):   # dims None: unpickling
             from .graph_systems import IsingGraph, grid_graph
             edges, n = grid_graph(dims, periodic)
             return IsingGraph(edges, n, J=J, h=h, nchains=nchains, ctx=ctx)      # not an instance of cls: __init__ is skipped
