@@ -658,6 +658,19 @@ def bench_c1(m, ctx, stream, args, sweeps=100000, cpu=True):
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - l0
     stats = _moments(series, N)
+    # error bars from the integrated autocorrelation times, computed on the device from the series it still holds
+    # (mcx_series_tau_int; autocorrelations.jl:28-65): err = sqrt(2 tau / n * var)
+    try:
+        from mcx_b200.measurements import series_tau_int_
+        tau_e = float(series_tau_int_(sys_, nmeasure, "energy")[0])
+        tau_m = float(series_tau_int_(sys_, nmeasure, "abs_magnetization")[0])
+        e = -series[:, 0, 0].astype(np.float64) / N
+        am = np.abs(series[:, 0, 1].astype(np.float64)) / N
+        stats.update({"tau_int_energy_in_measurements": tau_e, "tau_int_abs_m_in_measurements": tau_m,
+                      "err_energy_per_site": float(np.sqrt(2 * tau_e / nmeasure * e.var())),
+                      "err_abs_m": float(np.sqrt(2 * tau_m / nmeasure * am.var()))})
+    except Exception as ex:
+        stats["tau_int_error"] = repr(ex)
     # e2e: host spins in (pinned), the series out
     host = torch.from_numpy(sys_.spins.copy()).pin_memory()
     t0 = time.perf_counter()
@@ -683,9 +696,13 @@ def bench_c1(m, ctx, stream, args, sweeps=100000, cpu=True):
             out["cpu_baseline"] = cpu_leg_c1(1, sweeps)
             out["cpu_baseline_all_cores"] = cpu_leg_c1(_threads(), max(sweeps // 4, 1000))
             ref = out["cpu_baseline"]
-            out["parity"] = {"kind": "statistical (different update order and generator: random-site xoshiro vs checkerboard Philox)",
+            ref = out["cpu_baseline_all_cores"]           # 16+ independent chains: the better-averaged reference leg
+            out["parity"] = {"kind": "statistical (different update order and generator: random-site xoshiro vs checkerboard Philox); "
+                                     "differences against the all-cores reference leg, in units of this run's tau_int-based error",
                              "d_energy_per_site": stats["energy_per_site"] - ref["energy_per_site"],
-                             "d_abs_m": stats["abs_m"] - ref["abs_m"], "d_U4": stats["U4"] - ref["U4"]}
+                             "d_abs_m": stats["abs_m"] - ref["abs_m"], "d_U4": stats["U4"] - ref["U4"],
+                             "z_energy": (stats["energy_per_site"] - ref["energy_per_site"]) / max(stats.get("err_energy_per_site", 0.0), 1e-12),
+                             "z_abs_m": (stats["abs_m"] - ref["abs_m"]) / max(stats.get("err_abs_m", 0.0), 1e-12)}
         except Exception as e:
             out["cpu_baseline"] = {"error": repr(e)}
     return out

@@ -134,8 +134,8 @@ __device__ __forceinline__ uint4 bc_update_row(const uint4 tq, const uint4 U, co
         const uint32_t A = X + 3u * (X & 0x00ff00ffu);              // even bytes * 4: halfword = v1 * 256 + v0 * 4
         const uint32_t ttA = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (A & 0xffffu));
         const uint32_t ttB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (A >> 16));
-        const uint32_t hA = (__umulhi(rw[2 * w], 0x80000000u) & 0x7fff7fffu) | 0x80008000u;
-        const uint32_t hB = (__umulhi(rw[2 * w + 1], 0x80000000u) & 0x7fff7fffu) | 0x80008000u;
+        const uint32_t hA = ((rw[2 * w] >> 1) & 0x7fff7fffu) | 0x80008000u;
+        const uint32_t hB = ((rw[2 * w + 1] >> 1) & 0x7fff7fffu) | 0x80008000u;
         uint32_t rA, rB;
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rA) : "r"(ttA), "r"(hA));
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rB) : "r"(ttB), "r"(hB));

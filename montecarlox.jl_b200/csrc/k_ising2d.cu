@@ -178,7 +178,11 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         const uint32_t blk_step = (uint32_t)(half >> 3);
         Acc acc;
 
+#ifdef MCX_OPT_UNROLL2
+#pragma unroll 2
+#else
 #pragma unroll 1
+#endif
         for (int r = 0; r < R; r += 2) {
             const int row = row0 + r;
             // E = other row below the odd row; wraps only at the very last row of the lattice
@@ -642,7 +646,7 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
         if (Ly % bands != 0 || Ly / bands < 2 || lat->view.Ly % 2 != 0) return false;
         if (lat->storage != MCX_STORAGE_BIT && (int64_t)(lat->view.Ly / 2) * lat->view.Lz * (lat->view.half >> 4) < 96) return false;   // rows-of-8 territory
         const int64_t items_per_band = ((int64_t)(Ly / bands) * (lat->view.Ly / 4) * (lat->view.half >> 4) + kThreads - 1) / kThreads;
-        if (!forced && items_per_band < 64) return false;
+        if (!forced && items_per_band < 512) return false;      // 512^3: +16 %; 256^3 (128 items per band) loses to the launch rate: profiles/r02_bands3d.md
     } else {
         if (Ly % (R * bands) != 0) return false;
         const int64_t items_per_band = ((int64_t)(Ly / bands / R) * (lat->view.half >> 4) + kThreads - 1) / kThreads;

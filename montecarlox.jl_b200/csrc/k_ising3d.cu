@@ -80,8 +80,8 @@ __device__ __forceinline__ uint4 update_row3(const uint4 tq, const uint4 U, cons
         const uint32_t idx4 = tw[w] * 28u + nup[w] * 4u;        // byte b = 4 * (7 s + nup) of site 4w+b
         const uint32_t ttA = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (idx4 & 0xffffu));
         const uint32_t ttB = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(s_pair) + (idx4 >> 16));
-        const uint32_t hA = (__umulhi(rw[2 * w], 0x80000000u) & 0x7fff7fffu) | 0x80008000u;
-        const uint32_t hB = (__umulhi(rw[2 * w + 1], 0x80000000u) & 0x7fff7fffu) | 0x80008000u;
+        const uint32_t hA = ((rw[2 * w] >> 1) & 0x7fff7fffu) | 0x80008000u;
+        const uint32_t hB = ((rw[2 * w + 1] >> 1) & 0x7fff7fffu) | 0x80008000u;
         uint32_t rA, rB;
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rA) : "r"(ttA), "r"(hA));
         asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(rB) : "r"(ttB), "r"(hB));

@@ -233,7 +233,8 @@ bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps)
     if (want == 0 || nsweeps < 1) return false;
     if (lat->storage != MCX_STORAGE_INT8 || lat->slab || !lat->fast2d || lat->model != MCX_ISING) return false;
     if (knobs().variant >= 0 || knobs().rows_per_strip >= 0 || knobs().force_generic > 0) return false;
-    if (want < 0 && (lat->nchains < 2 || nsweeps < 4 || knobs().groups == 0)) return false;
+    if (want < 0 && (nsweeps < 4 || knobs().groups == 0)) return false;
+    const bool single = lat->nchains == 1;                      // one mid-size lattice: see the policy below
     mcx_ctx *ctx = lat->ctx;
     const LatView &L = lat->view;
     const int nseg = L.half >> 4;
@@ -245,18 +246,23 @@ bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps)
     const int64_t grid_max = (int64_t)ctx->sm_count * resident;
     // strip height: 16 rows if a half-sweep then still has an item for every resident CTA, else 8 (measured at 32
     // replicas of 1024 x 1024: 8 rows 1207 attempts/ns, 16 rows 1010, 4 rows 1018); MCX_QUEUE_ROWS overrides
+    // A single lattice of 1024 ... 8192 rows is launch- and tail-bound with one launch (or eight band launches) per
+    // half-sweep; as ONE series launch with strips short enough to give every resident CTA an item per half-sweep it runs
+    // at 1391 instead of 946 attempts/ns (L = 8192, 16-row strips), 963 / 598 (4096, 4 rows), 339 / 213 (2048, 2 rows),
+    // 118 / 67 (1024, 2 rows): profiles/r02_queue_single.md.  L = 16384 stays with the row bands (1522 against 1250).
     int R = knobs().queue_rows > 0 ? knobs().queue_rows : 16, ipc = 0;
+    const int r_min = single ? 2 : 8;
     for (;; R >>= 1) {
         int r = R;
         while (r > 2 && (L.Ly % r != 0 || r % 2 != 0)) --r;
         const int64_t Gt = (int64_t)(L.Ly / r) * nseg;
         ipc = (int)((Gt + kThreads - 1) / kThreads);
-        if ((int64_t)ipc * lat->nchains >= grid_max || R <= 8 || knobs().queue_rows > 0) { R = r; break; }
+        if ((int64_t)ipc * lat->nchains >= grid_max || R <= r_min || knobs().queue_rows > 0) { R = r; break; }
     }
     const int nstrips = L.Ly / R;
     if (nstrips < 3) return false;                             // the dependency span assumes distinct neighbours
     const int64_t per_half = (int64_t)ipc * lat->nchains;
-    if (want < 0 && (2 * per_half < grid_max || 2 * per_half > 3 * grid_max)) return false;
+    if (want < 0 && ((single ? 8 : 2) * per_half < grid_max || 2 * per_half > 3 * grid_max)) return false;
     if (per_half >= ((int64_t)1 << 31)) return false;
     // control block + progress words, sized for this lattice, zeroed per series
     const size_t need = sizeof(unsigned long long) * Q_WORDS + sizeof(uint32_t) * (size_t)per_half;

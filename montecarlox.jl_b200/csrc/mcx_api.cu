@@ -653,7 +653,8 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
             const uint64_t t = 2 * lat->sweep + (uint64_t)colour;
             if (force == 1) launch_sweep_generic(lat, colour, t);
             else if (force == 2 && launch_sweep_rows8(lat, colour, t)) {}
-            else if (launch_sweep_ising2d(lat, colour, t) || launch_sweep_bc2d(lat, colour, t) || launch_sweep_ising3d(lat, colour, t)) {
+            else if (launch_sweep_ising2d(lat, colour, t) || launch_sweep_bc2d(lat, colour, t) || launch_sweep_ising3d(lat, colour, t) ||
+                     launch_sweep_bc3d(lat, colour, t)) {
                 if (!lat->track_sums) lat->sums_dirty = true;
             }
             else if (!launch_sweep_rows8(lat, colour, t)) launch_sweep_generic(lat, colour, t);

@@ -164,6 +164,9 @@ void launch_staging_to_hostbits(mcx_lattice *lat, void *d_bits, cudaStream_t str
 // k_ising3d.cu: vectorised 3-D Ising half-sweep (Lx % 32 == 0), int8 or bit planes
 bool launch_sweep_ising3d(mcx_lattice *lat, int colour, uint64_t t);    // false: not applicable, nothing launched
 
+// k_bc3d.cu: vectorised 3-D Blume-Capel half-sweep, all three rules (Lx % 32 == 0)
+bool launch_sweep_bc3d(mcx_lattice *lat, int colour, uint64_t t);      // false: not applicable, nothing launched
+
 // k_slab.cu
 int32_t slab_half_sweep(mcx_lattice *lat);
 void slab_free(mcx_lattice *lat);

@@ -4,9 +4,9 @@
 mkdir -p gpurun_out/r02
 O=gpurun_out/r02/call10.log
 : > $O
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_bits.py -x -q -k "bands or blume or equal_int8" 2>&1 | tail -15 > gpurun_out/r02/call10_pytest.log
+timeout 1700 python -m pytest tests/test_gpu_checkpoint.py tests/test_gpu_multi.py tests/test_gpu_parity.py tests/test_gpu_bits.py tests/test_gpu_full_oracle.py -x -q 2>&1 | tail -25 > gpurun_out/r02/call10_pytest.log
 echo "pytest exit: ${PIPESTATUS[0]}" >> gpurun_out/r02/call10_pytest.log
-tail -5 gpurun_out/r02/call10_pytest.log
+tail -12 gpurun_out/r02/call10_pytest.log
 echo "== headline A/B: default, shr (shift on ALU), sub (plain subtraction), shrsub" >> $O
 timeout 900 bash scripts/gpu_ab.sh default shr sub shrsub >> $O 2>&1
 echo "== 3-D: bands off / default / 4 / 16" >> $O

@@ -213,6 +213,34 @@ def test_blume_capel_vectorised_kernel(m, oracle, dims, rule):
             assert outs[0][4] == a_or.accepted
 
 
+@pytest.mark.parametrize("dims", [[64, 16, 12], [32, 8, 24], [128, 32, 16]])
+@pytest.mark.parametrize("rule", [0, 1, 2])
+def test_blume_capel_3d_vectorised_kernel(m, oracle, dims, rule):
+    """k_bc3d (78-entry tables, z-neighbour rows as extra loads) against the oracle and against the rows-of-8 kernel"""
+    for beta, J, D, h, tracking in ((0.5, 1, 0, 0, True), (0.7, 1.0, 0.5, 0.1, False), (1.5, 1, 2.8, 0, True)):
+        nsweeps = 5
+        outs = []
+        for env in ({}, {"MCX_BC2D": "0"}):
+            os.environ.pop("MCX_BC2D", None)
+            os.environ.update(env)
+            sys_ = m.BlumeCapel(dims, J=J, D=D, h=h, nchains=2)
+            sys_.set_tracking(tracking)
+            alg = _make_alg(m, rule, beta, 78, 4)
+            sys_.init_("random", rng=alg.rng)
+            l0 = sys_.ctx.launch_count()
+            m.sweep_(sys_, alg, nsweeps)
+            outs.append((sys_.spins.copy(), np.array(sys_.pair_sum()), np.array(sys_.magnetization()), np.array(sys_.spin2_sum()),
+                         np.array(sys_.accepted())))
+        os.environ.pop("MCX_BC2D", None)
+        assert all(np.array_equal(a, b) for a, b in zip(*outs))
+        for c in range(2):
+            s_or, a_or = _oracle_run(oracle, oracle.BLUME_CAPEL, dims, rule, beta, J, h, D, 78, 4 + c, nsweeps)
+            assert np.array_equal(outs[0][0][c], s_or.spins)
+            assert outs[0][1][c] == s_or.pair_count() and outs[0][2][c] == s_or.magnetization(full=True) and outs[0][3][c] == s_or.spin2_sum()
+            if rule != 2:
+                assert outs[0][4][c] == a_or.accepted
+
+
 def test_blume_capel_vectorised_batched_labels(m, oracle):
     """chains with different tables (labels) and chain ids in one k_bc2d launch"""
     dims, n, nsweeps = [64, 64], 5, 5

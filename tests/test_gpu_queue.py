@@ -37,7 +37,7 @@ def _run(m, dims, nch, rule, track, nsweeps, seed, parts):
 @pytest.mark.parametrize("rule,track", [(0, True), (0, False), (1, True), (2, False)])
 def test_queue_series_equals_half_sweep_launches(m, dims, nch, rule, track, monkeypatch):
     nsweeps, parts = (7, 2) if dims != [1024, 1024] else (5, 1)
-    monkeypatch.delenv("MCX_QUEUE", raising=False)
+    monkeypatch.setenv("MCX_QUEUE", "0")
     monkeypatch.setenv("MCX_RESIDENT", "0")
     ref, _ = _run(m, dims, nch, rule, track, nsweeps, 99, parts)
     monkeypatch.setenv("MCX_QUEUE", "1")
@@ -45,6 +45,23 @@ def test_queue_series_equals_half_sweep_launches(m, dims, nch, rule, track, monk
     for a, b in zip(ref, got):
         assert np.array_equal(a, b)
     assert launches == parts                      # one launch per series (tracking off: + nothing; sums recomputed lazily)
+
+
+@pytest.mark.parametrize("dims,rows", [([2048, 2048], 2), ([4096, 4096], 4), ([1024, 1024], 2), ([4096, 1024], 2)])
+def test_single_mid_size_lattice_takes_the_queue_by_default(m, dims, rows, monkeypatch):
+    """one lattice of 1024 ... 8192 rows: the default policy runs a series of >= 4 sweeps as ONE launch with short strips
+    (2 / 4 rows); same trajectory as one launch per half-sweep"""
+    monkeypatch.setenv("MCX_RESIDENT", "0")
+    for rule, track in ((0, False), (2, True)):
+        monkeypatch.setenv("MCX_QUEUE", "0")
+        monkeypatch.setenv("MCX_BANDS", "0")
+        ref, l_ref = _run(m, dims, 1, rule, track, 6, 5, 1)
+        monkeypatch.delenv("MCX_QUEUE", raising=False)
+        monkeypatch.delenv("MCX_BANDS", raising=False)
+        got, launches = _run(m, dims, 1, rule, track, 6, 5, 1)
+        assert launches == 1 and l_ref >= 12, (launches, l_ref)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
 
 
 def test_queue_series_matches_oracle(m, oracle, monkeypatch):
