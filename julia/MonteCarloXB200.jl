@@ -526,4 +526,87 @@ function join_logdos(pieces::Vector{Vector{Float64}}, windows::Vector{UnitRange{
     return out
 end
 
+# ----------------------------------------------------------------------------------------------
+# 7. General topologies: IsingGraph / IsingMatrix with fields (SpinSystems/src/ising.jl:86-417) on the device.
+#    Built from the reference's own objects: `DeviceIsingGraph(ctx, sys_cpu)` takes the neighbour lists
+#    (`sys.nbrs`, ascending) or the sparse matrix (`J.colptr / rowval / nzval`; a symmetric CSC is its own CSR).
+#    sweep! visits the colour classes of a greedy first-fit colouring in site order; couplings are Float64, so the
+#    acceptance is evaluated on the device from (rule, beta) with the reference's own expression.
+# ----------------------------------------------------------------------------------------------
+mutable struct DeviceIsingGraph <: SpinSystems.AbstractIsing
+    h::Ptr{Cvoid}
+    n::Int
+    nchains::Int
+    rule_key::Any
+end
+
+function _graph_create(ctx::DeviceCtx, rowptr::Vector{Int64}, col::Vector{Int64}, val, J, hmode::Integer, hs, hv, nchains)
+    out = Ref{Ptr{Cvoid}}()
+    n = length(rowptr) - 1
+    GC.@preserve rowptr col val hv check(ccall((:mcx_graph_create, libmcx), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Float64, Int32, Float64, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, n, rowptr, col, val === nothing ? C_NULL : pointer(val), Float64(J), hmode, Float64(hs),
+        hv === nothing ? C_NULL : pointer(hv), nchains, out))
+    sys = DeviceIsingGraph(out[], n, nchains, nothing)
+    finalizer(s -> ccall((:mcx_graph_destroy, libmcx), Int32, (Ptr{Cvoid},), s.h), sys)
+    return sys
+end
+
+_field(sys) = hasproperty(sys, :h) ? (sys.h isa AbstractVector ? (2, 0.0, Float64.(sys.h)) : (1, Float64(sys.h), nothing)) : (0, 0.0, nothing)
+
+function DeviceIsingGraph(ctx::DeviceCtx, sys::SpinSystems.IsingGraph; nchains::Integer=1)
+    rowptr = Int64[0]; col = Int64[]
+    for nb in sys.nbrs                                   # ising.jl:120: collect(Graphs.neighbors(graph, i)), ascending
+        append!(col, Int64.(nb) .- 1); push!(rowptr, length(col))
+    end
+    hmode, hs, hv = _field(sys)
+    return _graph_create(ctx, rowptr, col, nothing, sys.J, hmode, hs, hv, nchains)
+end
+
+function DeviceIsingGraph(ctx::DeviceCtx, sys::SpinSystems.IsingMatrix; nchains::Integer=1)
+    J = sys.J                                            # symmetric SparseMatrixCSC (ising.jl:250-262): column i = row i
+    hmode, hs, hv = _field(sys)
+    return _graph_create(ctx, Int64.(J.colptr) .- 1, Int64.(J.rowval) .- 1, Float64.(J.nzval), 0.0, hmode, hs, hv, nchains)
+end
+
+function sweep!(sys::DeviceIsingGraph, alg, nsweeps::Integer=1)
+    rng = alg.rng::PhiloxRNG
+    β = alg isa MonteCarloX.HeatBath ? alg.β : MonteCarloX.ensemble(alg).beta
+    key = (typeof(alg), β, rng.seed, rng.chain)
+    if key != sys.rule_key
+        s = Ref{UInt64}(); n = Ref{UInt64}()
+        check(ccall((:mcx_graph_get_rng, libmcx), Int32, (Ptr{Cvoid}, Ref{UInt64}, Ref{UInt64}), sys.h, s, n))
+        check(ccall((:mcx_graph_set_rule, libmcx), Int32, (Ptr{Cvoid}, Int32, Float64), sys.h, rule_code(alg), β))
+        check(ccall((:mcx_graph_set_rng, libmcx), Int32, (Ptr{Cvoid}, UInt64, UInt64, UInt32), sys.h, rng.seed, n[], rng.chain))
+        sys.rule_key = key
+    end
+    check(ccall((:mcx_graph_sweep, libmcx), Int32, (Ptr{Cvoid}, Int64), sys.h, nsweeps))
+    alg.steps += nsweeps * sys.n * sys.nchains
+    return nothing
+end
+
+function SpinSystems.energy(sys::DeviceIsingGraph; full::Bool=false)
+    e = Vector{Float64}(undef, sys.nchains)
+    check(ccall((:mcx_graph_energies, libmcx), Int32, (Ptr{Cvoid}, Ptr{Float64}), sys.h, e))
+    return sys.nchains == 1 ? e[1] : e
+end
+
+# ----------------------------------------------------------------------------------------------
+# 8. integrated_autocorrelation_time (src/measurements/autocorrelations.jl:28-65) of a series measured on the
+#    device: `sweep_series!` leaves the snapshots there, `tau_int` reduces them to one Float64 per chain in place.
+# ----------------------------------------------------------------------------------------------
+function sweep_series!(sys::DeviceIsing, nmeasure::Integer, interval::Integer=1)
+    out = Array{Int64}(undef, 4, sys.nchains, nmeasure)           # {pair, spin, spin2, accepted} per chain and snapshot
+    check(ccall((:mcx_sweep_series, libmcx), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}), sys.h, nmeasure, interval, out))
+    return out
+end
+
+function tau_int(sys::DeviceIsing, nmeasure::Integer; observable::Symbol=:energy, max_lag::Integer=0, c::Real=5.0)
+    code = observable === :energy ? 0 : observable === :magnetization ? 1 : 2
+    tau = Vector{Float64}(undef, sys.nchains)
+    check(ccall((:mcx_series_tau_int, libmcx), Int32, (Ptr{Cvoid}, Int64, Int32, Int64, Float64, Ptr{Float64}),
+                sys.h, nmeasure, code, max_lag, c, tau))
+    return tau
+end
+
 end # module

@@ -235,6 +235,7 @@ bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps)
     if (knobs().variant >= 0 || knobs().rows_per_strip >= 0 || knobs().force_generic > 0) return false;
     if (want < 0 && (nsweeps < 4 || knobs().groups == 0)) return false;
     const bool single = lat->nchains == 1;                      // one mid-size lattice: see the policy below
+    if (want < 0 && single && knobs().bands >= 0) return false; // MCX_BANDS set: the caller chose (or excluded) the band launches
     mcx_ctx *ctx = lat->ctx;
     const LatView &L = lat->view;
     const int nseg = L.half >> 4;

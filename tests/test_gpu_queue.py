@@ -54,7 +54,7 @@ def test_single_mid_size_lattice_takes_the_queue_by_default(m, dims, rows, monke
     monkeypatch.setenv("MCX_RESIDENT", "0")
     for rule, track in ((0, False), (2, True)):
         monkeypatch.setenv("MCX_QUEUE", "0")
-        monkeypatch.setenv("MCX_BANDS", "0")
+        monkeypatch.setenv("MCX_BANDS", "0")                  # one launch per half-sweep
         ref, l_ref = _run(m, dims, 1, rule, track, 6, 5, 1)
         monkeypatch.delenv("MCX_QUEUE", raising=False)
         monkeypatch.delenv("MCX_BANDS", raising=False)
