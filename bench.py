@@ -241,7 +241,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     numa = numa_bind(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a mismatched collective must fail the run in minutes, not hold the box for NCCL's default ten
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     # an explicit (non-default) stream shared by torch and libmcx_b200, so that torch.cuda.Event
     # brackets exactly the kernels the library launches
     stream = torch.cuda.Stream()
@@ -274,7 +276,7 @@ def run_ours(args):
         elif args.config == "c4":
             leg = bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, cpu=not args.no_cpu)
         else:
-            leg = bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=16, walkers=64, cpu=not args.no_cpu, read_tables=True)
+            leg = bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=32, walkers=64, cpu=not args.no_cpu, read_tables=True)   # 2048 walkers per GPU
         leg.update({"n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
                     "scaling": "strong" if args.config in ("c3", "c4") else "weak", "vs_baseline": None,
                     "dtype": "u8" if args.config in ("c1", "c3") else "f64", "data": "synthetic", "clocks": None})
@@ -454,12 +456,11 @@ def run_ours(args):
         for key, fn in (("c1", lambda: bench_c1(m, ctx, stream, args, cpu=cpu and rank == 0)),
                         ("c4", lambda: bench_c4(m, ctx, stream, world, rank, barrier, max_over_ranks, iterations=2, therm=1, record=4, cpu=cpu)),
                         ("c5", lambda: bench_c5(m, world, rank, barrier, max_over_ranks, windows_per_gpu=16, walkers=32, cpu=cpu))):
-            if key == "c1" and rank != 0:
-                continue
-            try:
-                extras[key] = fn()
-            except Exception as e:
-                extras[key] = {"error": repr(e)}
+            if not (key == "c1" and rank != 0):          # c1 is one small chain: rank 0 only; every rank meets at the barrier
+                try:
+                    extras[key] = fn()
+                except Exception as e:
+                    extras[key] = {"error": repr(e)}
             barrier()
         out["configs"] = extras
 

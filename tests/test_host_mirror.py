@@ -188,3 +188,24 @@ def test_philox_rng_many_draws_do_not_alias_other_streams():
     assert rng.tag == 0 and all(0.0 <= u < 1.0 for u in first)
     again = m.PhiloxRNG(5, 1).position(0, 3, 17)
     assert [again.rand() for _ in range(300)] == first
+
+
+def test_graph_host_helpers():
+    """graph_systems.py host side: Graphs.SimpleGraphs.grid numbering and the symmetric CSR a SimpleGraph / a sparse J gives"""
+    import numpy as np
+    import mcx_b200 as m
+    from mcx_b200.graph_systems import _csr_from_edges
+    e, n = m.grid_graph([3, 2], periodic=False)          # sites i = x + 3 y
+    assert n == 6 and sorted(map(tuple, e.tolist())) == [(0, 1), (0, 3), (1, 2), (1, 4), (2, 5), (3, 4), (4, 5)]
+    e, n = m.grid_graph([4, 4], periodic=True)
+    assert len(e) == 32 and n == 16                      # 2 N edges on a periodic square lattice
+    e2, _ = m.grid_graph([2, 2], periodic=True)
+    assert len(e2) == 4                                  # a SimpleGraph keeps one edge per pair (ne(grid([2, 2])) == 4)
+    rowptr, col, val = _csr_from_edges([[0, 1], [1, 2], [2, 3], [3, 0]], 4, [1.0, 2.0, 3.0, 4.0])
+    assert rowptr.tolist() == [0, 2, 4, 6, 8] and col.tolist() == [1, 3, 0, 2, 1, 3, 0, 2]
+    assert val.tolist() == [1.0, 4.0, 1.0, 2.0, 2.0, 3.0, 4.0, 3.0]          # ascending neighbours, J_ij == J_ji
+    import pytest
+    with pytest.raises(AssertionError):
+        _csr_from_edges([[0, 1], [1, 2]], 3, [1.0])                          # ne(graph) != length(J) (ising.jl:384)
+    with pytest.raises(IndexError):
+        _csr_from_edges([[0, 5]], 3)
