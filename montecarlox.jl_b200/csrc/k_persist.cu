@@ -636,6 +636,11 @@ bool launch_pt_rounds_persistent(mcx_pt *pt, int64_t nrounds, int64_t S)
     if (lat->storage != MCX_STORAGE_INT8 || lat->slab || !lat->fast2d || lat->model != MCX_ISING) return false;
     if (knobs().variant >= 0 || knobs().rows_per_strip >= 0 || knobs().force_generic > 0) return false;
     if (want < 0 && S > 16) return false;
+    // Across ranks the rounds queued by the host are faster: measured on 4 B200s with 64 replicas of 1024 x 1024 per rank
+    // (profiles/r02_pt_multi_gpu.md), exchange after every sweep 13084 PT sweeps/s against 10659 through this launch, every
+    // 200 sweeps 21187 against 17663 -- one warp closing the round behind two system-scope fences, with every other warp
+    // of the rank parked, costs more than the publish / exchange kernels it replaces.  MCX_PT_PERSIST=1 still forces it.
+    if (want < 0 && pt->peers && pt->nranks > 1) return false;
     mcx_ctx *ctx = lat->ctx;
     // short rounds: keep the sums current per flip; long rounds: sweep without bookkeeping, one recompute phase per round
     const bool track = S < 3, recompute = !track;
