@@ -31,6 +31,10 @@ thread_local LaunchRange g_launch_range;
 namespace {
 
 constexpr int kThreads = 128;
+#ifndef MCX_MINB
+#define MCX_MINB 6
+#endif
+constexpr int kMinBlocks = MCX_MINB;   // CTAs per SM the register budget is held to (80 registers)
 
 // Cross-GPU ordering of a slab's half-sweep t (k_slab.cu): its boundary strips may start once both
 // neighbours have finished the boundary strips of their half-sweep t - 1 ...
@@ -79,8 +83,41 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #endif
 
-template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH, bool FULL, bool SLAB>
-__global__ void __launch_bounds__(kThreads, MINB)
+// The rows of a strip that update_row_fast() left undecided (bit r of `ties`: row row0 + r), redone one by one from global
+// memory with the full 32-bit draws.  The other colour plane does not change during a half-sweep and a left-over row was
+// not stored, so the row and its neighbours are still what the fast path saw.  Returns what the rows add to the packed
+// accumulators (flips, s, n, sn).  Everything comes by value: a reference to the kernel's LatView or Acc would put them
+// into local memory for the whole kernel.
+template <int COLOUR, bool HEATBATH, bool TRACK>
+__device__ __noinline__ uint4 settle_rows(uint8_t *tgt, const uint8_t *oth, const uint8_t *oth_up, const uint8_t *oth_dn,
+                                          const int half, const int Ly, const int row_offset, uint32_t ties, const int row0, const int R,
+                                          const int col, const int colL, const int colR, const uint32_t t_lo, const uint32_t c2,
+                                          const uint32_t c2lo, const uint32_t chain_id, const uint32_t seed_lo,
+                                          const uint32_t seed_hi, const uint32_t *s_thi, const uint32_t *s_tlo)
+{
+    const size_t h = (uint32_t)half;
+    Acc acc;
+    while (ties) {
+        const int p = __ffs((int)ties) - 1;                      // the loop shifted the flags in, two per trip, row a above row b
+        ties &= ties - 1;
+        const int r = R - 2 - (p & ~1) + (~p & 1);
+        const int row = row0 + r;
+        const int parity = (r & 1) ? (COLOUR ^ 1) : COLOUR;      // row0 is even
+        const uint8_t *pu = row == 0 ? oth_up + (size_t)(Ly - 1) * h : oth + (size_t)(row - 1) * h;
+        const uint8_t *pd = row + 1 == Ly ? oth_dn : oth + (size_t)(row + 1) * h;
+        const uint8_t *pc = oth + (size_t)row * h;
+        uint8_t *pt = tgt + (size_t)row * h + col;
+        const uint32_t side = pc[parity == 0 ? colL : colR];
+        const uint32_t blk = (uint32_t)(((int64_t)(row + row_offset) * half + col) >> 3);
+        const uint4 ex = row_settle<HEATBATH, TRACK>(parity, ldg128(pt), ldg128(pu + col), ldg128(pc + col), ldg128(pd + col), side, blk,
+                                                     t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_thi, s_tlo, acc);
+        *reinterpret_cast<uint4 *>(pt) = ex;
+    }
+    return make_uint4(acc.flips, (uint32_t)acc.s, (uint32_t)acc.n, (uint32_t)acc.sn);
+}
+
+template <int COLOUR, bool HEATBATH, bool TRACK, bool FULL, bool SLAB>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
           const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
           uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
@@ -90,6 +127,7 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
     int cur_label = -1;
 
     const int half = L.half;
+    const size_t h = (uint32_t)half;                              // row pitch, zero-extended once
     const int nseg = half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
     const int lane = threadIdx.x & 31;
@@ -109,19 +147,8 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         const int chain = item / blocks_per_chain;
         const int label = labels[chain];
         if (label != cur_label) {
-            // pair table of this chain's ensemble: entry (i1, i0) = t15[i0] | t15[i1] << 16 with
-            // t15 = min(T >> 17, 0x7fff) (T = 2^32, "always", ties on h15 == 0x7fff and is settled exactly)
             __syncthreads();
-            if (threadIdx.x < kTableLen) {
-                s_thi[threadIdx.x] = thi_g[label * kTableLen + threadIdx.x];
-                s_tlo[threadIdx.x] = tlo_g[label * kTableLen + threadIdx.x];
-            }
-            if (threadIdx.x < kTableLen * kTableLen) {
-                const int i1 = threadIdx.x / kTableLen, i0 = threadIdx.x - i1 * kTableLen;
-                const uint32_t a = min(thi_g[label * kTableLen + i0] >> 1, 0x7fffu);
-                const uint32_t b = min(thi_g[label * kTableLen + i1] >> 1, 0x7fffu);
-                s_pair[i1 * kPairRowWords + i0] = a | (b << 16);
-            }
+            load_pair_table(s_pair, s_thi, s_tlo, thi_g, tlo_g, label);
             __syncthreads();
             cur_label = label;
         }
@@ -155,58 +182,44 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
         // even rows of this strip have parity COLOUR, odd rows COLOUR ^ 1 (row0 is even)
         const bool edgeA = COLOUR == 0 ? loadL : loadR;
         const bool edgeB = COLOUR == 0 ? loadR : loadL;
-        const int colA = COLOUR == 0 ? colL : colR;
-        const int colB = COLOUR == 0 ? colR : colL;
+        // the edge bytes relative to the thread's own segment: row a, and row b one pitch further
+        const ptrdiff_t offA = (ptrdiff_t)((COLOUR == 0 ? colL : colR) - col);
+        const ptrdiff_t offB = (ptrdiff_t)((COLOUR == 0 ? colR : colL) - col) + (ptrdiff_t)h;
 
         // the row above row 0 / below row Ly - 1: the own plane (periodic) or, for a slab, the neighbours' planes
         const uint8_t *oth_dn = SLAB ? plane_ptr_of(L.dn_planes, L, chain, COLOUR ^ 1) : oth;
         const uint8_t *oth_up = SLAB ? plane_ptr_of(L.up_planes, L, chain, COLOUR ^ 1) : oth;
         const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
-        const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, current even row
-        uint8_t *pt = tgt + (int64_t)row0 * half + col;           // target plane, current even row
-        uint4 U = ldg128((SLAB && row0 == 0 ? oth_up : oth) + (int64_t)rowU * half + col);
-        uint4 C = ldg128(po + col);
-        uint4 D, Ta, Tb;
-        uint32_t sideA = 0, sideB = 0;
-        if (PREFETCH) {
-            D = ldg128(po + half + col);
-            Ta = ldg128(pt); Tb = ldg128(pt + half);
-            if (edgeA) sideA = po[colA];
-            if (edgeB) sideB = po[half + colB];
-        }
+        // Per-thread row pointers (segment included), advanced by two pitches per trip: every address of a trip is one of
+        // them, or one of them plus the pitch.
+        const uint8_t *po = oth + (size_t)row0 * h + col;         // other plane, current even row
+        uint8_t *pt = tgt + (size_t)row0 * h + col;               // target plane, current even row
+        uint4 U = ldg128((SLAB && row0 == 0 ? oth_up : oth) + (size_t)rowU * h + col);
+        uint4 C = ldg128(po);
+        // the other-plane row below the strip's last row wraps only at the very last row of the lattice
+        const bool wraps = row0 + R == L.Ly;
         uint32_t blk = (uint32_t)(((int64_t)(row0 + (SLAB ? L.row_offset : 0)) * half + col) >> 3);
-        const uint32_t blk_step = (uint32_t)(half >> 3);
+        const uint32_t blk_step = (uint32_t)(half >> 3), blk_step2 = 2 * blk_step;
+        const size_t h2 = 2 * h;
+        const PhiloxHead H = philox_head(t_lo, c2, chain_id, seed_lo, seed_hi);
+        const uint32_t pair_addr = (uint32_t)__cvta_generic_to_shared(s_pair);
         Acc acc;
+        uint32_t ties = 0;                                        // rows of the strip left to settle_rows() (R <= 32)
 
-#ifdef MCX_OPT_UNROLL2
-#pragma unroll 2
-#else
+        // One basic block per trip: a row whose 15-bit comparison leaves a site undecided (2^-15 per site) is not stored
+        // and settled after the loop, so the scheduler is free to run the Philox rounds of one row under the decision
+        // arithmetic of the other.
 #pragma unroll 1
-#endif
         for (int r = 0; r < R; r += 2) {
-            const int row = row0 + r;
-            // E = other row below the odd row; wraps only at the very last row of the lattice
-            const uint8_t *pe = (row + 2 == L.Ly) ? oth_dn : po + 2 * (int64_t)half;
-            const uint4 E = ldg128(pe + col);
-            uint4 Dn, Tan, Tbn;
-            uint32_t sideAn = 0, sideBn = 0;
-            if (PREFETCH) {
-                // prefetch the next trip's rows (the window slides by two rows)
-                Dn = D; Tan = Ta; Tbn = Tb;
-                if (r + 2 < R) {
-                    Dn = ldg128(po + 3 * (int64_t)half + col);
-                    Tan = ldg128(pt + 2 * (int64_t)half);
-                    Tbn = ldg128(pt + 3 * (int64_t)half);
-                    if (edgeA) sideAn = po[2 * (int64_t)half + colA];
-                    if (edgeB) sideBn = po[3 * (int64_t)half + colB];
-                }
-            } else {
-                // this trip's rows; their latency is covered by the Philox rounds below
-                D = ldg128(po + half + col);
-                Ta = ldg128(pt); Tb = ldg128(pt + half);
-                if (edgeA) sideA = po[colA];
-                if (edgeB) sideB = po[half + colB];
-            }
+            // this trip's rows, loads first: their latency is covered by the Philox rounds below
+            const uint8_t *pe = po + h2;
+            if (wraps && r + 2 == R) pe = oth_dn + col;
+            const uint4 E = ldg128(pe);
+            const uint4 D = ldg128(po + h);
+            const uint4 Ta = ldg128(pt), Tb = ldg128(pt + h);
+            uint32_t sideA = 0, sideB = 0;
+            if (edgeA) sideA = po[offA];
+            if (edgeB) sideB = po[offB];
             uint32_t sA, sB;
             if (COLOUR == 0) {
                 sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
@@ -217,17 +230,21 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             }
             if (edgeA) sA = sideA;
             if (edgeB) sB = sideB;
-            const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
-                                                                 seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            // finish (and store) row a before starting row b: fewer live registers, measured +4 %
-            if (active) *reinterpret_cast<uint4 *>(pt) = Na;
-            asm volatile("" ::: "memory");
-            const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
-                                                                     seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            if (active) *reinterpret_cast<uint4 *>(pt + half) = Nb;
+            bool tieA, tieB;
+            const uint4 Na = update_row_fast<COLOUR, HEATBATH, TRACK>(philox_tail(H, blk), philox_tail(H, blk + 1), Ta, U, C, D, sA,
+                                                                      pair_addr, acc, active, tieA);
+            if (active && !tieA) *reinterpret_cast<uint4 *>(pt) = Na;
+            const uint4 Nb = update_row_fast<COLOUR ^ 1, HEATBATH, TRACK>(philox_tail(H, blk + blk_step), philox_tail(H, blk + blk_step + 1),
+                                                                          Tb, C, D, E, sB, pair_addr, acc, active, tieB);
+            if (active && !tieB) *reinterpret_cast<uint4 *>(pt + h) = Nb;
+            ties = (ties << 2) | (tieA ? 2u : 0u) | (tieB ? 1u : 0u);   // trip k of K: bits 2 (K - 1 - k) + 1 (row a), + 0 (row b)
             U = D; C = E;
-            if (PREFETCH) { D = Dn; Ta = Tan; Tb = Tbn; sideA = sideAn; sideB = sideBn; }
-            po += 2 * (int64_t)half; pt += 2 * (int64_t)half; blk += 2 * blk_step;
+            po = pe; pt += h2; blk += blk_step2;
+        }
+        if (active && ties) {
+            const uint4 d = settle_rows<COLOUR, HEATBATH, TRACK>(tgt, oth, oth_up, oth_dn, half, L.Ly, SLAB ? L.row_offset : 0, ties, row0, R, col,
+                                                                 colL, colR, t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_thi, s_tlo);
+            acc.flips += d.x; acc.s += (int32_t)d.y; acc.n += (int32_t)d.z; acc.sn += (int32_t)d.w;
         }
 
         // per-chain sums: dspin = 2 - 4 s, dpair = -8 s nup + 16 s + 4 nup - 8 per changed site
@@ -401,7 +418,7 @@ int pick_rows_per_strip(int Ly, int want);
 int auto_rows_per_strip(const mcx_lattice *lat)
 {
     const int forced = knobs().rows_per_strip > 0 ? knobs().rows_per_strip : 0;
-    if (forced > 0) return pick_rows_per_strip(lat->view.Ly, forced);
+    if (forced > 0) return pick_rows_per_strip(lat->view.Ly, forced > 32 ? 32 : forced);   // the kernel flags left-over rows in 32 bits
     const int64_t nseg = lat->view.half >> 4;
     const int64_t ctas = (int64_t)lat->ctx->sm_count * 6;
     int R = 16;
@@ -423,8 +440,8 @@ int pick_rows_per_strip(int Ly, int want)
 
 
 
-template <int COLOUR, bool HEATBATH, bool TRACK, int MINB, bool PREFETCH>
-void launch_v(mcx_lattice *lat, uint64_t t)
+template <int COLOUR, bool HEATBATH, bool TRACK>
+void launch_t(mcx_lattice *lat, uint64_t t)
 {
     // a chain sub-range is the same launch on shifted base pointers: every per-chain array is indexed from them
     LatView L = lat->view;
@@ -461,16 +478,13 @@ void launch_v(mcx_lattice *lat, uint64_t t)
     const int nitems = (int)((int64_t)blocks_per_chain * nch);
     // the shipped variant also exists with the idle-lane predicate compiled out (+2.8 %, r01_tune_allactive.log)
     // and with the halo rows taken from the neighbour slabs (k_slab.cu)
-    constexpr bool kHasFull = MINB == 6 && !PREFETCH;
-    const bool slab = kHasFull && (lat->slab != nullptr || band);
-    const bool full = kHasFull && G % kThreads == 0 && knobs().full != 0;
-    auto kern = slab ? (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, kHasFull>
-                             : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, kHasFull>)
-                     : (full ? k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, kHasFull, false>
-                             : k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>);
+    const bool slab = lat->slab != nullptr || band;
+    const bool full = G % kThreads == 0 && knobs().full != 0;
+    auto kern = slab ? (full ? k_ising2d<COLOUR, HEATBATH, TRACK, true, true> : k_ising2d<COLOUR, HEATBATH, TRACK, false, true>)
+                     : (full ? k_ising2d<COLOUR, HEATBATH, TRACK, true, false> : k_ising2d<COLOUR, HEATBATH, TRACK, false, false>);
     static thread_local int resident = 0;
     if (!resident) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, MINB, PREFETCH, false, false>, kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_ising2d<COLOUR, HEATBATH, TRACK, false, false>, kThreads, 0);
         if (resident < 1) resident = 1;
     }
     const int ctas_per_sm = knobs().ctas_per_sm >= 0 ? knobs().ctas_per_sm : resident;
@@ -482,19 +496,6 @@ void launch_v(mcx_lattice *lat, uint64_t t)
                                        (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain + (uint32_t)c0, R,
                                        nstrips, blocks_per_chain, nitems);
     lat->ctx->launches++;
-}
-
-// MCX_VARIANT (tuning hook; every variant produces the same trajectories): default = 6 CTAs/SM with the
-// trip's loads issued before the Philox rounds; 0 = 5 CTAs/SM with a one-trip register prefetch.  (A cp.async staging
-// ring was measured slower -- latency is not the limiter, profiles/r01_tune_variants.log -- and is no longer built.)
-template <int COLOUR, bool HEATBATH, bool TRACK>
-void launch_t(mcx_lattice *lat, uint64_t t)
-{
-    const int variant = lat->slab || knobs().variant < 0 ? 3 : knobs().variant;
-    switch (variant) {
-    case 0: launch_v<COLOUR, HEATBATH, TRACK, 5, true>(lat, t); break;
-    default: launch_v<COLOUR, HEATBATH, TRACK, 6, false>(lat, t); break;
-    }
 }
 
 template <int COLOUR>
@@ -689,7 +690,7 @@ bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
     // small lattices: a chain yields fewer than one CTA of 16-byte segments x strips, so most lanes of
     // this kernel would idle; the rows-of-8 kernel (8 sites per thread) fills the machine instead
     {
-        const int R = pick_rows_per_strip(lat->view.Ly, knobs().rows_per_strip >= 0 ? knobs().rows_per_strip : 16);   // small-lattice test uses 16
+        const int R = pick_rows_per_strip(lat->view.Ly, knobs().rows_per_strip >= 0 ? (knobs().rows_per_strip > 32 ? 32 : knobs().rows_per_strip) : 16);   // small-lattice test uses 16
         const int64_t G = (int64_t)(lat->view.Ly / R) * (lat->view.half >> 4);
         if (G < 96 && !lat->slab && knobs().variant < 0 && knobs().rows_per_strip < 0) return false;
     }

@@ -43,6 +43,58 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
+// The same block, split by what its inputs depend on.  All lanes of a work item share c1, c2, c3 and the key and differ
+// in c0 only, and for two rounds half of the state does not see c0 yet: PhiloxHead holds those words, folded with the
+// round keys they are xored with, and the keys of the later rounds, so that a kernel forms them once per item (they live
+// in uniform registers) and a block costs 18 multiplies and 19 xors per lane.  philox_tail(philox_head(c1, c2, c3, k0, k1), c0)
+// == philox4x32_10(c0, c1, c2, c3, k0, k1).
+struct PhiloxHead {
+    uint32_t x1, x2, x3, x4;   // c3 ^ K1[0];  lo(M1 c2) ^ K0[1];  hi(M0 a) ^ K1[1];  lo(M0 a) ^ K1[2], a = hi(M1 c2) ^ c1 ^ K0[0]
+    uint32_t k0[8], k1[7];     // K0[2..9], K1[3..9]
+};
+
+__host__ __device__ __forceinline__ void mul_wide(uint32_t m, uint32_t c, uint32_t &hi, uint32_t &lo)
+{
+    const uint64_t p = (uint64_t)m * c;                        // one IMAD.WIDE.U32
+    hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+}
+
+__host__ __device__ __forceinline__ PhiloxHead philox_head(uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    PhiloxHead H;
+    uint32_t h1, l1, h0, l0;
+    mul_wide(0xCD9E8D57u, c2, h1, l1);
+    const uint32_t a = h1 ^ c1 ^ k0;
+    mul_wide(0xD2511F53u, a, h0, l0);
+    H.x1 = c3 ^ k1;
+    H.x2 = l1 ^ (k0 + 0x9E3779B9u);
+    H.x3 = h0 ^ (k1 + 0xBB67AE85u);
+    H.x4 = l0 ^ (k1 + 2u * 0xBB67AE85u);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) H.k0[r] = k0 + (uint32_t)(r + 2) * 0x9E3779B9u;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) H.k1[r] = k1 + (uint32_t)(r + 3) * 0xBB67AE85u;
+    return H;
+}
+
+__host__ __device__ __forceinline__ Philox4 philox_tail(const PhiloxHead &H, uint32_t c0)
+{
+    uint32_t h0, l0, h1, l1;
+    mul_wide(0xD2511F53u, c0, h0, l0);                         // round 1: c2' = h0 ^ x1, c3' = l0
+    mul_wide(0xCD9E8D57u, h0 ^ H.x1, h1, l1);                  // round 2: c0'' = h1 ^ x2, c1'' = l1, c2'' = l0 ^ x3, c3'' = lo(M0 a)
+    uint32_t c0_ = h1 ^ H.x2, c1_ = l1, c2_ = l0 ^ H.x3, c3_;
+    mul_wide(0xD2511F53u, c0_, h0, l0);                        // round 3
+    mul_wide(0xCD9E8D57u, c2_, h1, l1);
+    c0_ = h1 ^ c1_ ^ H.k0[0]; c1_ = l1; c2_ = h0 ^ H.x4; c3_ = l0;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {                              // rounds 4..10
+        mul_wide(0xD2511F53u, c0_, h0, l0);
+        mul_wide(0xCD9E8D57u, c2_, h1, l1);
+        c0_ = h1 ^ c1_ ^ H.k0[r]; c1_ = l1; c2_ = h0 ^ c3_ ^ H.k1[r - 1]; c3_ = l0;
+    }
+    return Philox4{c0_, c1_, c2_, c3_};
+}
+
 // counter word 2 of the stream layout
 __host__ __device__ __forceinline__ uint32_t ctr_word2(uint64_t t, uint32_t plane, uint32_t tag)
 {

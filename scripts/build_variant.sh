@@ -10,4 +10,4 @@ for f in mcx_api k_generic k_ising2d k_resident k_slab k_bc2d k_ising3d k_rows8 
 done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/libmcx_b200_$name.so $out/*.o
-grep -A2 "k_ising2dILi0ELb0ELb0ELi6ELb0E" $out/k_ising2d.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
+grep -A2 "k_ising2dILi0ELb0ELb0ELb1ELb1E" $out/k_ising2d.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $name"
