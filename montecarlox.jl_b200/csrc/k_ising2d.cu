@@ -32,9 +32,9 @@ namespace {
 
 constexpr int kThreads = 128;
 #ifndef MCX_MINB
-#define MCX_MINB 6
+#define MCX_MINB 8
 #endif
-constexpr int kMinBlocks = MCX_MINB;   // CTAs per SM the register budget is held to (80 registers)
+constexpr int kMinBlocks = MCX_MINB;   // CTAs per SM the register budget is held to: 8 -> 64 registers (6: 1571, 7: 1554, 8: 1634, 9: 1581, 10: 1530 attempts/ns on one box)
 
 // Cross-GPU ordering of a slab's half-sweep t (k_slab.cu): its boundary strips may start once both
 // neighbours have finished the boundary strips of their half-sweep t - 1 ...
@@ -152,11 +152,12 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
             __syncthreads();
             cur_label = label;
         }
-        const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
-        const bool active = FULL ? true : g0 < G;                 // FULL: G % kThreads == 0, no idle lanes
-        const int64_t g = active ? g0 : G - 1;
-        int strip = (int)(g / nseg);
-        const int seg = (int)(g - (int64_t)strip * nseg);
+        // thread-items of a chain are numbered in 32 bits (the launcher checks G < 2^31): one 32-bit division per item
+        const uint32_t g0 = (uint32_t)(item - chain * blocks_per_chain) * kThreads + threadIdx.x;
+        const bool active = FULL ? true : g0 < (uint32_t)G;       // FULL: G % kThreads == 0, no idle lanes
+        const uint32_t g = active ? g0 : (uint32_t)G - 1;
+        int strip = (int)(g / (uint32_t)nseg);
+        const int seg = (int)(g - (uint32_t)strip * (uint32_t)nseg);
         // Slab of a taller lattice: the two strips that touch the neighbour slabs come first (strip order
         // rotated by one), so that their rows are final -- and the neighbours told so -- while the interior
         // is still being swept.  Only the CTAs holding them wait for the neighbours' previous half-sweep.
@@ -474,6 +475,7 @@ void launch_t(mcx_lattice *lat, uint64_t t)
     const int nstrips = L.Ly / R;
     const int nseg = L.half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
+    // G < 2^31 always: 2^31 thread-items of 16 x R >= 32 bytes per plane are beyond the memory of the device
     const int blocks_per_chain = (int)((G + kThreads - 1) / kThreads);
     const int nitems = (int)((int64_t)blocks_per_chain * nch);
     // the shipped variant also exists with the idle-lane predicate compiled out (+2.8 %, r01_tune_allactive.log)
@@ -641,7 +643,13 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
     const int Ly = d3 ? lat->view.Lz : lat->view.Ly;      // the banded dimension
     const bool forced = bands_env > 1;
     int bands = forced ? (bands_env > 16 ? 16 : bands_env) : 8;
-    const int R = 16;
+    int R = knobs().band_rows > 0 ? knobs().band_rows : 16;            // MCX_BAND_ROWS: tuning hook
+    if (!d3 && !forced && knobs().band_rows <= 0 && Ly % (32 * 16) == 0 &&
+        ((int64_t)(Ly / 16 / 32) * (lat->view.half >> 4) + kThreads - 1) / kThreads >= 100) {
+        // big lattices at 8 CTAs/SM: 16 bands of 32-row strips (a CTA's set-up is spread over twice the rows, and twice
+        // the launches fill each other's tails): 1643 against 1601 attempts/ns at L = 16384 (profiles/r02_launch_shapes.md)
+        bands = 16; R = 32;
+    }
     if (d3) {
         // a band must leave its neighbours a plane of their own: at least two planes per band
         if (Ly % bands != 0 || Ly / bands < 2 || lat->view.Ly % 2 != 0) return false;

@@ -61,7 +61,7 @@ void knobs_refresh()
     k.full = knob("MCX_FULL"); k.groups = knob("MCX_GROUPS"); k.bands = knob("MCX_BANDS"); k.bc2d = knob("MCX_BC2D");
     k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
     k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
-    k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
+    k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.band_rows = knob("MCX_BAND_ROWS"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
     k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST"); k.flat_window = knob("MCX_FLAT_WINDOW");
     g_knobs_ready = true;
 }

@@ -116,6 +116,7 @@ struct Knobs {
     int queue_grid;   // MCX_QUEUE_GRID: CTAs of the persistent rounds kernel (tuning hook; default: every resident slot)
     int pt_persist;   // MCX_PT_PERSIST: 1 = mcx_pt_run as one persistent launch whenever the shape allows, 0 = never
     int flat_window;  // MCX_FLAT_WINDOW: 0 = flat-histogram chains read the log-weight table from global memory (no shared-memory window)
+    int band_rows;    // MCX_BAND_ROWS: strip height of the row-band launches (tuning hook; default 16)
     int wl_spec;      // MCX_WL_SPEC: Wang-Landau attempts decided at once (0 = serial loop, 8, 32; unset = adaptive)
 };
 const Knobs &knobs();
