@@ -20,7 +20,7 @@
 // result is bit-identical to k_sweep_generic and to the oracle.
 //
 // Persistent grid: gridDim.x = SMs x resident CTAs, items handed out round-robin.
-#include "k_row16.cuh"
+#include "k_strip.cuh"
 
 #include <cstdlib>
 
@@ -83,39 +83,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #endif
 
-// The rows of a strip that update_row_fast() left undecided (bit r of `ties`: row row0 + r), redone one by one from global
-// memory with the full 32-bit draws.  The other colour plane does not change during a half-sweep and a left-over row was
-// not stored, so the row and its neighbours are still what the fast path saw.  Returns what the rows add to the packed
-// accumulators (flips, s, n, sn).  Everything comes by value: a reference to the kernel's LatView or Acc would put them
-// into local memory for the whole kernel.
-template <int COLOUR, bool HEATBATH, bool TRACK>
-__device__ __noinline__ uint4 settle_rows(uint8_t *tgt, const uint8_t *oth, const uint8_t *oth_up, const uint8_t *oth_dn,
-                                          const int half, const int Ly, const int row_offset, uint32_t ties, const int row0, const int R,
-                                          const int col, const int colL, const int colR, const uint32_t t_lo, const uint32_t c2,
-                                          const uint32_t c2lo, const uint32_t chain_id, const uint32_t seed_lo,
-                                          const uint32_t seed_hi, const uint32_t *s_thi, const uint32_t *s_tlo)
-{
-    const size_t h = (uint32_t)half;
-    Acc acc;
-    while (ties) {
-        const int p = __ffs((int)ties) - 1;                      // the loop shifted the flags in, two per trip, row a above row b
-        ties &= ties - 1;
-        const int r = R - 2 - (p & ~1) + (~p & 1);
-        const int row = row0 + r;
-        const int parity = (r & 1) ? (COLOUR ^ 1) : COLOUR;      // row0 is even
-        const uint8_t *pu = row == 0 ? oth_up + (size_t)(Ly - 1) * h : oth + (size_t)(row - 1) * h;
-        const uint8_t *pd = row + 1 == Ly ? oth_dn : oth + (size_t)(row + 1) * h;
-        const uint8_t *pc = oth + (size_t)row * h;
-        uint8_t *pt = tgt + (size_t)row * h + col;
-        const uint32_t side = pc[parity == 0 ? colL : colR];
-        const uint32_t blk = (uint32_t)(((int64_t)(row + row_offset) * half + col) >> 3);
-        const uint4 ex = row_settle<HEATBATH, TRACK>(parity, ldg128(pt), ldg128(pu + col), ldg128(pc + col), ldg128(pd + col), side, blk,
-                                                     t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_thi, s_tlo, acc);
-        *reinterpret_cast<uint4 *>(pt) = ex;
-    }
-    return make_uint4(acc.flips, (uint32_t)acc.s, (uint32_t)acc.n, (uint32_t)acc.sn);
-}
-
 template <int COLOUR, bool HEATBATH, bool TRACK, bool FULL, bool SLAB>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
@@ -127,13 +94,9 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
     int cur_label = -1;
 
     const int half = L.half;
-    const size_t h = (uint32_t)half;                              // row pitch, zero-extended once
     const int nseg = half >> 4;
     const int64_t G = (int64_t)nstrips * nseg;
     const int lane = threadIdx.x & 31;
-    const uint32_t t_lo = (uint32_t)t;
-    const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
-    const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
 #ifdef MCX_OPT_TRACE
     const unsigned long long trace_t0 = globaltimer_ns();
     int trace_items = 0;
@@ -170,100 +133,21 @@ k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restr
                 __syncthreads();
             }
         }
-        const int row0 = strip * R;                               // even
-        const uint32_t chain_id = first_chain + (uint32_t)chain;
-
+        // the row above row 0 / below row Ly - 1: the own plane (periodic) or, for a slab or a row band, the neighbours' planes
         uint8_t *tgt = plane_ptr(L, chain, COLOUR);
-        const uint8_t *__restrict__ oth = plane_ptr(L, chain, COLOUR ^ 1);
-        const int col = seg << 4;
-        const int colL = (seg == 0 ? half : col) - 1;             // byte left of the segment (periodic)
-        const int colR = (seg == nseg - 1) ? 0 : col + 16;        // byte right of the segment
-        const bool loadL = (lane == 0) || (seg == 0);
-        const bool loadR = (lane == 31) || (seg == nseg - 1);
-        // even rows of this strip have parity COLOUR, odd rows COLOUR ^ 1 (row0 is even)
-        const bool edgeA = COLOUR == 0 ? loadL : loadR;
-        const bool edgeB = COLOUR == 0 ? loadR : loadL;
-        // the edge bytes relative to the thread's own segment: row a, and row b one pitch further
-        const ptrdiff_t offA = (ptrdiff_t)((COLOUR == 0 ? colL : colR) - col);
-        const ptrdiff_t offB = (ptrdiff_t)((COLOUR == 0 ? colR : colL) - col) + (ptrdiff_t)h;
-
-        // the row above row 0 / below row Ly - 1: the own plane (periodic) or, for a slab, the neighbours' planes
+        const uint8_t *oth = plane_ptr(L, chain, COLOUR ^ 1);
         const uint8_t *oth_dn = SLAB ? plane_ptr_of(L.dn_planes, L, chain, COLOUR ^ 1) : oth;
         const uint8_t *oth_up = SLAB ? plane_ptr_of(L.up_planes, L, chain, COLOUR ^ 1) : oth;
-        const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
-        // Per-thread row pointers (segment included), advanced by two pitches per trip: every address of a trip is one of
-        // them, or one of them plus the pitch.
-        const uint8_t *po = oth + (size_t)row0 * h + col;         // other plane, current even row
-        uint8_t *pt = tgt + (size_t)row0 * h + col;               // target plane, current even row
-        uint4 U = ldg128((SLAB && row0 == 0 ? oth_up : oth) + (size_t)rowU * h + col);
-        uint4 C = ldg128(po);
-        // the other-plane row below the strip's last row wraps only at the very last row of the lattice
-        const bool wraps = row0 + R == L.Ly;
-        uint32_t blk = (uint32_t)(((int64_t)(row0 + (SLAB ? L.row_offset : 0)) * half + col) >> 3);
-        const uint32_t blk_step = (uint32_t)(half >> 3), blk_step2 = 2 * blk_step;
-        const size_t h2 = 2 * h;
-        const PhiloxHead H = philox_head(t_lo, c2, chain_id, seed_lo, seed_hi);
-        const uint32_t pair_addr = (uint32_t)__cvta_generic_to_shared(s_pair);
-        Acc acc;
-        uint32_t ties = 0;                                        // rows of the strip left to settle_rows() (R <= 32)
-
-        // One basic block per trip: a row whose 15-bit comparison leaves a site undecided (2^-15 per site) is not stored
-        // and settled after the loop, so the scheduler is free to run the Philox rounds of one row under the decision
-        // arithmetic of the other.
-#pragma unroll 1
-        for (int r = 0; r < R; r += 2) {
-            // this trip's rows, loads first: their latency is covered by the Philox rounds below
-            const uint8_t *pe = po + h2;
-            if (wraps && r + 2 == R) pe = oth_dn + col;
-            const uint4 E = ldg128(pe);
-            const uint4 D = ldg128(po + h);
-            const uint4 Ta = ldg128(pt), Tb = ldg128(pt + h);
-            uint32_t sideA = 0, sideB = 0;
-            if (edgeA) sideA = po[offA];
-            if (edgeB) sideB = po[offB];
-            uint32_t sA, sB;
-            if (COLOUR == 0) {
-                sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
-                sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
-            } else {
-                sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
-                sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
-            }
-            if (edgeA) sA = sideA;
-            if (edgeB) sB = sideB;
-            bool tieA, tieB;
-            const uint4 Na = update_row_fast<COLOUR, HEATBATH, TRACK>(philox_tail(H, blk), philox_tail(H, blk + 1), Ta, U, C, D, sA,
-                                                                      pair_addr, acc, active, tieA);
-            if (active && !tieA) *reinterpret_cast<uint4 *>(pt) = Na;
-            const uint4 Nb = update_row_fast<COLOUR ^ 1, HEATBATH, TRACK>(philox_tail(H, blk + blk_step), philox_tail(H, blk + blk_step + 1),
-                                                                          Tb, C, D, E, sB, pair_addr, acc, active, tieB);
-            if (active && !tieB) *reinterpret_cast<uint4 *>(pt + h) = Nb;
-            ties = (ties << 2) | (tieA ? 2u : 0u) | (tieB ? 1u : 0u);   // trip k of K: bits 2 (K - 1 - k) + 1 (row a), + 0 (row b)
-            U = D; C = E;
-            po = pe; pt += h2; blk += blk_step2;
-        }
-        if (active && ties) {
-            const uint4 d = settle_rows<COLOUR, HEATBATH, TRACK>(tgt, oth, oth_up, oth_dn, half, L.Ly, SLAB ? L.row_offset : 0, ties, row0, R, col,
-                                                                 colL, colR, t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_thi, s_tlo);
-            acc.flips += d.x; acc.s += (int32_t)d.y; acc.n += (int32_t)d.z; acc.sn += (int32_t)d.w;
-        }
-
-        // per-chain sums: dspin = 2 - 4 s, dpair = -8 s nup + 16 s + 4 nup - 8 per changed site
-        const int nflip = warp_sum((int)acc.flips);
-        int dspin = 0, dpair = 0;
-        if (TRACK) {
-            const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
-            dspin = 2 * nflip - 4 * ss;
-            dpair = -8 * sn + 16 * ss + 4 * nn_ - 8 * nflip;
-        }
-        if (lane == 0) {
-            unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
-            if (nflip) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nflip);
-            if (TRACK) {
-                if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
-                if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
-            }
-        }
+        StripGeom sg;
+        sg.row0 = strip * R; sg.rows = R; sg.col = seg << 4;
+        sg.colL = (seg == 0 ? half : sg.col) - 1;
+        sg.colR = (seg == nseg - 1) ? 0 : sg.col + 16;
+        sg.loadL = (lane == 0) || (seg == 0);
+        sg.loadR = (lane == 31) || (seg == nseg - 1);
+        sg.active = active;
+        const Acc acc = sweep_strip<COLOUR, HEATBATH, TRACK, false>(tgt, oth, oth_up, oth_dn, half, L.Ly, SLAB ? L.row_offset : 0, sg, t,
+                                                                    first_chain + (uint32_t)chain, seed_lo, seed_hi, s_pair, s_thi, s_tlo);
+        strip_finish<TRACK>(acc, sums, chain);
         if (SLAB && boundary_item) {
             __syncthreads();
             if (threadIdx.x == 0) slab_signal(L.slab_ctl, t, (unsigned)((2 * (int64_t)nseg + kThreads - 1) / kThreads), L.slab_sides);

@@ -25,7 +25,7 @@
 // memory): thousands of warps polling one L2 word delayed the closing warp's own accesses by tens of microseconds.
 // Trajectories, ladder state and counters are bit-identical to mcx_sweep + mcx_pt_publish + mcx_pt_exchange per round
 // (tests/test_gpu_pt_persistent.py), which are held to the oracle.
-#include "k_row16.cuh"
+#include "k_strip.cuh"
 
 namespace mcx {
 
@@ -33,7 +33,10 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMinBlocks = 5;                 // 96 registers; 6 CTAs / 80 registers was measured slower for the series kernels
+#ifndef MCX_PERSIST_MINB
+#define MCX_PERSIST_MINB 5
+#endif
+constexpr int kMinBlocks = MCX_PERSIST_MINB;                 // 96 registers; 6 CTAs / 80 registers was measured slower for the series kernels
 // shared memory of one warp: the pair table, the exact 32-bit thresholds, padding to a multiple of 128 bytes
 constexpr int kWarpTableWords = (kPairWords + 2 * kTableLen + 31) / 32 * 32;
 
@@ -160,69 +163,21 @@ __device__ __forceinline__ void item_finish(const Acc &acc, long long *__restric
     }
 }
 
-// one item of one half-sweep: 32 thread-items, each a 16-byte column segment of a strip of rows
-// (the loop of k_ising2d without prefetch, slabs or bands; loads and stores through L2)
+// one item of one half-sweep: 32 thread-items, each a 16-byte column segment of a strip of rows (sweep_strip, k_strip.cuh:
+// the streaming kernel's loop with loads and stores through L2)
 template <int COLOUR, bool HEATBATH, bool TRACK>
 __device__ __forceinline__ void strip_item(const LatView &L, const int chain, const ItemGeom &g, const uint64_t t,
                                            const uint32_t *s_pair, const uint32_t *s_thi, const uint32_t *s_tlo,
                                            long long *__restrict__ sums, const uint32_t seed_lo, const uint32_t seed_hi,
                                            const uint32_t first_chain)
 {
-    const int half = L.half;
-    const uint32_t t_lo = (uint32_t)t;
-    const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
-    const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
-    const bool active = g.active;
-    const int row0 = g.row0, col = g.col;
-    const uint32_t chain_id = first_chain + (uint32_t)chain;
-
     uint8_t *tgt = plane_ptr(L, chain, COLOUR);
     const uint8_t *oth = plane_ptr(L, chain, COLOUR ^ 1);
-    // even rows of this strip have parity COLOUR, odd rows COLOUR ^ 1 (row0 is even)
-    const bool edgeA = COLOUR == 0 ? g.loadL : g.loadR;
-    const bool edgeB = COLOUR == 0 ? g.loadR : g.loadL;
-    const int colA = COLOUR == 0 ? g.colL : g.colR;
-    const int colB = COLOUR == 0 ? g.colR : g.colL;
-
-    const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
-    const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, current even row
-    uint8_t *pt = tgt + (int64_t)row0 * half + col;           // target plane, current even row
-    uint4 U = ld_cg128(oth + (int64_t)rowU * half + col);
-    uint4 C = ld_cg128(po + col);
-    uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
-    const uint32_t blk_step = (uint32_t)(half >> 3);
-    Acc acc;
-
-#pragma unroll 1
-    for (int r = 0; r < g.rows; r += 2) {
-        const int row = row0 + r;
-        // E = other row below the odd row; wraps only at the very last row of the lattice
-        const uint8_t *pe = (row + 2 == L.Ly) ? oth : po + 2 * (int64_t)half;
-        const uint4 E = ld_cg128(pe + col);
-        const uint4 D = ld_cg128(po + half + col);
-        const uint4 Ta = ld_cg128(pt), Tb = ld_cg128(pt + half);
-        uint32_t sideA = 0, sideB = 0;
-        if (edgeA) sideA = ld_cg8(po + colA);
-        if (edgeB) sideB = ld_cg8(po + half + colB);
-        uint32_t sA, sB;
-        if (COLOUR == 0) {
-            sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
-            sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
-        } else {
-            sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
-            sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
-        }
-        if (edgeA) sA = sideA;
-        if (edgeB) sB = sideB;
-        const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
-                                                             seed_hi, s_pair, s_thi, s_tlo, acc, active);
-        if (active) st_cg128(pt, Na);
-        const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
-                                                                 seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-        if (active) st_cg128(pt + half, Nb);
-        U = D; C = E;
-        po += 2 * (int64_t)half; pt += 2 * (int64_t)half; blk += 2 * blk_step;
-    }
+    StripGeom sg;
+    sg.row0 = g.row0; sg.rows = g.rows; sg.col = g.col; sg.colL = g.colL; sg.colR = g.colR;
+    sg.loadL = g.loadL; sg.loadR = g.loadR; sg.active = g.active;
+    const Acc acc = sweep_strip<COLOUR, HEATBATH, TRACK, true>(tgt, oth, oth, oth, L.half, L.Ly, 0, sg, t, first_chain + (uint32_t)chain,
+                                                               seed_lo, seed_hi, s_pair, s_thi, s_tlo);
     item_finish<TRACK>(acc, sums, chain);
 }
 
@@ -582,6 +537,7 @@ bool rounds_plan(const mcx_lattice *lat, K kern, RoundsPlan &q)
             const int64_t m = n16 <= q.workers_max ? 1 : (n16 + q.workers_max - 1) / q.workers_max;
             nstrips = m * q.workers_max / per_strip;
         }
+        if (nstrips < (L.Ly + 31) / 32) nstrips = (L.Ly + 31) / 32;           // sweep_strip flags left-over rows in 32 bits
         if (nstrips > L.Ly / 2) nstrips = L.Ly / 2;
         if (nstrips < 1) nstrips = 1;
         q.nstrips = (int)nstrips;
@@ -591,6 +547,7 @@ bool rounds_plan(const mcx_lattice *lat, K kern, RoundsPlan &q)
         q.geom = GEOM_UNIFORM;
         int r = knobs().queue_rows > 0 ? knobs().queue_rows : 16;
         if (r > L.Ly) r = L.Ly;
+        if (r > 32) r = 32;                                    // sweep_strip flags left-over rows in 32 bits
         r &= ~1;
         while (r > 2 && L.Ly % r != 0) r -= 2;
         if (r < 2) r = 2;

@@ -13,7 +13,7 @@
 // SMs never drain until the series ends.  Rows written by other SMs during the same launch are read with
 // ld.global.cg (L2; L1 is not coherent across SMs).  The per-site rule, the Philox counters and the sums are
 // the streaming kernel's (update_row, k_row16.cuh): trajectories are bit-identical.
-#include "k_row16.cuh"
+#include "k_strip.cuh"
 
 namespace mcx {
 
@@ -29,22 +29,6 @@ constexpr int kThreads = 128;
 
 enum { Q_TICKET = 0, Q_WORDS = 2 };
 
-__device__ __forceinline__ uint4 ld_cg128(const uint8_t *p)
-{
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_cg8(const uint8_t *p)
-{
-    uint32_t v;
-    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_cg128(uint8_t *p, const uint4 v)
-{
-    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 {
     uint32_t v;
@@ -52,8 +36,8 @@ __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
     return v;
 }
 
-// one CTA-item of one half-sweep: 128 thread-items, each a 16-byte column segment of a strip of R rows
-// (the loop of k_ising2d without prefetch, slabs or bands; loads and stores through L2)
+// one CTA-item of one half-sweep: 128 thread-items, each a 16-byte column segment of a strip of R rows (sweep_strip,
+// k_strip.cuh: the streaming kernel's loop with loads and stores through L2)
 template <int COLOUR, bool HEATBATH, bool TRACK>
 __device__ __forceinline__ void queue_item(const LatView &L, const int chain, const int item, const uint64_t t,
                                            const uint32_t *s_pair, const uint32_t *s_thi, const uint32_t *s_tlo,
@@ -62,88 +46,25 @@ __device__ __forceinline__ void queue_item(const LatView &L, const int chain, co
 {
     const int half = L.half;
     const int nseg = half >> 4;
-    const int64_t G = (int64_t)nstrips * nseg;
+    const uint32_t G = (uint32_t)nstrips * (uint32_t)nseg;       // < 2^31 (the launcher checks)
     const int lane = threadIdx.x & 31;
-    const uint32_t t_lo = (uint32_t)t;
-    const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
-    const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
-    const int64_t g0 = (int64_t)item * kThreads + threadIdx.x;
+    const uint32_t g0 = (uint32_t)item * kThreads + threadIdx.x;
     const bool active = g0 < G;
-    const int64_t g = active ? g0 : G - 1;
-    const int strip = (int)(g / nseg);
-    const int seg = (int)(g - (int64_t)strip * nseg);
-    const int row0 = strip * R;                               // even
-    const uint32_t chain_id = first_chain + (uint32_t)chain;
-
+    const uint32_t g = active ? g0 : G - 1;
+    const int strip = (int)(g / (uint32_t)nseg);
+    const int seg = (int)(g - (uint32_t)strip * (uint32_t)nseg);
     uint8_t *tgt = plane_ptr(L, chain, COLOUR);
     const uint8_t *oth = plane_ptr(L, chain, COLOUR ^ 1);
-    const int col = seg << 4;
-    const int colL = (seg == 0 ? half : col) - 1;             // byte left of the segment (periodic)
-    const int colR = (seg == nseg - 1) ? 0 : col + 16;        // byte right of the segment
-    const bool loadL = (lane == 0) || (seg == 0);
-    const bool loadR = (lane == 31) || (seg == nseg - 1);
-    // even rows of this strip have parity COLOUR, odd rows COLOUR ^ 1 (row0 is even)
-    const bool edgeA = COLOUR == 0 ? loadL : loadR;
-    const bool edgeB = COLOUR == 0 ? loadR : loadL;
-    const int colA = COLOUR == 0 ? colL : colR;
-    const int colB = COLOUR == 0 ? colR : colL;
-
-    const int rowU = row0 == 0 ? L.Ly - 1 : row0 - 1;
-    const uint8_t *po = oth + (int64_t)row0 * half;           // other plane, current even row
-    uint8_t *pt = tgt + (int64_t)row0 * half + col;           // target plane, current even row
-    uint4 U = ld_cg128(oth + (int64_t)rowU * half + col);
-    uint4 C = ld_cg128(po + col);
-    uint32_t blk = (uint32_t)(((int64_t)row0 * half + col) >> 3);
-    const uint32_t blk_step = (uint32_t)(half >> 3);
-    Acc acc;
-
-#pragma unroll 1
-    for (int r = 0; r < R; r += 2) {
-        const int row = row0 + r;
-        // E = other row below the odd row; wraps only at the very last row of the lattice
-        const uint8_t *pe = (row + 2 == L.Ly) ? oth : po + 2 * (int64_t)half;
-        const uint4 E = ld_cg128(pe + col);
-        const uint4 D = ld_cg128(po + half + col);
-        const uint4 Ta = ld_cg128(pt), Tb = ld_cg128(pt + half);
-        uint32_t sideA = 0, sideB = 0;
-        if (edgeA) sideA = ld_cg8(po + colA);
-        if (edgeB) sideB = ld_cg8(po + half + colB);
-        uint32_t sA, sB;
-        if (COLOUR == 0) {
-            sA = __shfl_up_sync(0xffffffffu, C.w, 1) >> 24;
-            sB = __shfl_down_sync(0xffffffffu, D.x, 1) & 0xffu;
-        } else {
-            sA = __shfl_down_sync(0xffffffffu, C.x, 1) & 0xffu;
-            sB = __shfl_up_sync(0xffffffffu, D.w, 1) >> 24;
-        }
-        if (edgeA) sA = sideA;
-        if (edgeB) sB = sideB;
-        const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(Ta, U, C, D, sA, blk, t_lo, c2, c2lo, chain_id, seed_lo,
-                                                             seed_hi, s_pair, s_thi, s_tlo, acc, active);
-        if (active) st_cg128(pt, Na);
-        const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(Tb, C, D, E, sB, blk + blk_step, t_lo, c2, c2lo, chain_id,
-                                                                 seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-        if (active) st_cg128(pt + half, Nb);
-        U = D; C = E;
-        po += 2 * (int64_t)half; pt += 2 * (int64_t)half; blk += 2 * blk_step;
-    }
-
-    // per-chain sums: dspin = 2 - 4 s, dpair = -8 s nup + 16 s + 4 nup - 8 per changed site
-    const int nflip = warp_sum((int)acc.flips);
-    int dspin = 0, dpair = 0;
-    if (TRACK) {
-        const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
-        dspin = 2 * nflip - 4 * ss;
-        dpair = -8 * sn + 16 * ss + 4 * nn_ - 8 * nflip;
-    }
-    if (lane == 0) {
-        unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
-        if (nflip) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nflip);
-        if (TRACK) {
-            if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
-            if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
-        }
-    }
+    StripGeom sg;
+    sg.row0 = strip * R; sg.rows = R; sg.col = seg << 4;
+    sg.colL = (seg == 0 ? half : sg.col) - 1;
+    sg.colR = (seg == nseg - 1) ? 0 : sg.col + 16;
+    sg.loadL = (lane == 0) || (seg == 0);
+    sg.loadR = (lane == 31) || (seg == nseg - 1);
+    sg.active = active;
+    const Acc acc = sweep_strip<COLOUR, HEATBATH, TRACK, true>(tgt, oth, oth, oth, half, L.Ly, 0, sg, t, first_chain + (uint32_t)chain,
+                                                               seed_lo, seed_hi, s_pair, s_thi, s_tlo);
+    strip_finish<TRACK>(acc, sums, chain);
 }
 
 template <bool HEATBATH, bool TRACK>
@@ -251,7 +172,7 @@ bool launch_sweeps_ising2d_queue(mcx_lattice *lat, int64_t nsweeps)
     // half-sweep; as ONE series launch with strips short enough to give every resident CTA an item per half-sweep it runs
     // at 1391 instead of 946 attempts/ns (L = 8192, 16-row strips), 963 / 598 (4096, 4 rows), 339 / 213 (2048, 2 rows),
     // 118 / 67 (1024, 2 rows): profiles/r02_queue_single.md.  L = 16384 stays with the row bands (1522 against 1250).
-    int R = knobs().queue_rows > 0 ? knobs().queue_rows : 16, ipc = 0;
+    int R = knobs().queue_rows > 0 ? (knobs().queue_rows > 32 ? 32 : knobs().queue_rows) : 16, ipc = 0;   // <= 32: sweep_strip's flags
     const int r_min = single ? 2 : 8;
     for (;; R >>= 1) {
         int r = R;
