@@ -117,6 +117,13 @@ __device__ __forceinline__ Acc sweep_strip(uint8_t *tgt, const uint8_t *__restri
     const uint32_t pair_addr = (uint32_t)__cvta_generic_to_shared(s_pair);
     Acc acc;
     uint32_t ties = 0;                                           // rows left to settle_rows()
+    // ONE prefetch per trip pulls the next trip's four new row segments into L2 (a hint: no registers wait for it): lane l
+    // asks for row (l & 3) of {other + 3, other + 4, target + 2, target + 3} at the segment of lane (l & ~3), so the four
+    // 128-byte lines of each row are each named by two lanes.  Past the strip the addresses fall into the next strip (or
+    // the slack rows behind the last plane, mcx_lattice_create).  +1 % at L = 16384; into L1 or two rows further ahead:
+    // no better (profiles/r02_call27_28_prefetch.log).
+    const int pf_k = threadIdx.x & 3;
+    const uint8_t *ppf = (pf_k < 2 ? oth : (const uint8_t *)tgt) + (size_t)(row0 + (pf_k == 1 ? 4 : pf_k == 2 ? 2 : 3)) * h + (col - 16 * pf_k);
 
 #pragma unroll 1
     for (int r = 0; r < R; r += 2) {
@@ -126,6 +133,10 @@ __device__ __forceinline__ Acc sweep_strip(uint8_t *tgt, const uint8_t *__restri
         const uint4 E = strip_ld128<L2ONLY>(pe);
         const uint4 D = strip_ld128<L2ONLY>(po + h);
         const uint4 Ta = strip_ld128<L2ONLY>(pt), Tb = strip_ld128<L2ONLY>(pt + h);
+        if (!L2ONLY) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ppf));
+            ppf += h2;
+        }
         uint32_t sideA = 0, sideB = 0;
         if (edgeA) sideA = strip_ld8<L2ONLY>(po + offA);
         if (edgeB) sideB = strip_ld8<L2ONLY>(po + offB);

@@ -286,8 +286,10 @@ int32_t mcx_lattice_create(mcx_ctx *ctx, int32_t model, int32_t ndim, const int3
     lat->fast2d = (ndim == 2) && (v.Lx % 32 == 0);
     lat->track_sums = true;
     const size_t plane_bytes = (size_t)v.plane_stride * 2 * (size_t)nchains;
+    // slack behind the last plane: the strip loop's L2 prefetch (k_strip.cuh) names a few rows past a strip
+    const size_t plane_slack = ((size_t)8 * (size_t)v.half + 255) / 256 * 256;
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&v.planes, plane_bytes)) != cudaSuccess ||
+    if ((e = cudaMalloc((void **)&v.planes, plane_bytes + plane_slack)) != cudaSuccess ||
         (e = cudaMalloc((void **)&lat->d_sums, sizeof(long long) * SUM_FIELDS * (size_t)nchains)) != cudaSuccess ||
         (e = cudaMalloc((void **)&lat->d_labels, sizeof(int32_t) * (size_t)nchains)) != cudaSuccess) {
         lattice_free(lat);
