@@ -7,7 +7,7 @@
 // working form, runs the int8 kernel's own update_row (same Philox positions, same packed 15-bit decision, same exact
 // redo) and writes one word back.  0.375 B per attempt instead of 3; an L = 16384 lattice is 2 x 16 MiB and stays in L2.
 #include "k_bits.cuh"
-#include "k_row16.cuh"
+#include "k_strip.cuh"
 
 namespace mcx {
 
@@ -15,8 +15,40 @@ namespace {
 
 constexpr int kBitThreads = 128;
 
+// The rows of a strip that the loop left undecided (flags as in k_strip.cuh), redone one by one: the row's 16 bits are
+// cut out of its word, settled with the full 32-bit draws and merged back (only this thread writes the word).
+template <int COLOUR, bool HEATBATH, bool TRACK>
+__device__ __noinline__ uint4 settle_rows_bits(uint8_t *tgt, const uint8_t *oth, const uint8_t *oth_up, const uint8_t *oth_dn,
+                                               const int half, const int Ly, const int row_offset, uint32_t ties, const int row0,
+                                               const int R, const int seg, const int colL, const int colR, const uint32_t t_lo,
+                                               const uint32_t c2, const uint32_t c2lo, const uint32_t chain_id, const uint32_t seed_lo,
+                                               const uint32_t seed_hi, const uint32_t *s_thi, const uint32_t *s_tlo)
+{
+    const int nseg = half >> 4, col = seg << 4;
+    Acc acc;
+    while (ties) {
+        const int p = __ffs((int)ties) - 1;
+        ties &= ties - 1;
+        const int r = R - 2 - (p & ~1) + (~p & 1);
+        const int row = row0 + r;
+        const int rho = r & 1;                                   // row0 is even: the row's place in its word
+        const int parity = rho ? (COLOUR ^ 1) : COLOUR;
+        const uint4 U = row == 0 ? bits_expand(*bits_word(oth_up, Ly - 1, nseg, seg), 1) : bits_expand(*bits_word(oth, row - 1, nseg, seg), rho ^ 1);
+        const uint4 D = row + 1 == Ly ? bits_expand(*bits_word(oth_dn, 0, nseg, seg), 0) : bits_expand(*bits_word(oth, row + 1, nseg, seg), rho ^ 1);
+        const uint4 C = bits_expand(*bits_word(oth, row, nseg, seg), rho);
+        const uint32_t side = bits_site(oth, row, nseg, parity == 0 ? colL : colR);
+        uint32_t *ptw = reinterpret_cast<uint32_t *>(tgt) + (int64_t)(row >> 1) * nseg + seg;
+        const uint32_t Tw = *ptw;
+        const uint32_t blk = (uint32_t)(((int64_t)(row + row_offset) * half + col) >> 3);
+        const uint4 ex = row_settle<HEATBATH, TRACK>(parity, bits_expand(Tw, rho), U, C, D, side, blk, t_lo, c2, c2lo, chain_id, seed_lo,
+                                                     seed_hi, s_thi, s_tlo, acc);
+        *ptw = (Tw & (rho ? 0x0f0f0f0fu : 0xf0f0f0f0u)) | (bits_compress(ex) << (4 * rho));
+    }
+    return make_uint4(acc.flips, (uint32_t)acc.s, (uint32_t)acc.n, (uint32_t)acc.sn);
+}
+
 template <int COLOUR, bool HEATBATH, bool TRACK, bool FULL, bool SLAB>
-__global__ void __launch_bounds__(kBitThreads, 6)
+__global__ void __launch_bounds__(kBitThreads, 8)
 k_ising2d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
                const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
                uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
@@ -27,11 +59,12 @@ k_ising2d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__
 
     const int half = L.half;
     const int nseg = half >> 4;
-    const int64_t G = (int64_t)nstrips * nseg;
+    const uint32_t G = (uint32_t)nstrips * (uint32_t)nseg;       // thread-items of a chain: < 2^31
     const int lane = threadIdx.x & 31;
     const uint32_t t_lo = (uint32_t)t;
     const uint32_t c2 = ctr_word2(t, 0, TAG_SWEEP);
     const uint32_t c2lo = ctr_word2(t, 1, TAG_SWEEP);
+    const uint32_t pair_addr = (uint32_t)__cvta_generic_to_shared(s_pair);
 
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int chain = item / blocks_per_chain;
@@ -42,11 +75,11 @@ k_ising2d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__
             __syncthreads();
             cur_label = label;
         }
-        const int64_t g0 = (int64_t)(item - chain * blocks_per_chain) * kBitThreads + threadIdx.x;
+        const uint32_t g0 = (uint32_t)(item - chain * blocks_per_chain) * kBitThreads + threadIdx.x;
         const bool active = FULL ? true : g0 < G;
-        const int64_t g = active ? g0 : G - 1;
-        const int strip = (int)(g / nseg);
-        const int seg = (int)(g - (int64_t)strip * nseg);
+        const uint32_t g = active ? g0 : G - 1;
+        const int strip = (int)(g / (uint32_t)nseg);
+        const int seg = (int)(g - (uint32_t)strip * (uint32_t)nseg);
         const int row0 = strip * R;                               // even
         const uint32_t chain_id = first_chain + (uint32_t)chain;
 
@@ -76,8 +109,11 @@ k_ising2d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__
         uint4 C = bits_expand(Wc, 0);
         uint32_t blk = (uint32_t)(((int64_t)(row0 + (SLAB ? L.row_offset : 0)) * half + col) >> 3);
         const uint32_t blk_step = (uint32_t)(half >> 3);
+        const PhiloxHead H = philox_head(t_lo, c2, chain_id, seed_lo, seed_hi);
         Acc acc;
+        uint32_t ties = 0;                                        // rows left to settle_rows_bits() (R <= 32)
 
+        // one basic block per trip, as in k_strip.cuh: a row with an undecided site keeps its bits and is settled after the strip
 #pragma unroll 1
         for (int r = 0; r < R; r += 2) {
             const int row = row0 + r;
@@ -99,34 +135,25 @@ k_ising2d_bits(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__
             }
             if (edgeA) sA = sideA;
             if (edgeB) sB = sideB;
-            const uint4 Na = update_row<COLOUR, HEATBATH, TRACK>(bits_expand(Tw, 0), U, C, D, sA, blk, t_lo, c2, c2lo, chain_id,
-                                                                 seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            uint32_t out = bits_compress(Na);
+            bool tieA, tieB;
+            const uint4 Na = update_row_fast<COLOUR, HEATBATH, TRACK>(philox_tail(H, blk), philox_tail(H, blk + 1), bits_expand(Tw, 0), U, C, D, sA,
+                                                                      pair_addr, acc, active, tieA);
+            uint32_t out = tieA ? (Tw & 0x0f0f0f0fu) : bits_compress(Na);
             const uint4 E = bits_expand(We, 0);
-            const uint4 Nb = update_row<COLOUR ^ 1, HEATBATH, TRACK>(bits_expand(Tw, 1), C, D, E, sB, blk + blk_step, t_lo, c2, c2lo,
-                                                                     chain_id, seed_lo, seed_hi, s_pair, s_thi, s_tlo, acc, active);
-            out += bits_compress(Nb) << 4;
+            const uint4 Nb = update_row_fast<COLOUR ^ 1, HEATBATH, TRACK>(philox_tail(H, blk + blk_step), philox_tail(H, blk + blk_step + 1),
+                                                                          bits_expand(Tw, 1), C, D, E, sB, pair_addr, acc, active, tieB);
+            out |= tieB ? (Tw & 0xf0f0f0f0u) : (bits_compress(Nb) << 4);
             if (active) *ptw = out;
+            ties = (ties << 2) | (tieA ? 2u : 0u) | (tieB ? 1u : 0u);
             U = D; C = E; Wc = We;
             pw += nseg; ptw += nseg; blk += 2 * blk_step;
         }
-
-        // per-chain sums: dspin = 2 - 4 s, dpair = -8 s nup + 16 s + 4 nup - 8 per changed site
-        const int nflip = warp_sum((int)acc.flips);
-        int dspin = 0, dpair = 0;
-        if (TRACK) {
-            const int ss = warp_sum(acc.s), nn_ = warp_sum(acc.n), sn = warp_sum(acc.sn);
-            dspin = 2 * nflip - 4 * ss;
-            dpair = -8 * sn + 16 * ss + 4 * nn_ - 8 * nflip;
+        if (active && ties) {
+            const uint4 d = settle_rows_bits<COLOUR, HEATBATH, TRACK>(tgt, oth, oth_up, oth_dn, half, L.Ly, SLAB ? L.row_offset : 0, ties, row0, R,
+                                                                      seg, colL, colR, t_lo, c2, c2lo, chain_id, seed_lo, seed_hi, s_thi, s_tlo);
+            acc.flips += d.x; acc.s += (int32_t)d.y; acc.n += (int32_t)d.z; acc.sn += (int32_t)d.w;
         }
-        if (lane == 0) {
-            unsigned long long *o = (unsigned long long *)(sums + (int64_t)chain * SUM_FIELDS);
-            if (nflip) atomicAdd(o + SUM_ACC, (unsigned long long)(long long)nflip);
-            if (TRACK) {
-                if (dpair) atomicAdd(o + SUM_PAIR, (unsigned long long)(long long)dpair);
-                if (dspin) atomicAdd(o + SUM_SPIN, (unsigned long long)(long long)dspin);
-            }
-        }
+        strip_finish<TRACK>(acc, sums, chain);
     }
 }
 
@@ -369,7 +396,7 @@ void launch_bits_t(mcx_lattice *lat, uint64_t t)
             if (items >= 4 * ctas || R <= 4) break;
         }
         while (L.Ly % R != 0) R -= 2;
-        if (knobs().rows_per_strip > 0 && L.Ly % knobs().rows_per_strip == 0 && knobs().rows_per_strip % 2 == 0) R = knobs().rows_per_strip;
+        if (knobs().rows_per_strip > 0 && knobs().rows_per_strip <= 32 && L.Ly % knobs().rows_per_strip == 0 && knobs().rows_per_strip % 2 == 0) R = knobs().rows_per_strip;   // <= 32: the kernel flags left-over rows in 32 bits
     }
     const int nstrips = L.Ly / R;
     const int nseg = L.half >> 4;
