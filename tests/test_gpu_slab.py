@@ -27,7 +27,7 @@ def _alg(m, rule, seed):
 
 @pytest.mark.parametrize("dims,nslabs", [([256, 256], 2), ([256, 256], 4), ([1024, 96], 3), ([64, 512], 8), ([512, 64], 1)])
 @pytest.mark.parametrize("rule", [0, 1, 2])
-def test_local_slabs_equal_whole_lattice(m, dims, nslabs, rule):
+def test_local_slabs_equal_whole_lattice(m, oracle, dims, nslabs, rule):
     nsweeps = 5
     os.environ["MCX_RESIDENT"] = "0"
     try:
@@ -37,6 +37,12 @@ def test_local_slabs_equal_whole_lattice(m, dims, nslabs, rule):
         m.sweep_(whole, a0, nsweeps)
     finally:
         os.environ.pop("MCX_RESIDENT", None)
+    # the unsplit lattice the slabs are compared with is itself the oracle's trajectory (not only the device's own)
+    ref = oracle.System(oracle.ISING, dims)
+    ref.init_random(77, 2)
+    ralg = oracle.Alg(rule, BETA_C)
+    ref.sweep_checkerboard(ralg, 77, 2, 0, nsweeps)
+    assert np.array_equal(whole.spins, ref.spins) and whole.pair_sum() == ref.pair_count()
     for tracking in (True, False):
         slabs = m.SlabIsing(dims, nslabs=nslabs)
         slabs.set_tracking(tracking)
