@@ -237,8 +237,10 @@ int32_t mcx_pt_exchange(mcx_pt *pt);
  * ranks' energies, decides the exchanges and releases the next round -- same decisions, same trajectories as
  * mcx_sweep + mcx_pt_publish + mcx_pt_exchange per round (MCX_PT_PERSIST=0 forces that path). */
 int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round);
-/* how the last mcx_pt_run was executed: *path = 1 one persistent launch (*strip_rows = rows per work item), 0 = rounds
- * queued from the host.  Diagnostics for bench.py and the tests. */
+/* how the last mcx_pt_run was executed: *path = 1 one persistent launch (*strip_rows = rows per work item), 2 = rounds
+ * replayed from a CUDA graph of eight rounds whose kernels read the half-sweep index and the round from a device clock
+ * (intervals of one or two sweeps, where queuing the ~25 stream operations of a round bounds the rate; MCX_PT_GRAPH=0
+ * disables it), 0 = rounds queued from the host launch by launch.  Diagnostics for bench.py and the tests. */
 int32_t mcx_pt_run_info(mcx_pt *pt, int32_t *path, int32_t *strip_rows);
 int32_t mcx_pt_state(mcx_pt *pt, int64_t *indices /*[n] 1-based*/, int64_t *steps /*[n-1]*/,
                      int64_t *accepted /*[n-1]*/, int64_t *stage, int64_t *round);

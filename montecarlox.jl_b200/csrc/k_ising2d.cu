@@ -27,6 +27,7 @@
 namespace mcx {
 
 thread_local LaunchRange g_launch_range;
+thread_local const unsigned long long *g_t_clock = nullptr;
 
 namespace {
 
@@ -87,8 +88,10 @@ template <int COLOUR, bool HEATBATH, bool TRACK, bool FULL, bool SLAB>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 k_ising2d(LatView L, const uint32_t *__restrict__ thi_g, const uint32_t *__restrict__ tlo_g,
           const int32_t *__restrict__ labels, long long *__restrict__ sums, uint32_t seed_lo, uint32_t seed_hi,
-          uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems)
+          uint64_t t, uint32_t first_chain, int R, int nstrips, int blocks_per_chain, int nitems, const unsigned long long *t_clock)
 {
+    // a launch replayed from a CUDA graph (mcx_pt_run): t counts from the device clock of the round (PtClock::t_base)
+    if (t_clock) t += *(const volatile unsigned long long *)t_clock;
     __shared__ uint32_t s_pair[kPairWords];
     __shared__ uint32_t s_thi[kTableLen], s_tlo[kTableLen];
     int cur_label = -1;
@@ -380,7 +383,7 @@ void launch_t(mcx_lattice *lat, uint64_t t)
     if (grid > nitems) grid = nitems;
     kern<<<grid, kThreads, 0, stream>>>(L, lat->d_thi, lat->d_tlo, lat->d_labels + c0, lat->d_sums + (int64_t)c0 * SUM_FIELDS,
                                        (uint32_t)lat->seed, (uint32_t)(lat->seed >> 32), t, lat->first_chain + (uint32_t)c0, R,
-                                       nstrips, blocks_per_chain, nitems);
+                                       nstrips, blocks_per_chain, nitems, g_t_clock);
     lat->ctx->launches++;
 }
 

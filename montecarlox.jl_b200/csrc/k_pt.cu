@@ -42,13 +42,20 @@ __device__ __forceinline__ void pt_wait_all(const unsigned long long *arrived, i
     __threadfence_system();
 }
 
+// clock != nullptr (a round replayed from a CUDA graph): the round comes from the device clock; `stage` then holds the
+// parity of stage - round, which no exchange changes, and `x` the base of the two round-parity buffers (xstride apart).
 __global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__restrict__ betas,
                               const double *x, int32_t *__restrict__ index,
                               int32_t *__restrict__ slot_of, long long *__restrict__ steps,
                               long long *__restrict__ accepted, int32_t *__restrict__ labels, int nlocal,
                               int first_slot, uint32_t seed_lo, uint32_t seed_hi, const unsigned long long *arrived,
-                              int nranks, int *err, int *ctx_err)
+                              int nranks, int *err, int *ctx_err, const PtClock *clock, int xstride)
 {
+    if (clock) {
+        round = *(const volatile unsigned long long *)&clock->round;
+        stage = (int)((round + (uint64_t)stage) & 1);
+        x += (size_t)(round & 1) * (size_t)xstride;
+    }
     if (arrived) {      // energies arrive by peer stores: wait for every rank's publish of this round
         if (threadIdx.x == 0) pt_wait_all(arrived, nranks, round + 1, err, ctx_err);
         __syncthreads();
@@ -81,8 +88,14 @@ __global__ void k_pt_exchange(int n, int stage, uint64_t round, const double *__
 // arrival counter bumped on every rank: the all-gather of replica_exchange.jl:239 fused into the publish.
 __global__ void k_pt_publish_peers(const long long *__restrict__ sums, double *const *__restrict__ peer_x,
                                    unsigned long long *const *__restrict__ peer_arrived, int nranks, int rank, int nlocal,
-                                   int first_slot, int offset, unsigned long long value, double J, double h, double D, int model)
+                                   int first_slot, int offset, unsigned long long value, double J, double h, double D, int model,
+                                   const PtClock *clock, int n)
 {
+    if (clock) {                                               // graph replay: the round parity buffer and the arrival value of this round
+        const unsigned long long round = *(const volatile unsigned long long *)&clock->round;
+        offset = (int)(round & 1) * n;
+        value = round + 1;
+    }
     for (int c = threadIdx.x; c < nlocal; c += blockDim.x) {
         const long long *s = sums + (int64_t)c * SUM_FIELDS;
         double e = -(J * (double)s[SUM_PAIR]);
@@ -98,13 +111,33 @@ __global__ void k_pt_publish_peers(const long long *__restrict__ sums, double *c
     }
 }
 
-void launch_pt_publish(mcx_pt *pt)
+__global__ void k_pt_clock_set(PtClock *clock, unsigned long long t_base, unsigned long long round)
+{
+    clock->t_base = t_base; clock->round = round;
+}
+__global__ void k_pt_clock_advance(PtClock *clock, unsigned long long dt)
+{
+    clock->t_base += dt; clock->round += 1;
+}
+
+void launch_pt_clock_set(mcx_pt *pt)
+{
+    k_pt_clock_set<<<1, 1, 0, pt->lat->ctx->stream>>>(pt->d_clock, 2 * pt->lat->sweep, pt->round);
+    pt->lat->ctx->launches++;
+}
+void launch_pt_clock_advance(mcx_pt *pt, int64_t sweeps)
+{
+    k_pt_clock_advance<<<1, 1, 0, pt->lat->ctx->stream>>>(pt->d_clock, 2 * (unsigned long long)sweeps);
+    pt->lat->ctx->launches++;
+}
+
+void launch_pt_publish(mcx_pt *pt, const PtClock *clock)
 {
     if (pt->peers) {
         mcx_lattice *lat = pt->lat;
         k_pt_publish_peers<<<1, 256, 0, lat->ctx->stream>>>(lat->d_sums, pt->d_peer_x, pt->d_peer_arrived, pt->nranks, pt->rank,
                                                           lat->nchains, pt->first_slot, (int)(pt->round & 1) * pt->n,
-                                                          pt->round + 1, lat->J, lat->h, lat->D, lat->model);
+                                                          pt->round + 1, lat->J, lat->h, lat->D, lat->model, clock, pt->n);
         lat->ctx->launches++;
         return;
     }
@@ -116,15 +149,19 @@ void launch_pt_publish(mcx_pt *pt)
     }
 }
 
-void launch_pt_exchange(mcx_pt *pt)
+void launch_pt_exchange(mcx_pt *pt, const PtClock *clock)
 {
     mcx_lattice *lat = pt->lat;
     const int npairs = (pt->n - 1 + 1) / 2;
     const int blocks = npairs > 0 ? (npairs + 127) / 128 : 1;
+    // graph replay: stage - round keeps its parity, the kernel rebuilds the stage and the parity buffer from the clock's round
+    const int stage = clock ? (int)(((uint64_t)pt->stage + pt->round) & 1) : pt->stage;
+    const double *x = clock ? pt->d_x : pt->d_x + (pt->peers ? (pt->round & 1) * pt->n : 0);
     k_pt_exchange<<<blocks, 128, 0, lat->ctx->stream>>>(
-        pt->n, pt->stage, pt->round, pt->d_betas, pt->d_x + (pt->peers ? (pt->round & 1) * pt->n : 0), pt->d_index, pt->d_slot_of,
+        pt->n, stage, pt->round, pt->d_betas, x, pt->d_index, pt->d_slot_of,
         pt->d_steps, pt->d_accepted, lat->d_labels, lat->nchains, pt->first_slot, (uint32_t)lat->seed,
-        (uint32_t)(lat->seed >> 32), pt->peers ? pt->d_arrived : nullptr, pt->nranks, pt->d_err, lat->ctx->d_err);
+        (uint32_t)(lat->seed >> 32), pt->peers ? pt->d_arrived : nullptr, pt->nranks, pt->d_err, lat->ctx->d_err, clock,
+        pt->peers ? pt->n : 0);
     lat->ctx->launches++;
 }
 

@@ -62,7 +62,7 @@ void knobs_refresh()
     k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
     k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
     k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.band_rows = knob("MCX_BAND_ROWS"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
-    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST"); k.flat_window = knob("MCX_FLAT_WINDOW");
+    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST"); k.pt_graph = knob("MCX_PT_GRAPH"); k.flat_window = knob("MCX_FLAT_WINDOW");
     g_knobs_ready = true;
 }
 const Knobs &knobs()
@@ -854,6 +854,8 @@ int32_t mcx_pt_destroy(mcx_pt *pt)
     cudaFree(pt->d_betas); cudaFree(pt->d_x); cudaFree(pt->d_index); cudaFree(pt->d_slot_of);
     cudaFree(pt->d_steps); cudaFree(pt->d_accepted); cudaFree(pt->d_arrived); cudaFree(pt->d_err);
     cudaFree(pt->d_peer_x); cudaFree(pt->d_peer_arrived); cudaFree(pt->d_dev);
+    if (pt->graph_exec) cudaGraphExecDestroy(pt->graph_exec);
+    cudaFree(pt->d_clock);
     delete pt;
     return MCX_OK;
 }
@@ -982,6 +984,98 @@ int32_t mcx_pt_exchange(mcx_pt *pt)
     return check_launch(pt->lat->ctx);
 }
 
+}  // extern "C"
+
+// One round of mcx_pt_run queued with the kernels reading the device clock: sweeps (chain groups or plain launches of
+// k_ising2d), publish, exchange, clock advance.  false: some launch is not available for this lattice.
+static bool pt_enqueue_clocked_round(mcx_pt *pt, int64_t S)
+{
+    mcx_lattice *lat = pt->lat;
+    const uint64_t sweep0 = lat->sweep;
+    lat->sweep = 0;                                             // launch arguments relative to the clock
+    mcx::g_t_clock = &pt->d_clock->t_base;
+    bool ok = mcx::launch_sweeps_ising2d_grouped(lat, S);
+    if (!ok) {
+        ok = true;
+        for (int64_t s = 0; s < S && ok; ++s)
+            for (int colour = 0; colour < 2 && ok; ++colour) ok = mcx::launch_sweep_ising2d(lat, colour, 2 * (uint64_t)s + (uint64_t)colour);
+    }
+    mcx::g_t_clock = nullptr;
+    lat->sweep = sweep0;
+    if (!ok) return false;
+    mcx::launch_pt_publish(pt, pt->d_clock);
+    mcx::launch_pt_exchange(pt, pt->d_clock);
+    mcx::launch_pt_clock_advance(pt, S);
+    return true;
+}
+
+// Rounds of mcx_pt_run replayed from a CUDA graph.  Returns the number of rounds done (0: not applicable, the caller
+// queues them launch by launch), -1 on a CUDA error.
+static int64_t pt_run_graph(mcx_pt *pt, int64_t nrounds, int64_t S)
+{
+    using namespace mcx;
+    mcx_lattice *lat = pt->lat;
+    mcx_ctx *ctx = lat->ctx;
+    constexpr int kGraphRounds = 8;                            // rounds per replay
+    const Knobs &k = knobs();
+    if (k.pt_graph == 0 || S >= 3 || nrounds < 2 * kGraphRounds) return 0;
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->N < (1 << 20)) return 0;
+    if (k.variant >= 0 || k.rows_per_strip >= 0 || k.force_generic > 0 || k.queue > 0 || k.resident > 0) return 0;
+    if (!pt->d_clock && cudaMalloc((void **)&pt->d_clock, sizeof(PtClock)) != cudaSuccess) { cudaGetLastError(); pt->d_clock = nullptr; return 0; }
+    if (lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
+    mcx_pt::GraphKey key;                                       // what the captured launch arguments depend on
+    memset(&key, 0, sizeof(key));
+    key.seed = lat->seed; key.first_chain = lat->first_chain; key.rule = lat->rule; key.S = (int)S; key.n = pt->n;
+    key.nchains = lat->nchains; key.peers = pt->peers ? 1 : 0;
+    key.thi = lat->d_thi; key.labels = lat->d_labels; key.sums = lat->d_sums; key.planes = lat->view.planes; key.x = pt->d_x;
+    if (pt->graph_exec && memcmp(&key, &pt->graph_key, sizeof(key)) != 0) {
+        cudaGraphExecDestroy(pt->graph_exec);
+        pt->graph_exec = nullptr;
+    }
+    if (!pt->graph_exec) {
+        // one round launch by launch first: whatever the launchers create lazily (streams, events) exists before the capture
+        const int32_t st0 = mcx_sweep(lat, S);
+        if (st0 != MCX_OK || mcx_pt_publish(pt) != MCX_OK || mcx_pt_exchange(pt) != MCX_OK) return -1;
+        nrounds -= 1;
+        const uint64_t launches0 = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
+        bool ok = true;
+        for (int r = 0; r < kGraphRounds && ok; ++r) ok = pt_enqueue_clocked_round(pt, S);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        pt->graph_launches = ctx->launches - launches0;
+        ctx->launches = launches0;
+        if (!ok || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return 1;                                          // the warm-up round is done; the caller queues the rest
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&pt->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { cudaGetLastError(); pt->graph_exec = nullptr; return 1; }
+        pt->graph_key = key;
+        pt->graph_rounds = kGraphRounds;
+        // the warm-up round counts as done
+        const int64_t rest = pt_run_graph(pt, nrounds, S);
+        return rest < 0 ? -1 : 1 + rest;
+    }
+    const int64_t replays = nrounds / pt->graph_rounds;
+    if (replays < 1) return 0;
+    launch_pt_clock_set(pt);
+    for (int64_t g = 0; g < replays; ++g) {
+        if (cudaGraphLaunch(pt->graph_exec, ctx->stream) != cudaSuccess) return -1;
+        ctx->launches += pt->graph_launches;
+    }
+    const int64_t done = replays * pt->graph_rounds;
+    lat->sweep += (uint64_t)(done * S);
+    lat->steps += done * S * lat->N;
+    pt->round += (uint64_t)done;
+    pt->stage = (int)((pt->stage + done) & 1);
+    return done;
+}
+
+extern "C" {
+
 // The user loop of pt_Ising2D.jl:52-57 -- `for i in 1:n; sweep; i % interval == 0 && update!(pt); end` -- queued
 // in one call: nrounds x (sweeps_per_round sweeps, publish, exchange).  Needs the energies to reach all ranks
 // without the host (one rank, or peer stores attached); otherwise MCX_ERR_UNSUPPORTED and the caller loops.
@@ -997,13 +1091,27 @@ int32_t mcx_pt_run(mcx_pt *pt, int64_t nrounds, int64_t sweeps_per_round)
     ASYNC_CHECK(lat->ctx);
     CUDA_TRY(cudaSetDevice(lat->ctx->device));
     if (nrounds == 0) return MCX_OK;
+    pt->last_path = 0;
+    // Intervals of one or two sweeps on lattices too big for shared memory: queued launch by launch the rounds are bound by
+    // the host (some 25 stream operations per round), so they are replayed from a CUDA graph of eight rounds whose kernels
+    // read the half-sweep index and the round from a device clock.  On one B200 this is as fast as the persistent launch
+    // below at 32 replicas of 1024 x 1024 (23749 against 23650 PT sweeps/s) and faster at 64 (14817 against 12732), and it
+    // works across ranks (profiles/r02_call34_pt_graph.log); MCX_PT_PERSIST=1 still prefers the persistent launch.
+    if (knobs().pt_persist <= 0) {
+        const bool was_tracking = lat->track_sums;
+        lat->track_sums = sweeps_per_round < 3;
+        const int64_t done = pt_run_graph(pt, nrounds, sweeps_per_round);
+        if (done < 0) return fail(MCX_ERR_CUDA, "replaying the rounds from a CUDA graph failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (done > 0) pt->last_path = 2; else lat->track_sums = was_tracking;
+        nrounds -= done;
+        if (nrounds == 0) return check_launch(lat->ctx);
+    }
     // all rounds in ONE persistent launch (k_persist.cu): sweeps, energies to every rank, exchange, labels -- the
     // host queues nothing between rounds
     if (launch_pt_rounds_persistent(pt, nrounds, sweeps_per_round)) {
-        pt->last_path = 1;
+        if (pt->last_path == 0) pt->last_path = 1;
         return check_launch(lat->ctx);
     }
-    pt->last_path = 0;
     // exchanging every sweep or two: keep the energy sums current per flip; longer intervals: recompute on publish
     lat->track_sums = sweeps_per_round < 3;
     for (int64_t r = 0; r < nrounds; ++r) {

@@ -147,6 +147,14 @@ __device__ __forceinline__ const uint8_t *plane_ptr_of(const uint8_t *planes, co
     return planes + ((int64_t)chain * 2 + colour) * L.plane_stride;
 }
 
+// Device-side clock of a parallel-tempering handle: what changes from round to round.  The kernels of a round captured into a
+// CUDA graph (mcx_pt_run) read it instead of taking the half-sweep index and the round as launch arguments, so one
+// instantiated graph serves every round; the last node of a round advances it.
+struct PtClock {
+    unsigned long long t_base;   // half-sweep index of the round's first half-sweep
+    unsigned long long round;    // exchange round
+};
+
 // per-chain accumulator block
 enum { SUM_PAIR = 0, SUM_SPIN = 1, SUM_SPIN2 = 2, SUM_ACC = 3, SUM_FIELDS = 4 };
 

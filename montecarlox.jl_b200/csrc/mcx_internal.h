@@ -69,7 +69,7 @@ struct mcx_pt {
     int n, first_slot;
     void *d_dev;                // k_persist.cu: device copy of the ladder view the persistent rounds read
     int persist_R;              // tallest strip the in-kernel rounds last ran with (reported by mcx_pt_run_info)
-    int last_path;              // 0: host-queued rounds, 1: one persistent launch (k_persist.cu)
+    int last_path;              // 0: host-queued rounds, 1: one persistent launch (k_persist.cu), 2: rounds replayed from a CUDA graph
     double *d_betas;            // [n] ladder
     double *d_x;                // [n] per-slot energies
     int32_t *d_index;           // [n] 0-based ladder index held by slot
@@ -87,6 +87,13 @@ struct mcx_pt {
     unsigned long long **d_peer_arrived;   // [nranks] every rank's d_arrived
     int *d_err;
     void *ipc_opened[2 * 64];
+    // rounds replayed from a CUDA graph (mcx_pt_run with short intervals): the clock the captured kernels read, the
+    // instantiated graph of graph_rounds rounds and what it was captured for
+    mcx::PtClock *d_clock;
+    cudaGraphExec_t graph_exec;
+    int graph_rounds;
+    uint64_t graph_launches;    // kernel launches one replay stands for
+    struct GraphKey { uint64_t seed; uint32_t first_chain; int rule, S, n, nchains, peers; const void *thi, *labels, *sums, *planes, *x; } graph_key;
 };
 constexpr int kMaxPtRanks = 64;
 
@@ -114,6 +121,7 @@ struct Knobs {
     int queue_rows;   // MCX_QUEUE_ROWS: strip height of the ticket-queue kernel (tuning hook)
     int queue;        // MCX_QUEUE: 1 = series of sweeps through the ticket-queue kernel (k_queue.cu)
     int queue_grid;   // MCX_QUEUE_GRID: CTAs of the persistent rounds kernel (tuning hook; default: every resident slot)
+    int pt_graph;     // MCX_PT_GRAPH: 0 = mcx_pt_run never replays its rounds from a CUDA graph
     int pt_persist;   // MCX_PT_PERSIST: 1 = mcx_pt_run as one persistent launch whenever the shape allows, 0 = never
     int flat_window;  // MCX_FLAT_WINDOW: 0 = flat-histogram chains read the log-weight table from global memory (no shared-memory window)
     int band_rows;    // MCX_BAND_ROWS: strip height of the row-band launches (tuning hook; default 16)
@@ -192,8 +200,11 @@ const char *async_error_text(int code);
 bool launch_sweep_rows8(mcx_lattice *lat, int colour, uint64_t t);     // false: shape not supported
 
 // k_pt.cu
-void launch_pt_publish(mcx_pt *pt);
-void launch_pt_exchange(mcx_pt *pt);
+void launch_pt_publish(mcx_pt *pt, const mcx::PtClock *clock = nullptr);     // clock: round read on the device (graph replay)
+void launch_pt_exchange(mcx_pt *pt, const mcx::PtClock *clock = nullptr);
+void launch_pt_clock_set(mcx_pt *pt);                      // clock <- the host's sweep index and round
+void launch_pt_clock_advance(mcx_pt *pt, int64_t sweeps);  // last node of a captured round
+extern thread_local const unsigned long long *g_t_clock;   // k_ising2d launches add *g_t_clock to their half-sweep index
 
 // k_flat.cu
 void launch_flat_load(mcx_flat *f);      // planes -> interleaved + state

@@ -56,7 +56,7 @@ def main():
             import ctypes as C
             path, strip = C.c_int32(-1), C.c_int32(0)
             m.lib().mcx_pt_run_info(pt._pt, C.byref(path), C.byref(strip))
-            print(json.dumps({"path": "persistent launch, %d-row strips" % strip.value if path.value == 1 else "host-queued rounds","replicas_on_rank": count, "L": args.L, "every": args.every,
+            print(json.dumps({"path": "persistent launch, %d-row strips" % strip.value if path.value == 1 else "graph replay" if path.value == 2 else "host-queued rounds","replicas_on_rank": count, "L": args.L, "every": args.every,
                               "rank_sweeps_per_s": sweeps / (ms * 1e-3), "us_per_sweep": ms * 1e3 / sweeps, "host_enqueue_us_per_sweep": round(host_us, 2),
                               "attempts_per_ns": sweeps * count * args.L * args.L / (ms * 1e6),
                               "rows_per_strip": os.environ.get("MCX_ROWS_PER_STRIP", "auto")}), flush=True)

@@ -117,6 +117,21 @@ def test_persistent_rounds_match_oracle(m, oracle, monkeypatch):
         assert p.value == 1
 
 
+@pytest.mark.parametrize("calls", [[(40, 1)], [(20, 2), (17, 1)], [(33, 1), (5, 1), (16, 2)]])
+def test_graph_replayed_rounds_equal_host_queued_rounds(m, calls, monkeypatch):
+    """short-interval rounds replayed from a CUDA graph (kernels read the half-sweep index and the round from a device
+    clock) against the same rounds queued launch by launch"""
+    monkeypatch.setenv("MCX_PT_PERSIST", "0")
+    monkeypatch.setenv("MCX_PT_GRAPH", "0")
+    ref, ref_spins, ref_paths = _run(m, [1024, 1024], 5, 123, calls)
+    assert all(p == 0 for p, _ in ref_paths)
+    monkeypatch.delenv("MCX_PT_GRAPH")
+    got, got_spins, paths = _run(m, [1024, 1024], 5, 123, calls)
+    assert any(p == 2 for p, _ in paths), paths
+    assert got == ref
+    assert np.array_equal(got_spins, ref_spins)
+
+
 def test_persistent_then_manual_rounds(m, monkeypatch):
     """a persistent run followed by explicit sweep_ / update_ rounds (and the other way round) continues the same ladder"""
     L, n, seed = 64, 6, 3
