@@ -578,6 +578,78 @@ bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps)
     return true;
 }
 
+__global__ void k_tclock_set(unsigned long long *clock, unsigned long long v) { *clock = v; }
+__global__ void k_tclock_add(unsigned long long *clock, unsigned long long dv) { *clock += dv; }
+
+// A long series of sweeps of one big lattice costs the host 64 - 128 stream operations per sweep (launches, event records and
+// waits of the row bands) -- as long as a sweep takes on the device, and worse when eight ranks share a host.  The band
+// launches of 32 sweeps are therefore captured once into a CUDA graph whose kernels add a device clock to their
+// half-sweep index (the last node advances it), and a series is that graph replayed.  Same launches, same trajectories.
+int64_t launch_sweeps_ising2d_banded_graph(mcx_lattice *lat, int64_t nsweeps)
+{
+    // sweeps per replay: a replay ends with all bands joined, which costs the overlap of one half-sweep's tail -- 3 % of the
+    // rate at 4 sweeps per replay (1650 against 1704 attempts/ns at L = 16384), < 0.5 % at 32; MCX_SWEEP_GRAPH=n sets it
+    const Knobs &k = knobs();
+    const int kSweeps = k.sweep_graph > 1 ? (k.sweep_graph > 256 ? 256 : k.sweep_graph) : 32;
+    if (k.sweep_graph == 0 || nsweeps < 2 * kSweeps + 1) return 0;
+    if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->nchains != 1) return 0;
+    if (k.variant >= 0 || k.rows_per_strip >= 0 || k.force_generic > 0 || k.bands == 0 || k.bands == 1) return 0;
+    mcx_ctx *ctx = lat->ctx;
+    if (!lat->d_tclock && cudaMalloc((void **)&lat->d_tclock, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        lat->d_tclock = nullptr;
+        return 0;
+    }
+    mcx_lattice::SweepGraphKey key;                             // what the captured launch arguments depend on
+    memset(&key, 0, sizeof(key));
+    key.seed = lat->seed; key.first_chain = lat->first_chain; key.rule = lat->rule; key.track = lat->track_sums ? 1 : 0;
+    key.bands = k.bands; key.band_rows = k.band_rows * 1024 + kSweeps;
+    key.planes = lat->view.planes; key.thi = lat->d_thi; key.labels = lat->d_labels; key.sums = lat->d_sums;
+    if (lat->sweep_graph && memcmp(&key, &lat->sweep_graph_key, sizeof(key)) != 0) {
+        cudaGraphExecDestroy(lat->sweep_graph);
+        lat->sweep_graph = nullptr;
+    }
+    int64_t done = 0;
+    if (!lat->sweep_graph) {
+        // one sweep launch by launch first: the auxiliary streams and events exist before the capture
+        if (!launch_sweeps_ising2d_banded(lat, 1)) return 0;
+        lat->sweep += 1;                                       // (the caller adds what this function returns)
+        done = 1; nsweeps -= 1;
+        const uint64_t launches0 = ctx->launches, sweep0 = lat->sweep;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); lat->sweep -= 1; return done; }
+        lat->sweep = 0;                                        // launch arguments relative to the clock
+        g_t_clock = lat->d_tclock;
+        const bool ok = launch_sweeps_ising2d_banded(lat, kSweeps);
+        g_t_clock = nullptr;
+        lat->sweep = sweep0;
+        if (ok) k_tclock_add<<<1, 1, 0, ctx->stream>>>(lat->d_tclock, 2ull * kSweeps);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        lat->sweep_graph_launches = ctx->launches - launches0 + 1;
+        ctx->launches = launches0;
+        lat->sweep -= 1;                                       // undo the local bookkeeping of the warm-up sweep: the caller adds `done`
+        if (!ok || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return done;
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&lat->sweep_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { cudaGetLastError(); lat->sweep_graph = nullptr; return done; }
+        lat->sweep_graph_key = key;
+        lat->sweep_graph_K = kSweeps;
+    }
+    const int64_t replays = nsweeps / lat->sweep_graph_K;
+    if (replays < 1) return done;
+    k_tclock_set<<<1, 1, 0, ctx->stream>>>(lat->d_tclock, 2 * (lat->sweep + (uint64_t)done));
+    ctx->launches++;
+    for (int64_t g = 0; g < replays; ++g) {
+        if (cudaGraphLaunch(lat->sweep_graph, ctx->stream) != cudaSuccess) { cudaGetLastError(); return done + g * lat->sweep_graph_K; }
+        ctx->launches += lat->sweep_graph_launches;
+    }
+    return done + replays * lat->sweep_graph_K;
+}
+
 bool launch_sweep_ising2d(mcx_lattice *lat, int colour, uint64_t t)
 {
     if (!lat->fast2d || lat->model != MCX_ISING) return false;

@@ -62,7 +62,7 @@ void knobs_refresh()
     k.ising3d = knob("MCX_ISING3D"); k.resident = knob("MCX_RESIDENT"); k.resident_cluster = knob("MCX_RESIDENT_CLUSTER");
     k.resident_rows = knob("MCX_RESIDENT_ROWS"); k.resident_threads = knob("MCX_RESIDENT_THREADS");
     k.force_generic = knob("MCX_FORCE_GENERIC"); k.wl_spec = knob("MCX_WL_SPEC"); k.band_rows = knob("MCX_BAND_ROWS"); k.queue = knob("MCX_QUEUE"); k.queue_rows = knob("MCX_QUEUE_ROWS");
-    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST"); k.pt_graph = knob("MCX_PT_GRAPH"); k.flat_window = knob("MCX_FLAT_WINDOW");
+    k.queue_grid = knob("MCX_QUEUE_GRID"); k.pt_persist = knob("MCX_PT_PERSIST"); k.pt_graph = knob("MCX_PT_GRAPH"); k.sweep_graph = knob("MCX_SWEEP_GRAPH"); k.flat_window = knob("MCX_FLAT_WINDOW");
     g_knobs_ready = true;
 }
 const Knobs &knobs()
@@ -239,6 +239,8 @@ static void lattice_free(mcx_lattice *lat)
     cudaFree(lat->d_staging);
     cudaFree(lat->d_hostbits);
     cudaFree(lat->d_queue);
+    if (lat->sweep_graph) cudaGraphExecDestroy(lat->sweep_graph);
+    cudaFree(lat->d_tclock);
     cudaFree(lat->d_series);
     cudaFree(lat->d_tau);
     if (lat->copy_stream) {
@@ -641,6 +643,16 @@ int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps)
                 if (!lat->track_sums) lat->sums_dirty = true;
                 s = nsweeps;
                 continue;
+            }
+            // one big lattice, a long series: the row-band launches of four sweeps replayed from a CUDA graph (device clock)
+            if (lat->nchains == 1) {
+                const int64_t gdone = launch_sweeps_ising2d_banded_graph(lat, nsweeps - s);
+                if (gdone > 0) {
+                    if (!lat->track_sums) lat->sums_dirty = true;
+                    lat->sweep += (uint64_t)gdone;
+                    s += gdone;
+                    continue;
+                }
             }
             // chain groups (batches) or row bands (one big lattice) on auxiliary streams overlap each other's launch tails
             if (lat->nchains > 1 ? launch_sweeps_ising2d_grouped(lat, nsweeps - s) : launch_sweeps_ising2d_banded(lat, nsweeps - s)) {

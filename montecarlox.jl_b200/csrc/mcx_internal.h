@@ -51,6 +51,13 @@ struct mcx_lattice {
     cudaStream_t copy_stream;
     cudaEvent_t ev_copied, ev_packed;   // copy finished; last conversion out of d_staging finished
     bool upload_pending, packed_recorded;
+    // series of sweeps of one big lattice replayed from a CUDA graph (launch_sweeps_ising2d_banded_graph): the device clock
+    // its kernels read, the instantiated graph of sweep_graph_K sweeps and what it was captured for
+    unsigned long long *d_tclock;
+    cudaGraphExec_t sweep_graph;
+    int sweep_graph_K;
+    uint64_t sweep_graph_launches;
+    struct SweepGraphKey { uint64_t seed; uint32_t first_chain; int rule, track, bands, band_rows; const void *planes, *thi, *labels, *sums; } sweep_graph_key;
     void *d_queue;              // k_queue.cu / k_persist.cu: control words (ticket counter, ...) and per-item progress words
     size_t queue_bytes;
     long long *d_series;        // mcx_sweep_series: snapshots of the sums, grown on demand
@@ -121,6 +128,7 @@ struct Knobs {
     int queue_rows;   // MCX_QUEUE_ROWS: strip height of the ticket-queue kernel (tuning hook)
     int queue;        // MCX_QUEUE: 1 = series of sweeps through the ticket-queue kernel (k_queue.cu)
     int queue_grid;   // MCX_QUEUE_GRID: CTAs of the persistent rounds kernel (tuning hook; default: every resident slot)
+    int sweep_graph;  // MCX_SWEEP_GRAPH: 0 = series of row-band sweeps are never replayed from a CUDA graph; n > 1: n sweeps per replay (default 32)
     int pt_graph;     // MCX_PT_GRAPH: 0 = mcx_pt_run never replays its rounds from a CUDA graph
     int pt_persist;   // MCX_PT_PERSIST: 1 = mcx_pt_run as one persistent launch whenever the shape allows, 0 = never
     int flat_window;  // MCX_FLAT_WINDOW: 0 = flat-histogram chains read the log-weight table from global memory (no shared-memory window)
@@ -156,6 +164,7 @@ bool launch_sweeps_ising2d_grouped(mcx_lattice *lat, int64_t nsweeps);
 // nsweeps sweeps of one big lattice with its rows dealt into bands on auxiliary streams; a band's half-sweep
 // waits (events) only for its own and its two neighbour bands' previous half-sweep; false: not applicable
 bool launch_sweeps_ising2d_banded(mcx_lattice *lat, int64_t nsweeps);
+int64_t launch_sweeps_ising2d_banded_graph(mcx_lattice *lat, int64_t nsweeps);   // sweeps done by graph replays (0: not applicable)
 // k_bc2d.cu: vectorised 2-D Blume-Capel half-sweep (Metropolis / Glauber, Lx % 32 == 0)
 bool launch_sweep_bc2d(mcx_lattice *lat, int colour, uint64_t t);       // false: not applicable, nothing launched
 

@@ -85,6 +85,36 @@ def test_fast_kernel_equals_generic_kernel(m, L):
         assert np.array_equal(o[0], outs[0][0]) and o[1:] == outs[0][1:]
 
 
+@pytest.mark.parametrize("rule,track", [(0, False), (0, True), (2, False), (1, True)])
+def test_graph_replayed_sweep_series_equals_launches(m, rule, track):
+    """a long series of row-band sweeps replayed from a CUDA graph (kernels add a device clock to their half-sweep index)
+    gives the trajectory of the same launches queued one by one, over several calls"""
+    keys = ("MCX_BANDS", "MCX_SWEEP_GRAPH", "MCX_RESIDENT")
+
+    def run(env):
+        for k in keys:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        s = m.Ising([1024, 1024])
+        s.set_tracking(track)
+        alg = _make_alg(m, rule, BETA_C, 5, 0)
+        s.init_("random", rng=alg.rng)
+        l0 = s.ctx.launch_count()
+        for n in (30, 3, 17):
+            m.sweep_(s, alg, n)
+        out = (s.spins.copy(), np.array(s.pair_sum()), np.array(s.magnetization()), np.array(s.accepted()), s.energy(full=True))
+        return out, s.ctx.launch_count() - l0
+
+    try:
+        ref, l_ref = run({"MCX_BANDS": "4", "MCX_SWEEP_GRAPH": "0", "MCX_RESIDENT": "0"})
+        got, l_got = run({"MCX_BANDS": "4", "MCX_SWEEP_GRAPH": "4", "MCX_RESIDENT": "0"})      # 4 sweeps per replay (default 32)
+        assert l_got != l_ref, "the graph replay was not taken"
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+    finally:
+        for k in keys:
+            os.environ.pop(k, None)
+
+
 @pytest.mark.parametrize("dims,nchains,envs", [
     ([1024, 1024], 1, [{"MCX_BANDS": "2"}, {"MCX_BANDS": "4"}, {"MCX_BANDS": "8"}]),
     ([2048, 512], 1, [{"MCX_BANDS": "4"}]),
