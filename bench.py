@@ -493,7 +493,7 @@ def bench_plain(m, ctx, stream, L, S, rule, rank, storage, track, barrier, max_o
     alg = (m.Metropolis, m.Glauber, m.HeatBath)[rule](rng, beta=BETA_C)
     s._bind_alg(alg)
     s.init_("random", rng=rng)
-    check(lib().mcx_sweep(s.h_lat, 10))
+    check(lib().mcx_sweep(s.h_lat, S))        # warm-up with the timed call's own length (a long series builds its CUDA graph once)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
