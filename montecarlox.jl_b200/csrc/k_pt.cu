@@ -111,6 +111,79 @@ __global__ void k_pt_publish_peers(const long long *__restrict__ sums, double *c
     }
 }
 
+// The tail of a graph-replayed round in ONE launch of one block: publish (k_pt_publish / k_pt_publish_peers), the wait for
+// the other ranks, the exchange (k_pt_exchange) and the clock advance -- three dependent launches fewer per round, which at
+// an exchange after every sweep is a sixth of the round.  Same expressions, same order per pair as the separate kernels.
+__global__ void __launch_bounds__(256)
+k_pt_round_tail(const long long *__restrict__ sums, double *const *__restrict__ peer_x, unsigned long long *const *__restrict__ peer_arrived,
+                const unsigned long long *arrived, int nranks, int rank, int nlocal, int first_slot, double J, double h, double D,
+                int model, PtClock *clock, int n, int stage_par, const double *__restrict__ betas, double *x_base,
+                int32_t *__restrict__ index, int32_t *__restrict__ slot_of, long long *__restrict__ steps,
+                long long *__restrict__ accepted, int32_t *__restrict__ labels, uint32_t seed_lo, uint32_t seed_hi, int *err,
+                int *ctx_err, unsigned long long dt)
+{
+    const unsigned long long round = *(const volatile unsigned long long *)&clock->round;
+    const bool peers = peer_x != nullptr;
+    const int offset = peers ? (int)(round & 1) * n : 0;
+    for (int c = threadIdx.x; c < nlocal; c += blockDim.x) {
+        const long long *s = sums + (int64_t)c * SUM_FIELDS;
+        double e = -(J * (double)s[SUM_PAIR]);
+        if (h != 0.0) e -= h * (double)s[SUM_SPIN];
+        if (model == MCX_BLUME_CAPEL) e += D * (double)s[SUM_SPIN2];
+        if (peers) { for (int r = 0; r < nranks; ++r) peer_x[r][offset + first_slot + c] = e; }
+        else x_base[first_slot + c] = e;
+    }
+    if (peers) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < nranks) {
+            *(volatile unsigned long long *)(peer_arrived[threadIdx.x] + rank) = round + 1;
+            __threadfence_system();
+        }
+        if (threadIdx.x == 0) pt_wait_all(arrived, nranks, round + 1, err, ctx_err);
+    } else {
+        __threadfence();
+    }
+    __syncthreads();
+    const int stage = (int)((round + (unsigned long long)stage_par) & 1);
+    const double *x = x_base + offset;
+    for (int k = (stage & 1) + 2 * (int)threadIdx.x; k < n - 1; k += 2 * (int)blockDim.x) {
+        const int ri = slot_of[k], rj = slot_of[k + 1];
+        steps[k] += 1;
+        const Philox4 p = stream_block(seed_lo, seed_hi, (uint32_t)ri, TAG_EXCHANGE, round, 0, 0);
+        const uint64_t w = ((uint64_t)p.y << 32) | p.x;
+        const double u = (double)(w >> 11) * (1.0 / 9007199254740992.0);
+        const double bi = betas[k], bj = betas[k + 1];
+        const double xi = ((const volatile double *)x)[ri], xj = ((const volatile double *)x)[rj];
+        const double lr = ((-bi * xj) - (-bi * xi)) + ((-bj * xi) - (-bj * xj));
+        const bool acc = (lr > 0) || (u < exp(lr));
+        if (acc) {
+            accepted[k] += 1;
+            index[ri] = k + 1; index[rj] = k;
+            slot_of[k] = rj; slot_of[k + 1] = ri;
+            if (ri >= first_slot && ri < first_slot + nlocal) labels[ri - first_slot] = k + 1;
+            if (rj >= first_slot && rj < first_slot + nlocal) labels[rj - first_slot] = k;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        clock->t_base += dt;
+        clock->round = round + 1;
+    }
+}
+
+void launch_pt_round_tail(mcx_pt *pt, int64_t sweeps)
+{
+    mcx_lattice *lat = pt->lat;
+    const int stage_par = (int)(((uint64_t)pt->stage + pt->round) & 1);
+    k_pt_round_tail<<<1, 256, 0, lat->ctx->stream>>>(lat->d_sums, pt->peers ? pt->d_peer_x : nullptr, pt->d_peer_arrived, pt->d_arrived,
+                                                   pt->nranks, pt->rank, lat->nchains, pt->first_slot, lat->J, lat->h, lat->D, lat->model,
+                                                   pt->d_clock, pt->n, stage_par, pt->d_betas, pt->d_x, pt->d_index, pt->d_slot_of,
+                                                   pt->d_steps, pt->d_accepted, lat->d_labels, (uint32_t)lat->seed,
+                                                   (uint32_t)(lat->seed >> 32), pt->d_err, lat->ctx->d_err, 2 * (unsigned long long)sweeps);
+    lat->ctx->launches++;
+}
+
 __global__ void k_pt_clock_set(PtClock *clock, unsigned long long t_base, unsigned long long round)
 {
     clock->t_base = t_base; clock->round = round;

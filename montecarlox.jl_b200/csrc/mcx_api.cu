@@ -1015,9 +1015,13 @@ static bool pt_enqueue_clocked_round(mcx_pt *pt, int64_t S)
     mcx::g_t_clock = nullptr;
     lat->sweep = sweep0;
     if (!ok) return false;
-    mcx::launch_pt_publish(pt, pt->d_clock);
-    mcx::launch_pt_exchange(pt, pt->d_clock);
-    mcx::launch_pt_clock_advance(pt, S);
+    if (mcx::knobs().pt_graph == 2) {                         // MCX_PT_GRAPH=2: the tail as three launches (A/B hook)
+        mcx::launch_pt_publish(pt, pt->d_clock);
+        mcx::launch_pt_exchange(pt, pt->d_clock);
+        mcx::launch_pt_clock_advance(pt, S);
+    } else {
+        mcx::launch_pt_round_tail(pt, S);
+    }
     return true;
 }
 

@@ -213,6 +213,7 @@ void launch_pt_publish(mcx_pt *pt, const mcx::PtClock *clock = nullptr);     // 
 void launch_pt_exchange(mcx_pt *pt, const mcx::PtClock *clock = nullptr);
 void launch_pt_clock_set(mcx_pt *pt);                      // clock <- the host's sweep index and round
 void launch_pt_clock_advance(mcx_pt *pt, int64_t sweeps);  // last node of a captured round
+void launch_pt_round_tail(mcx_pt *pt, int64_t sweeps);     // publish + wait + exchange + clock advance of a captured round in one launch
 extern thread_local const unsigned long long *g_t_clock;   // k_ising2d launches add *g_t_clock to their half-sweep index
 
 // k_flat.cu
