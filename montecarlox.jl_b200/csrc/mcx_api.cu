@@ -1032,8 +1032,8 @@ static int64_t pt_run_graph(mcx_pt *pt, int64_t nrounds, int64_t S)
     using namespace mcx;
     mcx_lattice *lat = pt->lat;
     mcx_ctx *ctx = lat->ctx;
-    constexpr int kGraphRounds = 8;                            // rounds per replay
     const Knobs &k = knobs();
+    const int kGraphRounds = k.pt_graph > 2 ? (k.pt_graph > 256 ? 256 : k.pt_graph) : 8;   // rounds per replay (MCX_PT_GRAPH=n > 2 sets it)
     if (k.pt_graph == 0 || S >= 3 || nrounds < 2 * kGraphRounds) return 0;
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->N < (1 << 20)) return 0;
     if (k.variant >= 0 || k.rows_per_strip >= 0 || k.force_generic > 0 || k.queue > 0 || k.resident > 0) return 0;
@@ -1041,7 +1041,7 @@ static int64_t pt_run_graph(mcx_pt *pt, int64_t nrounds, int64_t S)
     if (lat->sums_dirty) { launch_recompute(lat); lat->sums_dirty = false; }
     mcx_pt::GraphKey key;                                       // what the captured launch arguments depend on
     memset(&key, 0, sizeof(key));
-    key.seed = lat->seed; key.first_chain = lat->first_chain; key.rule = lat->rule; key.S = (int)S; key.n = pt->n;
+    key.seed = lat->seed; key.first_chain = lat->first_chain; key.rule = lat->rule; key.S = (int)S + 1024 * kGraphRounds + (k.groups == 0 ? 1 << 20 : 0); key.n = pt->n;
     key.nchains = lat->nchains; key.peers = pt->peers ? 1 : 0;
     key.thi = lat->d_thi; key.labels = lat->d_labels; key.sums = lat->d_sums; key.planes = lat->view.planes; key.x = pt->d_x;
     if (pt->graph_exec && memcmp(&key, &pt->graph_key, sizeof(key)) != 0) {
