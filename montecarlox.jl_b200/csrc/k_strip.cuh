@@ -125,7 +125,11 @@ __device__ __forceinline__ Acc sweep_strip(uint8_t *tgt, const uint8_t *__restri
     const int pf_k = threadIdx.x & 3;
     const uint8_t *ppf = (pf_k < 2 ? oth : (const uint8_t *)tgt) + (size_t)(row0 + (pf_k == 1 ? 4 : pf_k == 2 ? 2 : 3)) * h + (col - 16 * pf_k);
 
-#pragma unroll 1
+    // two trips per loop iteration in the streaming kernel: the window hand-over (U = D, C = E) becomes renaming and the round
+    // keys are formed once per two trips (398 against 411 instructions per trip, +1.1 % at L = 16384); the series kernels at
+    // 5 CTAs/SM lose 3 % with it (profiles/r02_call44_unroll2.log)
+    constexpr int kTripsPerIteration = L2ONLY ? 1 : 2;
+#pragma unroll (kTripsPerIteration)
     for (int r = 0; r < R; r += 2) {
         // this trip's rows, loads first: their latency is covered by the Philox rounds below
         const uint8_t *pe = po + h2;
