@@ -1042,7 +1042,9 @@ static int64_t pt_run_graph(mcx_pt *pt, int64_t nrounds, int64_t S)
     mcx_pt::GraphKey key;                                       // what the captured launch arguments depend on
     memset(&key, 0, sizeof(key));
     key.seed = lat->seed; key.first_chain = lat->first_chain; key.rule = lat->rule; key.S = (int)S + 1024 * kGraphRounds + (k.groups == 0 ? 1 << 20 : 0); key.n = pt->n;
-    key.nchains = lat->nchains; key.peers = pt->peers ? 1 : 0;
+    key.nchains = lat->nchains;
+    // the captured tail holds the parity of stage - round, which exchanges keep but mcx_pt_set_state / mcx_pt_reset may change
+    key.peers = (pt->peers ? 1 : 0) | (int)((((uint64_t)pt->stage + pt->round) & 1) << 1);
     key.thi = lat->d_thi; key.labels = lat->d_labels; key.sums = lat->d_sums; key.planes = lat->view.planes; key.x = pt->d_x;
     if (pt->graph_exec && memcmp(&key, &pt->graph_key, sizeof(key)) != 0) {
         cudaGraphExecDestroy(pt->graph_exec);
