@@ -591,7 +591,7 @@ int64_t launch_sweeps_ising2d_banded_graph(mcx_lattice *lat, int64_t nsweeps)
     // rate at 4 sweeps per replay (1650 against 1704 attempts/ns at L = 16384), < 0.5 % at 32; MCX_SWEEP_GRAPH=n sets it
     const Knobs &k = knobs();
     const int kSweeps = k.sweep_graph > 1 ? (k.sweep_graph > 256 ? 256 : k.sweep_graph) : 32;
-    if (k.sweep_graph == 0 || nsweeps < 2 * kSweeps + 1) return 0;
+    if (k.sweep_graph == 0 || nsweeps < 2 * kSweeps + 1 || lat->sweep_graph_K < 0) return 0;   // < 0: this context's stream cannot be captured
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->nchains != 1) return 0;
     if (k.variant >= 0 || k.rows_per_strip >= 0 || k.force_generic > 0 || k.bands == 0 || k.bands == 1) return 0;
     mcx_ctx *ctx = lat->ctx;
@@ -616,7 +616,12 @@ int64_t launch_sweeps_ising2d_banded_graph(mcx_lattice *lat, int64_t nsweeps)
         lat->sweep += 1;                                       // (the caller adds what this function returns)
         done = 1; nsweeps -= 1;
         const uint64_t launches0 = ctx->launches, sweep0 = lat->sweep;
-        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); lat->sweep -= 1; return done; }
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            lat->sweep_graph_K = -1;                           // e.g. the legacy default stream: do not try again on this handle
+            lat->sweep -= 1;
+            return done;
+        }
         lat->sweep = 0;                                        // launch arguments relative to the clock
         g_t_clock = lat->d_tclock;
         const bool ok = launch_sweeps_ising2d_banded(lat, kSweeps);

@@ -1034,7 +1034,7 @@ static int64_t pt_run_graph(mcx_pt *pt, int64_t nrounds, int64_t S)
     mcx_ctx *ctx = lat->ctx;
     const Knobs &k = knobs();
     const int kGraphRounds = k.pt_graph > 2 ? (k.pt_graph > 256 ? 256 : k.pt_graph) : 8;   // rounds per replay (MCX_PT_GRAPH=n > 2 sets it)
-    if (k.pt_graph == 0 || S >= 3 || nrounds < 2 * kGraphRounds) return 0;
+    if (k.pt_graph == 0 || S >= 3 || nrounds < 2 * kGraphRounds || pt->graph_rounds < 0) return 0;   // < 0: the stream cannot be captured
     if (!lat->fast2d || lat->model != MCX_ISING || lat->storage != MCX_STORAGE_INT8 || lat->slab || lat->N < (1 << 20)) return 0;
     if (k.variant >= 0 || k.rows_per_strip >= 0 || k.force_generic > 0 || k.queue > 0 || k.resident > 0) return 0;
     if (!pt->d_clock && cudaMalloc((void **)&pt->d_clock, sizeof(PtClock)) != cudaSuccess) { cudaGetLastError(); pt->d_clock = nullptr; return 0; }
@@ -1056,7 +1056,11 @@ static int64_t pt_run_graph(mcx_pt *pt, int64_t nrounds, int64_t S)
         if (st0 != MCX_OK || mcx_pt_publish(pt) != MCX_OK || mcx_pt_exchange(pt) != MCX_OK) return -1;
         nrounds -= 1;
         const uint64_t launches0 = ctx->launches;
-        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return 1; }
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+            cudaGetLastError();
+            pt->graph_rounds = -1;                             // do not try again on this handle
+            return 1;
+        }
         bool ok = true;
         for (int r = 0; r < kGraphRounds && ok; ++r) ok = pt_enqueue_clocked_round(pt, S);
         cudaGraph_t graph = nullptr;
