@@ -83,10 +83,6 @@ __device__ __forceinline__ int32_t ld_cg32(const int32_t *p)
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_cg128(uint8_t *p, const uint4 v)
-{
-    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 {
     uint32_t v;
@@ -98,12 +94,6 @@ __device__ __forceinline__ unsigned long long ld_acquire64(const unsigned long l
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-// publish: every earlier write of the calling thread -- and, after a __syncwarp(), of its warp -- is visible at GPU
-// scope before the word is (fence.acq_rel + store; __threadfence() would be the heavier fence.sc)
-__device__ __forceinline__ void st_release(uint32_t *p, const uint32_t v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long now_ns()
 {
