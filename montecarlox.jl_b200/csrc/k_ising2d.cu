@@ -609,20 +609,19 @@ int64_t launch_sweeps_ising2d_banded_graph(mcx_lattice *lat, int64_t nsweeps)
         cudaGraphExecDestroy(lat->sweep_graph);
         lat->sweep_graph = nullptr;
     }
+    // `done` sweeps have been queued by this call; lat->sweep itself is advanced by the caller with the return value
     int64_t done = 0;
     if (!lat->sweep_graph) {
         // one sweep launch by launch first: the auxiliary streams and events exist before the capture
         if (!launch_sweeps_ising2d_banded(lat, 1)) return 0;
-        lat->sweep += 1;                                       // (the caller adds what this function returns)
         done = 1; nsweeps -= 1;
         const uint64_t launches0 = ctx->launches, sweep0 = lat->sweep;
         if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
             cudaGetLastError();
             lat->sweep_graph_K = -1;                           // e.g. the legacy default stream: do not try again on this handle
-            lat->sweep -= 1;
             return done;
         }
-        lat->sweep = 0;                                        // launch arguments relative to the clock
+        lat->sweep = 0;                                        // captured launch arguments are relative to the clock
         g_t_clock = lat->d_tclock;
         const bool ok = launch_sweeps_ising2d_banded(lat, kSweeps);
         g_t_clock = nullptr;
@@ -631,8 +630,7 @@ int64_t launch_sweeps_ising2d_banded_graph(mcx_lattice *lat, int64_t nsweeps)
         cudaGraph_t graph = nullptr;
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         lat->sweep_graph_launches = ctx->launches - launches0 + 1;
-        ctx->launches = launches0;
-        lat->sweep -= 1;                                       // undo the local bookkeeping of the warm-up sweep: the caller adds `done`
+        ctx->launches = launches0;                             // captured, not executed
         if (!ok || e != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
