@@ -151,7 +151,10 @@ int32_t mcx_get_rng(mcx_lattice *lat, uint64_t *seed, uint64_t *next_sweep);
 
 /* sweep!(sys, alg, nsweeps): nsweeps x (colour 0 half-sweep, colour 1 half-sweep) on every chain.
  * One attempt per site per sweep = the reference's `for _ in 1:N; spin_flip!(sys, alg); end`
- * (docs/src/examples/spin_systems/pt_Ising2D.jl:52-57) in checkerboard order.  Asynchronous. */
+ * (docs/src/examples/spin_systems/pt_Ising2D.jl:52-57) in checkerboard order.  Asynchronous.
+ * How the sweeps are launched (row bands, chain groups, one resident / ticket-queue launch for a whole series, a CUDA graph
+ * of 32 sweeps replayed for series of >= 65 sweeps of one big lattice) never changes the trajectory; the first long series
+ * of a handle pays the one-off capture of its graph (MCX_SWEEP_GRAPH=0 switches the replay off). */
 int32_t mcx_sweep(mcx_lattice *lat, int64_t nsweeps);
 
 /* measure!(measurements, sys, i) with an interval schedule (src/measurements/measurements.jl:192-200)
